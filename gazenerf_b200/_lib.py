@@ -1,0 +1,129 @@
+"""Build + load libgnrf.so (the C-ABI shared library declared in include/gnrf.h) and bind it with ctypes.
+
+The library is compiled in-tree with nvcc for sm_100a only.  There is NO fallback: if the library is missing or
+the device is not a B200, every entry point raises (the product path must fail loudly, never route to a CPU
+or eager-PyTorch implementation).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+from typing import List, Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+CSRC = os.path.join(_HERE, "csrc")
+INCLUDE = os.path.join(_ROOT, "include")
+LIB_PATH = os.path.join(_HERE, "libgnrf.so")
+
+SOURCES = ["abi.cu", "geometry.cu", "mlp_simt.cu", "mlp_tc.cu", "compose.cu", "neural_render.cu"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "--shared", "-Xcompiler", "-fPIC",
+    "-Xptxas", "-v",
+]
+
+SYMBOLS = [
+    "gnrf_abi_version", "gnrf_last_error", "gnrf_device_check",
+    "gnrf_ray_setup", "gnrf_coarse_depths", "gnrf_fine_depths",
+    "gnrf_mlp_simt_fwd", "gnrf_composite_fwd",
+    "gnrf_mlp_tc_packed_bytes", "gnrf_mlp_tc_bias_floats", "gnrf_mlp_tc_pack", "gnrf_mlp_tc_fold",
+    "gnrf_mlp_tc_workspace_bytes", "gnrf_mlp_tc_fwd",
+    "gnrf_compose_fwd", "gnrf_nr_workspace_bytes", "gnrf_neural_render_fwd",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; cannot build libgnrf.so")
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "gnrf.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into gazenerf_b200/libgnrf.so (nvcc cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-o", tmp] + srcs
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + proc.stdout)
+    os.replace(tmp, LIB_PATH)
+    log = os.path.join(_HERE, "build.log")
+    with open(log, "w") as f:
+        f.write(" ".join(cmd) + "\n" + proc.stdout)
+    if verbose:
+        print(proc.stdout)
+    return LIB_PATH
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load (building first if needed and possible) and return the bound library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if _stale():
+        try:
+            build()
+        except Exception as e:  # on a box without nvcc a prebuilt, possibly "stale by mtime" .so is still fine
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError("libgnrf.so is missing and cannot be built: %s" % e)
+    L = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    vp, i32, f32, sz = c.c_void_p, c.c_int, c.c_float, c.c_size_t
+    L.gnrf_abi_version.restype = i32
+    L.gnrf_last_error.restype = c.c_char_p
+    L.gnrf_device_check.restype = i32
+    L.gnrf_ray_setup.argtypes = [vp, vp, vp, i32, i32, vp, vp]
+    L.gnrf_coarse_depths.argtypes = [vp, vp, vp, i32, i32, i32, f32, f32, vp, vp]
+    L.gnrf_fine_depths.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]
+    L.gnrf_mlp_simt_fwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]
+    L.gnrf_composite_fwd.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]
+    L.gnrf_mlp_tc_packed_bytes.restype = sz
+    L.gnrf_mlp_tc_bias_floats.restype = sz
+    L.gnrf_mlp_tc_pack.argtypes = [vp, vp, vp]
+    L.gnrf_mlp_tc_fold.argtypes = [vp, vp, vp, i32, vp, vp]
+    L.gnrf_mlp_tc_workspace_bytes.restype = sz
+    L.gnrf_mlp_tc_workspace_bytes.argtypes = [i32, i32, i32]
+    L.gnrf_mlp_tc_fwd.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, sz, vp]
+    L.gnrf_compose_fwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]
+    L.gnrf_nr_workspace_bytes.restype = sz
+    L.gnrf_nr_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
+    L.gnrf_neural_render_fwd.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, sz, vp]
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is c.c_int and name not in ("gnrf_abi_version",):
+            fn.restype = i32
+    _lib = L
+    return L
+
+
+def check(code: int, what: str = "") -> None:
+    """Raise RuntimeError carrying gnrf_last_error() for a non-zero status (the reference's train loop catches
+    Exception per batch, trainer/gazenerf_trainer.py:576-582)."""
+    if code != 0:
+        msg = lib().gnrf_last_error().decode("utf-8", "replace")
+        raise RuntimeError("libgnrf %s failed (code %d): %s" % (what, code, msg))
+
+
+def ptr_array(ptrs: List[int]):
+    """Host array of device pointers (const float* const*)."""
+    arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+    return arr

@@ -1,0 +1,302 @@
+// 2-D neural renderer: 1x1-conv GEMMs with fused epilogues, pixel-shuffle, 3x3 binomial blur, RGB skip pyramid.
+// Reference: models/neural_renderer.py:98-113 (NeuralRenderer.forward),
+//            models/pixel_shuffle_upsample.py:7-42 (Blur -> kornia.filters.filter2d, PixelShuffleUpsample).
+#include "common.cuh"
+
+namespace gnrf {
+
+constexpr int BM = 64;    // output channels per CTA
+constexpr int BN = 128;   // pixels per CTA
+constexpr int BK = 8;
+constexpr int kGemmThreads = 256;
+
+enum Epilogue { EPI_LRELU = 0, EPI_PSU = 1 };
+
+__device__ __forceinline__ float lrelu(float v) { return v >= 0.0f ? v : 0.2f * v; }
+
+// out[n][co][p] = epi( sum_ci W[co][ci] * X[n][ci][p] + bias[co] ),  X: [N, K, HW] (NCHW, 1x1 conv == GEMM).
+// EPI_PSU: v = lrelu(.) + res[n][co % Cres][p], written pixel-shuffled (factor 2):
+//          out[n][co/4][2h + (co%4)/2][2w + (co%4)%2]   (pixel_shuffle_upsample.py:34-40)
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads)
+conv1x1_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ X, int M, int K, int HW,
+               int Wd, const float* __restrict__ res, int Cres, float* __restrict__ out) {
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int tid = threadIdx.x;
+  const int n = blockIdx.z;
+  const int co0 = blockIdx.y * BM;
+  const int p0 = blockIdx.x * BN;
+  const float* Xn = X + (size_t)n * K * HW;
+  const int ty = tid >> 4, tx = tid & 15;  // thread tile: 4 co x (4 + 4) px
+
+  // global->register staging
+  float a_st[2];
+  float4 b_st;
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      int idx = tid + i * kGemmThreads;  // 0..511
+      int m = idx >> 3, kk = idx & 7;
+      a_st[i] = (co0 + m < M && k0 + kk < K) ? __ldg(W + (size_t)(co0 + m) * K + k0 + kk) : 0.0f;
+    }
+    int kk = tid >> 5, c4 = tid & 31;
+    int px = p0 + c4 * 4;
+    b_st = (k0 + kk < K && px < HW) ? __ldg(reinterpret_cast<const float4*>(Xn + (size_t)(k0 + kk) * HW + px))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto commit = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      int idx = tid + i * kGemmThreads;
+      As[buf][idx & 7][idx >> 3] = a_st[i];
+    }
+    int kk = tid >> 5, c4 = tid & 31;
+    *reinterpret_cast<float4*>(&Bs[buf][kk][c4 * 4]) = b_st;
+  };
+
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+
+  const int n_k = (K + BK - 1) / BK;
+  fetch(0);
+  commit(0);
+  __syncthreads();
+  for (int kc = 0; kc < n_k; ++kc) {
+    const int buf = kc & 1;
+    if (kc + 1 < n_k) fetch((kc + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float4 a = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      float av[4] = {a.x, a.y, a.z, a.w};
+      float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kc + 1 < n_k) commit(buf ^ 1);
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int co = co0 + ty * 4 + i;
+    if (co >= M) continue;
+    float bv = __ldg(bias + co);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int px = p0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (px >= HW) continue;
+      float v = lrelu(acc[i][j] + bv);
+      if (EPI == EPI_LRELU) {
+        out[((size_t)n * M + co) * HW + px] = v;
+      } else {
+        v += __ldg(res + ((size_t)n * Cres + (co % Cres)) * HW + px);
+        int h = px / Wd, w = px - h * Wd;
+        int c = co >> 2, si = (co >> 1) & 1, sj = co & 1;
+        out[(((size_t)n * (M >> 2) + c) * (2 * (HW / Wd)) + (2 * h + si)) * (2 * Wd) + 2 * w + sj] = v;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ int reflect(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+
+// Depthwise [1,2,1]x[1,2,1]/16 with reflect border (pixel_shuffle_upsample.py:7-16). planes = N*C.
+__global__ void blur3x3_kernel(const float* __restrict__ in, int H, int Wd, long long total, float* __restrict__ out) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int x = (int)(idx % Wd);
+  int y = (int)((idx / Wd) % H);
+  const float* pl = in + (idx / ((long long)H * Wd)) * (long long)H * Wd;
+  int ym = reflect(y - 1, H), yp = reflect(y + 1, H), xm = reflect(x - 1, Wd), xp = reflect(x + 1, Wd);
+  float r0 = pl[(size_t)ym * Wd + xm] + 2.0f * pl[(size_t)ym * Wd + x] + pl[(size_t)ym * Wd + xp];
+  float r1 = pl[(size_t)y * Wd + xm] + 2.0f * pl[(size_t)y * Wd + x] + pl[(size_t)y * Wd + xp];
+  float r2 = pl[(size_t)yp * Wd + xm] + 2.0f * pl[(size_t)yp * Wd + x] + pl[(size_t)yp * Wd + xp];
+  out[idx] = (r0 + 2.0f * r1 + r2) * 0.0625f;
+}
+
+// rgb[n][j][p] = sum_c W[j][c] net[n][c][p] + b[j] (+ prev[n][j][p]); optional sigmoid (neural_renderer.py:100,106,110).
+__global__ void to_rgb_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ net, int C,
+                              int HW, const float* __restrict__ prev, int do_sigmoid, float* __restrict__ rgb) {
+  extern __shared__ float s_w[];  // [3][C]
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_w[i] = W[i];
+  __syncthreads();
+  int n = blockIdx.y;
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const float* x = net + (size_t)n * C * HW + p;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int c = 0; c < C; ++c) {
+    float v = x[(size_t)c * HW];
+    a0 = fmaf(s_w[c], v, a0);
+    a1 = fmaf(s_w[C + c], v, a1);
+    a2 = fmaf(s_w[2 * C + c], v, a2);
+  }
+  float r[3] = {a0 + bias[0], a1 + bias[1], a2 + bias[2]};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    size_t o = ((size_t)n * 3 + j) * HW + p;
+    float v = r[j];
+    if (prev != nullptr) v = prev[o] + v;
+    if (do_sigmoid) v = 1.0f / (1.0f + expf(-v));
+    rgb[o] = v;
+  }
+}
+
+// out = Blur(bilinear_up2(in)), in [planes,H,W] -> out [planes,2H,2W]  (neural_renderer.py:65-67).
+__device__ __forceinline__ float up2_at(const float* pl, int H, int Wd, int Y, int X) {
+  // bilinear, align_corners=False, scale 2: src = (dst + .5)/2 - .5, clamped at 0 (PyTorch semantics)
+  int y0 = (Y >> 1) - ((Y & 1) ? 0 : 1), x0 = (X >> 1) - ((X & 1) ? 0 : 1);
+  float wy1 = (Y & 1) ? 0.25f : 0.75f, wx1 = (X & 1) ? 0.25f : 0.75f;  // weight of the upper neighbour (y0+1, x0+1)
+  int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, Wd - 1);
+  if (y0 < 0) { y0 = 0; }
+  if (x0 < 0) { x0 = 0; }
+  float wy0 = 1.0f - wy1, wx0 = 1.0f - wx1;
+  float top = wx0 * pl[(size_t)y0 * Wd + x0] + wx1 * pl[(size_t)y0 * Wd + x1];
+  float bot = wx0 * pl[(size_t)y1 * Wd + x0] + wx1 * pl[(size_t)y1 * Wd + x1];
+  return wy0 * top + wy1 * bot;
+}
+
+__global__ void rgb_up_blur_kernel(const float* __restrict__ in, int H, int Wd, long long total, float* __restrict__ out) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int H2 = 2 * H, W2 = 2 * Wd;
+  int X = (int)(idx % W2);
+  int Y = (int)((idx / W2) % H2);
+  const float* pl = in + (idx / ((long long)H2 * W2)) * (long long)H * Wd;
+  const float k[3] = {1.0f, 2.0f, 1.0f};
+  float acc = 0.0f;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+    int yy = reflect(Y + dy, H2);
+    float row = 0.0f;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) row += k[dx + 1] * up2_at(pl, H, Wd, yy, reflect(X + dx, W2));
+    acc += k[dy + 1] * row;
+  }
+  out[idx] = acc * 0.0625f;
+}
+
+struct NrPlan {
+  size_t t1, sh, bl, net, rgb_a, rgb_b, total;  // byte offsets / total
+};
+
+static NrPlan nr_plan(int N, int C, int S, int n_blocks, int min_feat) {
+  size_t m_t1 = 0, m_sh = 0, m_net = 0;
+  for (int i = 0; i < n_blocks; ++i) {
+    size_t ci = (size_t)((C >> i) > min_feat ? (C >> i) : min_feat);
+    size_t co = (size_t)((C >> (i + 1)) > min_feat ? (C >> (i + 1)) : min_feat);
+    size_t s = (size_t)S << i;
+    m_t1 = max(m_t1, (size_t)N * 2 * ci * s * s);
+    m_sh = max(m_sh, (size_t)N * ci * 4 * s * s);
+    m_net = max(m_net, (size_t)N * co * 4 * s * s);
+  }
+  size_t P = (size_t)S << n_blocks;
+  size_t m_rgb = (size_t)N * 3 * P * P;
+  auto al = [](size_t v) { return (v * sizeof(float) + 255) & ~(size_t)255; };
+  NrPlan p;
+  p.t1 = 0;
+  p.sh = p.t1 + al(m_t1);
+  p.bl = p.sh + al(m_sh);
+  p.net = p.bl + al(m_sh);
+  p.rgb_a = p.net + 2 * al(m_net);  // two net buffers (ping-pong between levels)
+  p.rgb_b = p.rgb_a + al(m_rgb);
+  p.total = p.rgb_b + al(m_rgb);
+  return p;
+}
+
+}  // namespace gnrf
+
+using namespace gnrf;
+
+extern "C" size_t gnrf_nr_workspace_bytes(int N, int C, int S, int n_blocks, int min_feat) {
+  if (N <= 0 || C <= 0 || S <= 0 || n_blocks < 0) return 0;
+  return nr_plan(N, C, S, n_blocks, min_feat).total;
+}
+
+extern "C" int gnrf_neural_render_fwd(const float* const* params, const float* featmap, int N, int C, int S, int n_blocks,
+                                      int min_feat, float* img, void* workspace, size_t workspace_bytes, gnrf_stream_t stream) {
+  GNRF_CHECK_ARG(params && featmap && img && workspace);
+  GNRF_CHECK_ARG(N > 0 && C > 0 && S >= 2 && n_blocks >= 1 && n_blocks <= 6);
+  GNRF_CHECK_ARG(S % 4 == 0);
+  NrPlan pl = nr_plan(N, C, S, n_blocks, min_feat);
+  if (workspace_bytes < pl.total)
+    return fail(GNRF_ERR_ARG, "gnrf_neural_render_fwd: workspace %zu < required %zu bytes", workspace_bytes, pl.total);
+  cudaStream_t st = as_stream(stream);
+  char* ws = static_cast<char*>(workspace);
+  float* t1 = reinterpret_cast<float*>(ws + pl.t1);
+  float* sh = reinterpret_cast<float*>(ws + pl.sh);
+  float* bl = reinterpret_cast<float*>(ws + pl.bl);
+  float* netbuf[2] = {reinterpret_cast<float*>(ws + pl.net), reinterpret_cast<float*>(ws + pl.net + (pl.rgb_a - pl.net) / 2)};
+  float* rgb_a = reinterpret_cast<float*>(ws + pl.rgb_a);
+  float* rgb_b = reinterpret_cast<float*>(ws + pl.rgb_b);
+
+  // parameter indexing (see gnrf.h): psu i: [4i..4i+3]; to_rgb j: [4nb + 2j, +1]; feat i: [4nb + 2(nb+1) + 2i, +1]
+  auto psu_w = [&](int i, int l) { return params[4 * i + 2 * l]; };
+  auto psu_b = [&](int i, int l) { return params[4 * i + 2 * l + 1]; };
+  auto rgb_w = [&](int j) { return params[4 * n_blocks + 2 * j]; };
+  auto rgb_bi = [&](int j) { return params[4 * n_blocks + 2 * j + 1]; };
+  auto feat_w = [&](int i) { return params[4 * n_blocks + 2 * (n_blocks + 1) + 2 * i]; };
+  auto feat_b = [&](int i) { return params[4 * n_blocks + 2 * (n_blocks + 1) + 2 * i + 1]; };
+  for (int i = 0; i < 8 * n_blocks + 2; ++i) GNRF_CHECK_ARG(params[i] != nullptr);
+
+  auto launch_rgb = [&](const float* w, const float* b, const float* net, int Cn, int HW, const float* prev, int sig, float* dst) {
+    dim3 grid(ceil_div(HW, 256), N);
+    to_rgb_kernel<<<grid, 256, 3 * Cn * sizeof(float), st>>>(w, b, net, Cn, HW, prev, sig, dst);
+  };
+  auto launch_up = [&](const float* src, int H, float* dst) {
+    long long total = (long long)N * 3 * 4 * H * H;
+    rgb_up_blur_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, H, H, total, dst);
+  };
+
+  int s = S;
+  // rgb = rgb_upsample(feat_2_rgb_list[0](x))
+  launch_rgb(rgb_w(0), rgb_bi(0), featmap, C, s * s, nullptr, 0, rgb_a);
+  launch_up(rgb_a, s, rgb_b);
+  GNRF_LAUNCH_CHECK();
+  const float* net = featmap;
+  float* rgb_up = rgb_b;   // upsampled running rgb
+  float* rgb_cur = rgb_a;  // scratch for the next sum
+  for (int i = 0; i < n_blocks; ++i) {
+    int ci = (C >> i) > min_feat ? (C >> i) : min_feat;
+    int co = (C >> (i + 1)) > min_feat ? (C >> (i + 1)) : min_feat;
+    int HW = s * s;
+    {  // PSU layer_1: ci -> 2ci, LeakyReLU
+      dim3 grid(ceil_div(HW, BN), ceil_div(2 * ci, BM), N);
+      conv1x1_kernel<EPI_LRELU><<<grid, kGemmThreads, 0, st>>>(psu_w(i, 0), psu_b(i, 0), net, 2 * ci, ci, HW, s, nullptr, 1, t1);
+    }
+    {  // PSU layer_2: 2ci -> 4ci, LeakyReLU, + repeat(x,4), pixel_shuffle(2)
+      dim3 grid(ceil_div(HW, BN), ceil_div(4 * ci, BM), N);
+      conv1x1_kernel<EPI_PSU><<<grid, kGemmThreads, 0, st>>>(psu_w(i, 1), psu_b(i, 1), t1, 4 * ci, 2 * ci, HW, s, net, ci, sh);
+    }
+    s *= 2;
+    HW = s * s;
+    {
+      long long total = (long long)N * ci * HW;
+      blur3x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sh, s, s, total, bl);
+    }
+    float* net_out = netbuf[i & 1];
+    {  // feat_layers[i]: ci -> co, LeakyReLU
+      dim3 grid(ceil_div(HW, BN), ceil_div(co, BM), N);
+      conv1x1_kernel<EPI_LRELU><<<grid, kGemmThreads, 0, st>>>(feat_w(i), feat_b(i), bl, co, ci, HW, s, nullptr, 1, net_out);
+    }
+    bool last = (i == n_blocks - 1);
+    launch_rgb(rgb_w(i + 1), rgb_bi(i + 1), net_out, co, HW, rgb_up, last ? 1 : 0, last ? img : rgb_cur);
+    if (!last) {
+      float* dst = (rgb_cur == rgb_a) ? rgb_b : rgb_a;  // == rgb_up's buffer, whose contents are now consumed
+      launch_up(rgb_cur, s, dst);
+      rgb_up = dst;
+      rgb_cur = (dst == rgb_a) ? rgb_b : rgb_a;
+    }
+    net = net_out;
+    GNRF_LAUNCH_CHECK();
+  }
+  return GNRF_OK;
+}

@@ -1,0 +1,135 @@
+/* gnrf.h -- C ABI of the B200-native GazeNeRF render hot path (libgnrf.so).
+ *
+ * The reference (AlessandroRuzzi/GazeNeRF) is 100 % Python/PyTorch and has no native boundary; the boundary
+ * it DOES have is the module call  GazeNeRFNet.forward(mode, batch_xy, batch_uv, bg_code, shape_code,
+ * appea_code, gaze_code, batch_Rmats, batch_Tvecs, batch_inv_inmats)  (models/gaze_nerf.py:322-351).  Each
+ * entry point below replaces one stage of that call; the reference file:line it replaces is cited per
+ * function.  gazenerf_b200/net.py binds these with ctypes and re-creates the module API on top.
+ *
+ * Conventions (all functions)
+ *   - plain pointers + ints only; every pointer is a DEVICE pointer on the current CUDA device unless the
+ *     parameter is documented "host"; float = IEEE fp32; tensors are dense, row-major in the stated shape.
+ *   - no allocation, no ownership transfer: the caller owns every input, output and workspace buffer.
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); calls are asynchronous and re-entrant.
+ *   - return 0 on success, a GNRF_ERR_* code otherwise; gnrf_last_error() returns a thread-local message.
+ *     No exception or abort ever crosses the boundary (the reference's train loop swallows exceptions per
+ *     batch, trainer/gazenerf_trainer.py:576-582 -- the Python wrapper raises RuntimeError from the code).
+ */
+#ifndef GNRF_H_
+#define GNRF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNRF_ABI_VERSION 1
+
+enum {
+  GNRF_OK = 0,
+  GNRF_ERR_ARG = 1,         /* bad shape / null pointer / unsupported size */
+  GNRF_ERR_CUDA = 2,        /* a CUDA runtime call or launch failed */
+  GNRF_ERR_UNSUPPORTED = 3  /* configuration outside what the sm_100a kernels are specialised for */
+};
+
+/* Fixed network geometry of the path (models/gaze_nerf.py:22-62, configs/gazenerf_options.py:11-26). */
+#define GNRF_PE_DIMS 63          /* 3 + 6*10 positional-encoding channels */
+#define GNRF_SHAPE_EXT_DIMS 181  /* iden 100 + expr 79 + gaze 2 */
+#define GNRF_APPEA_DIMS 127      /* text 100 + illu 27 */
+#define GNRF_MLP_NPARAMS 24      /* 12 layers x (weight, bias), state_dict order */
+
+typedef void* gnrf_stream_t; /* cudaStream_t */
+
+int gnrf_abi_version(void);
+const char* gnrf_last_error(void);
+/* 0 if the current device is sm_100 (B200) and the kernels can run, else GNRF_ERR_UNSUPPORTED. */
+int gnrf_device_check(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Ray generation.  Replaces GenSamplePoints.forward, utils/model_utils.py:364-372.
+ *   xy [B,2,N_r] (row 0 = x, row 1 = y), rmats [B,3,3] cam-to-world, inv_inmats [B,3,3]
+ *   -> ray_dl [B,N_r,4] = (d_x, d_y, d_z, l) with d = normalize(R K^-1 (x,y,1)), l = -1/d_z.
+ * (ray origin o = Tvec is passed separately to the consumers.) */
+int gnrf_ray_setup(const float* xy, const float* rmats, const float* inv_inmats, int B, int N_r, float* ray_dl,
+                   gnrf_stream_t stream);
+
+/* Coarse depth edges.  Replaces GenSamplePoints._calc_sample_points + the jitter of
+ * _calc_sample_points_by_zvals, utils/model_utils.py:332-357, 302-307.
+ *   tvecs [B,3]; t_vals [N_s+1] = linspace(0,1,N_s+1) supplied by the host (keeps torch's rounding);
+ *   jitter_u [B,N_r,N_s+1] uniform draws (train mode) or NULL (eval)
+ *   -> z_edges [B,N_r,N_s+1];  sample k has depth z_edges[k] and extent (z_edges[k+1]-z_edges[k]) * l. */
+int gnrf_coarse_depths(const float* tvecs, const float* t_vals, const float* jitter_u, int B, int N_r, int N_s,
+                       float world_z1, float world_z2, float* z_edges, gnrf_stream_t stream);
+
+/* Hierarchical (inverse-CDF) fine sampling.  Replaces FineSample.forward, utils/model_utils.py:404-477.
+ *   weights [B,N_r,N_c] coarse compositing weights; z_edges_coarse [B,N_r,N_c+1];
+ *   u: [N_f1] shared by all rays when u_per_ray == 0, else [B*N_r, N_f1]   (N_f1 = num_sample_fine + 1)
+ *   -> inds (int64 [B*N_r, N_f1], may be NULL) = searchsorted(cdf, u, right=True), bit-exact integer work;
+ *      z_edges_fine [B,N_r,N_c+N_f1] = sort(cat(coarse sample depths, fine depths)). */
+int gnrf_fine_depths(const float* weights, const float* z_edges_coarse, const float* u, int u_per_ray, int B, int N_r,
+                     int N_c, int N_f1, int64_t* inds, float* z_edges_fine, gnrf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Radiance MLP, exact-fp32 CUDA-core path (one fused kernel per branch: ray points -> positional encoding
+ * -> 12 dense layers).  Replaces Embedder.forward (utils/model_utils.py:272-280), the code broadcast/concat
+ * (models/gaze_nerf.py:248-262,136-143) and MLPforNeRF.forward (models/mlp_nerf.py:95-119), literally (no
+ * algebraic folds).  params: HOST array of 24 device pointers, state_dict order:
+ *   FeaExt_module_0..7 (w,b), density_module (w,b), RGB_layer_0 (w,b), RGB_layer_1 (w,b), RGB_layer_2 (w,b).
+ *   -> feat_pts [B,N_r,N_s,n_feat], sigma_pts [B,N_r,N_s] (post-ReLU). */
+int gnrf_mlp_simt_fwd(const float* const* params, const float* ray_dl, const float* tvecs, const float* z_edges,
+                      const float* shape_ext, const float* appea, int B, int N_r, int N_s, int hidden, int n_feat,
+                      float* feat_pts, float* sigma_pts, gnrf_stream_t stream);
+
+/* Alpha compositing.  Replaces CalcRayColor.forward, utils/model_utils.py:493-534.
+ *   -> feat_ray [B,n_feat,N_r], bg_alpha [B,N_r], depth [B,N_r] (nullable), weights [B,N_r,N_s] (nullable). */
+int gnrf_composite_fwd(const float* feat_pts, const float* sigma_pts, const float* z_edges, const float* ray_dl, int B,
+                       int N_r, int N_s, int n_feat, float* feat_ray, float* bg_alpha, float* depth, float* weights,
+                       gnrf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Radiance MLP, tcgen05 tensor-core path (sm_100a): ONE fused kernel for both branches doing
+ * ray points -> PE -> dense stack (bf16x3 split-precision UMMA, fp32 accumulate in TMEM, weights streamed by
+ * TMA bulk copies) -> ReLU density -> per-ray alpha composite.  Same reference lines as the two entries above.
+ * Exact algebraic folds used: per-face code columns folded into bias vectors, density row
+ * appended to the RGB head, RGB_layer_0*RGB_layer_1 pre-multiplied, RGB_layer_2 applied after compositing.
+ *
+ * gnrf_mlp_tc_pack: params (host array of 24 device ptrs) -> packed (device, gnrf_mlp_tc_packed_bytes()).
+ * gnrf_mlp_tc_fold: per-face bias block [B, gnrf_mlp_tc_bias_floats()] from the packed fold matrices + codes.
+ * gnrf_mlp_tc_fwd : n_branch in {1,2}; packed[i], bias[i] per branch (host arrays of device pointers)
+ *   -> feat_ray[i] [B,n_feat,N_r], bg_alpha[i] [B,N_r], weights[i] [B,N_r,N_s] (array or entries may be NULL).
+ * N_s must divide 128 (1 tile = 128 consecutive samples = 128/N_s whole rays). */
+size_t gnrf_mlp_tc_packed_bytes(void);
+size_t gnrf_mlp_tc_bias_floats(void);
+int gnrf_mlp_tc_pack(const float* const* params, void* packed, gnrf_stream_t stream);
+int gnrf_mlp_tc_fold(const void* packed, const float* shape_ext, const float* appea, int B, float* bias,
+                     gnrf_stream_t stream);
+size_t gnrf_mlp_tc_workspace_bytes(int n_branch, int B, int N_r);
+int gnrf_mlp_tc_fwd(int n_branch, const void* const* packed, const float* const* bias, const float* ray_dl,
+                    const float* tvecs, const float* z_edges, int B, int N_r, int N_s, float* const* feat_ray,
+                    float* const* bg_alpha, float* const* weights, void* workspace, size_t workspace_bytes,
+                    gnrf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Feature-map compose: background blend, gaze rotation of channel triplets, max-merge.
+ * Replaces models/gaze_nerf.py:175-203 and rotate()/rotation_matrix_2d(), utils/model_utils.py:11-46.
+ *   feat_* [B,C,P], a_* [B,P], bg [C,P], gaze [B,2] (rad)  ->  out [3,B,C,P] = (merge_face, eyes_planes, merge). */
+int gnrf_compose_fwd(const float* feat_face, const float* a_face, const float* feat_eyes, const float* a_eyes,
+                     const float* bg, const float* gaze, int B, int C, int P, float* out, gnrf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * 2-D neural renderer (pixel-shuffle upsampler).  Replaces NeuralRenderer.forward (models/neural_renderer.py:
+ * 98-113), PixelShuffleUpsample.forward and Blur.forward (models/pixel_shuffle_upsample.py:7-42).
+ * params: HOST array of device pointers in state_dict order without bg_featmap and without the Blur buffers:
+ *   for i < n_blocks: feat_upsample_list.i.layer_1 (w,b), layer_2 (w,b);
+ *   then feat_2_rgb_list.0..n_blocks (w,b); then feat_layers.0..n_blocks-1 (w,b)     [n = 8*n_blocks + 2]
+ *   featmap [N,C,S,S] -> img [N,3,S*2^n_blocks,S*2^n_blocks] in (0,1). */
+size_t gnrf_nr_workspace_bytes(int N, int C, int S, int n_blocks, int min_feat);
+int gnrf_neural_render_fwd(const float* const* params, const float* featmap, int N, int C, int S, int n_blocks,
+                           int min_feat, float* img, void* workspace, size_t workspace_bytes, gnrf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNRF_H_ */
