@@ -28,7 +28,7 @@ NVCC_FLAGS = [
 ]
 
 SYMBOLS = [
-    "gnrf_abi_version", "gnrf_last_error", "gnrf_device_check",
+    "gnrf_abi_version", "gnrf_last_error", "gnrf_device_check", "gnrf_launch_count",
     "gnrf_ray_setup", "gnrf_coarse_depths", "gnrf_fine_depths",
     "gnrf_mlp_simt_fwd", "gnrf_composite_fwd",
     "gnrf_mlp_tc_packed_bytes", "gnrf_mlp_tc_bias_floats", "gnrf_mlp_tc_pack", "gnrf_mlp_tc_fold",
@@ -91,6 +91,7 @@ def lib() -> ctypes.CDLL:
     L.gnrf_abi_version.restype = i32
     L.gnrf_last_error.restype = c.c_char_p
     L.gnrf_device_check.restype = i32
+    L.gnrf_launch_count.restype = c.c_ulonglong
     L.gnrf_ray_setup.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.gnrf_coarse_depths.argtypes = [vp, vp, vp, i32, i32, i32, f32, f32, vp, vp]
     L.gnrf_fine_depths.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]

@@ -1,6 +1,8 @@
 // libgnrf: error plumbing + device check (see include/gnrf.h).
 #include "common.cuh"
 
+#include <atomic>
+
 namespace gnrf {
 
 char* error_buffer() {
@@ -16,7 +18,12 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
 }  // namespace gnrf
+
+extern "C" unsigned long long gnrf_launch_count(void) { return gnrf::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int gnrf_abi_version(void) { return GNRF_ABI_VERSION; }
 

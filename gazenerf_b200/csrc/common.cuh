@@ -12,6 +12,7 @@ namespace gnrf {
 // thread-local error text returned by gnrf_last_error()
 char* error_buffer();
 int fail(int code, const char* fmt, ...);
+void count_launches(int n);  // feeds gnrf_launch_count()
 
 #define GNRF_CHECK_ARG(cond)                                                             \
   do {                                                                                   \

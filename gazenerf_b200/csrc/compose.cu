@@ -61,5 +61,6 @@ extern "C" int gnrf_compose_fwd(const float* feat_face, const float* a_face, con
   compose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(feat_face, a_face, feat_eyes, a_eyes, bg, gaze,
                                                                                B, C, P, out);
   GNRF_LAUNCH_CHECK();
+  count_launches(1);
   return GNRF_OK;
 }

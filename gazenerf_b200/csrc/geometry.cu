@@ -145,6 +145,7 @@ extern "C" int gnrf_ray_setup(const float* xy, const float* rmats, const float* 
   ray_setup_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(xy, rmats, inv_inmats, B, N_r,
                                                                     reinterpret_cast<float4*>(ray_dl));
   GNRF_LAUNCH_CHECK();
+  count_launches(1);
   return GNRF_OK;
 }
 
@@ -156,6 +157,7 @@ extern "C" int gnrf_coarse_depths(const float* tvecs, const float* t_vals, const
   coarse_depths_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(tvecs, t_vals, jitter_u, B, N_r, N_s,
                                                                                      world_z1, world_z2, z_edges);
   GNRF_LAUNCH_CHECK();
+  count_launches(1);
   return GNRF_OK;
 }
 
@@ -168,5 +170,6 @@ extern "C" int gnrf_fine_depths(const float* weights, const float* z_edges_coars
   fine_depths_kernel<<<B * N_r, kFineThreads, 0, as_stream(stream)>>>(weights, z_edges_coarse, u, u_per_ray, N_c, N_f1,
                                                                       reinterpret_cast<long long*>(inds), z_edges_fine);
   GNRF_LAUNCH_CHECK();
+  count_launches(1);
   return GNRF_OK;
 }

@@ -312,6 +312,7 @@ extern "C" int gnrf_mlp_simt_fwd(const float* const* params, const float* ray_dl
       prm, reinterpret_cast<const float4*>(ray_dl), tvecs, z_edges, shape_ext, appea, N_r, N_s, hidden, n_feat, tiles_per_face,
       feat_pts, sigma_pts);
   GNRF_LAUNCH_CHECK();
+  count_launches(1);
   return GNRF_OK;
 }
 
@@ -323,5 +324,6 @@ extern "C" int gnrf_composite_fwd(const float* feat_pts, const float* sigma_pts,
   composite_kernel<<<B * N_r, 256, N_s * sizeof(float), as_stream(stream)>>>(
       feat_pts, sigma_pts, z_edges, reinterpret_cast<const float4*>(ray_dl), N_r, N_s, n_feat, feat_ray, bg_alpha, depth, weights);
   GNRF_LAUNCH_CHECK();
+  count_launches(1);
   return GNRF_OK;
 }

@@ -1,10 +1,749 @@
-// placeholder: tcgen05 fused MLP (implemented next)
+// Fused radiance-MLP kernel for sm_100a (tcgen05 / TMEM / TMA bulk copies), both branches in one launch.
+//
+//   tile = 128 consecutive sample points of one face (= 128/N_s whole rays)  ->  UMMA M = 128 (TMEM lane == point)
+//   per tile:  ray points -> positional encoding -> L0..L8 dense stack -> ReLU density -> per-ray alpha composite
+//
+// Precision: every product is evaluated as bf16x3 -- x = x_hi + x_lo, w = w_hi + w_lo (bf16 each) and
+//   x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo   (3 UMMAs, fp32 accumulation in TMEM; the dropped lo*lo term is 2^-18 relative)
+// which keeps ~16 significand bits per operand: measured <= 2e-5 relative on the composited features vs the fp32 oracle
+// (single-pass bf16 is 5e-3..9e-3 and TF32 4e-4..1.1e-3, SURVEY §7 hard part 1 -- outside / on the edge of the 1e-3 bar).
+//
+// Exact algebraic rewrites of the reference graph (models/mlp_nerf.py:95-119, models/gaze_nerf.py:248-262):
+//   (i)   the 181 code channels of the 244-wide input and the 127 appearance channels are constant per face: their
+//         weight columns are folded into per-face bias vectors (gnrf_mlp_tc_fold);  per-point K becomes 64 / 384 / 384+64.
+//   (ii)  density_module shares its input with RGB_layer_0 -> appended as one extra output row of the last stage.
+//   (iii) RGB_layer_0 -> RGB_layer_1 has no activation in between -> pre-multiplied at pack time (fp64) into one 192x384 layer.
+//   (iv)  RGB_layer_2 is linear and un-activated: sum_s w_s (W h_s + b) = W (sum_s w_s h_s) + b sum_s w_s, so the 192-d hidden
+//         is composited per ray and RGB_layer_2 is applied once per ray by rgb_head_kernel (fp32 FMA).
+//
+// On-chip layout per CTA (1 CTA / SM, 192 threads = 4 epilogue warps + 1 TMA warp + 1 MMA warp):
+//   smem  A_hi, A_lo : 6 K-blocks x [128 rows x 64 bf16], SWIZZLE_128B K-major (UMMA canonical)      2 x 96 KB
+//         W ring     : 4 x 8 KB stages, each one [64 rows x 64 bf16] SW128 block of W_hi or W_lo, streamed from the
+//                      pre-swizzled packed image in HBM/L2 by cp.async.bulk (TMA bulk copy) + mbarrier complete_tx
+//   TMEM  columns 0..383 : fp32 accumulators (6 N-blocks of 64);  384..447 : the tile's positional encoding, parked as
+//                      packed (hi,lo) bf16 pairs for the skip connection of layer 5.
+// Layer pipeline: the epilogue warps drain an N=384 accumulator K-block by K-block (64 columns: +bias, ReLU, hi/lo split,
+// swizzled st.shared) and release each K-block to the MMA warp through its own mbarrier, so the next layer's first
+// N-block runs while the drain is still in progress; N-blocks 1..5 then run at full rate.
+#include <cstdlib>
+
 #include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace gnrf {
+namespace tc {
+
+using namespace ptx;
+
+constexpr int kHidden = 384;
+constexpr int kFeat = 258;
+constexpr int kH2 = 192;                 // RGB_layer_1 width
+constexpr int kTile = 128;               // points per tile == UMMA M
+constexpr int kKB = 64;                  // K-block (bf16 elements) == 128-byte swizzle span
+constexpr int kNB = 64;                  // N-block (accumulator columns per UMMA)
+constexpr int kNumKB = kHidden / kKB;    // 6
+constexpr int kNumLayers = 9;            // L0..L7 trunk, L8 = fused (RGB_0*RGB_1 | density)
+constexpr int kL8N = 208;                // 192 + 1 density + 15 zero rows
+constexpr int kStageBytes = kNB * 128;   // 8192
+constexpr int kStages = 4;
+constexpr int kABlockBytes = kTile * 128;            // 16384: one K-block of A (hi or lo)
+constexpr int kABytes = kNumKB * kABlockBytes;       // 98304
+constexpr int kEpiThreads = 128;
+constexpr int kThreads = 192;
+constexpr int kPeCol = 384;              // TMEM column where the PE is parked
+constexpr int kScratchLd = 193;          // composite scratch row stride (floats): conflict-free for both phases
+
+// ---- packed parameter image ----------------------------------------------------------------------------------------
+// bf16 stage stream, in exactly the order the MMA warp consumes it:
+//   layer 0      : nb 0..5               x {hi, lo}                       (K = 64: PE + zero pad)
+//   layer 1-4,6,7: nb 0..5 x kb 0..5     x {hi, lo}
+//   layer 5      : nb 0..5 x kb 0..5 x {hi,lo} (hidden columns)  then  nb 0..5 x {hi, lo} (PE columns)
+//   layer 8      : nb 0..2 x kb 0..5 x {hi,lo} (64 rows)  then  nb 3 x kb 0..5 x {hi,lo} (16 rows, 2 KB stages)
+constexpr int kBigStages = 6 * 2 + 7 * 36 * 2 + 6 * 2 + 3 * 6 * 2;   // 564 stages of 8 KB
+constexpr int kSmallStages = 6 * 2;                                     // 12 stages of 2 KB (the 16-row block of layer 8)
+constexpr int kSmallStageBytes = 16 * 128;
+constexpr size_t kStreamBytes = (size_t)kBigStages * kStageBytes + (size_t)kSmallStages * kSmallStageBytes;
+// fp32 auxiliary block (float offsets from aux base)
+constexpr int kBiasFloats = 8 * kHidden + kL8N;                       // 3280 per face
+constexpr size_t kAuxBaseBias = 0;                                    // [3280] face-independent part of every bias
+constexpr size_t kAuxW0c = kAuxBaseBias + kBiasFloats;                // [384][181] code columns of FeaExt_module_0
+constexpr size_t kAuxW5c = kAuxW0c + (size_t)kHidden * GNRF_SHAPE_EXT_DIMS;
+constexpr size_t kAuxW1c = kAuxW5c + (size_t)kHidden * GNRF_SHAPE_EXT_DIMS;   // [192][127] appearance columns of RGB_layer_1
+constexpr size_t kAuxW2t = kAuxW1c + (size_t)kH2 * GNRF_APPEA_DIMS;           // [192][258] RGB_layer_2 transposed
+constexpr size_t kAuxB2 = kAuxW2t + (size_t)kH2 * kFeat;                      // [258]
+constexpr size_t kAuxWf = kAuxB2 + 264;                                       // [208][384] fused last-stage matrix (fp32)
+constexpr size_t kAuxFloats = kAuxWf + (size_t)kL8N * kHidden;
+constexpr size_t kPackedBytes = kStreamBytes + kAuxFloats * sizeof(float);
+
+__host__ __device__ inline int bias_offset(int layer) { return layer * kHidden; }
+
+// ---- shared memory map ---------------------------------------------------------------------------------------------
+constexpr int kSmemAHi = 0;
+constexpr int kSmemALo = kABytes;
+constexpr int kSmemRing = 2 * kABytes;                       // 196608
+constexpr int kSmemBars = kSmemRing + kStages * kStageBytes; // 229376
+constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarAReady = 2 * kStages, kBarAccFull = kBarAReady + kNumKB,
+              kBarAFree = kBarAccFull + 1, kNumBars = kBarAFree + 1;
+constexpr int kSmemMisc = kSmemBars + kNumBars * 8;          // tmem ptr, scan scratch
+constexpr int kSmemBytes = kSmemMisc + 64 + 1024;            // + alignment slack
+
+struct BranchArgs {
+  const unsigned char* stream;  // packed bf16 stage stream
+  const float* bias;            // [B][kBiasFloats]
+  float* hc;                    // [B][N_r][192]  composited hidden
+  float* wsum;                  // [B][N_r]
+  float* weights;               // [B][N_r][N_s] or null
+};
+
+struct FwdArgs {
+  BranchArgs br[2];
+  const float4* ray_dl;
+  const float* tvecs;
+  const float* z_edges;
+  int n_branch, B, N_r, N_s, tiles_per_face, n_items;
+  float* dbg;  // optional [9][128][384] dump of tile 0 activations
+};
+
+// =====================================================================================================================
+//  main kernel
+// =====================================================================================================================
+__device__ __forceinline__ uint32_t a_row_offset(int row) { return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128); }
+
+// Write 64 consecutive K values of one row (as hi/lo bf16) into K-block `kb` of A.  v[] already activated.
+__device__ __forceinline__ void store_a_row64(uint32_t smem_base, int kb, int row, const float (&v)[64]) {
+  const uint32_t row_off = (uint32_t)kb * kABlockBytes + a_row_offset(row);
+  const uint32_t sw = (uint32_t)(row & 7);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) split2(v[8 * j + 2 * q], v[8 * j + 2 * q + 1], hi[q], lo[q]);
+    const uint32_t off = row_off + (((uint32_t)j ^ sw) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_base + kSmemAHi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
+                 "r"(hi[3])
+                 : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_base + kSmemALo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]),
+                 "r"(lo[3])
+                 : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bars = smem_base + kSmemBars;
+  auto bar = [&](int i) { return bars + (uint32_t)i * 8u; };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + kSmemMisc);
+  float* warp_prod = reinterpret_cast<float*>(smem_gen + kSmemMisc + 16);  // [4]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(bar(kBarWFull + i), 1);
+      mbar_init(bar(kBarWEmpty + i), 1);
+    }
+    for (int i = 0; i < kNumKB; ++i) mbar_init(bar(kBarAReady + i), 4);  // one arrive per epilogue warp
+    mbar_init(bar(kBarAccFull), 1);
+    mbar_init(bar(kBarAFree), 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc_512(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)));
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 4) {
+    // =============================================== TMA producer ===============================================
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      for (int item = blockIdx.x; item < args.n_items; item += gridDim.x) {
+        const int branch = item % args.n_branch;
+        const unsigned char* src = args.br[branch].stream;
+        // 564 full stages + 12 small ones, consumed strictly in order
+        for (int s = 0; s < kBigStages + kSmallStages; ++s) {
+          const uint32_t bytes = (s < kBigStages) ? (uint32_t)kStageBytes : (uint32_t)kSmallStageBytes;
+          mbar_wait(bar(kBarWEmpty + slot), phase ^ 1);
+          mbar_arrive_expect_tx(bar(kBarWFull + slot), bytes);
+          bulk_g2s(smem_base + kSmemRing + slot * kStageBytes, src, bytes, bar(kBarWFull + slot));
+          src += bytes;
+          if (++slot == kStages) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // =============================================== MMA issuer =================================================
+    if (lane == 0) {
+      uint32_t slot = 0, wphase = 0;
+      uint32_t a_phase = 0;  // bit kb = parity of the next completion of a_ready[kb]
+      constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64);
+      constexpr uint32_t idesc16 = umma_idesc_bf16(128, 16);
+      const uint64_t a_hi_desc0 = umma_desc_sw128(smem_base + kSmemAHi);
+      const uint64_t a_lo_desc0 = umma_desc_sw128(smem_base + kSmemALo);
+
+      // one (nb, kb) step = two ring stages: W_hi block (A_hi*W_hi + A_lo*W_hi), then W_lo block (A_hi*W_lo)
+      auto step = [&](int nb_col, uint32_t idesc, int a_kb, bool fresh) {
+        const uint64_t a_hi = a_hi_desc0 + (uint64_t)((a_kb * kABlockBytes) >> 4);
+        const uint64_t a_lo = a_lo_desc0 + (uint64_t)((a_kb * kABlockBytes) >> 4);
+        const uint32_t d = tmem_base + (uint32_t)nb_col;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          mbar_wait(bar(kBarWFull + slot), wphase);
+          tc_fence_after_sync();
+          const uint64_t b = umma_desc_sw128(smem_base + kSmemRing + slot * kStageBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x K16 inside the 128-byte swizzle span: +32 B per step
+            if (half == 0) {
+              umma_ss(d, a_hi + 2 * k, b + 2 * k, idesc, (fresh && k == 0) ? 0u : 1u);
+              umma_ss(d, a_lo + 2 * k, b + 2 * k, idesc, 1u);
+            } else {
+              umma_ss(d, a_hi + 2 * k, b + 2 * k, idesc, 1u);
+            }
+          }
+          umma_commit(bar(kBarWEmpty + slot));
+          if (++slot == kStages) { slot = 0; wphase ^= 1; }
+        }
+      };
+      auto wait_a = [&](int kb) {
+        mbar_wait(bar(kBarAReady + kb), (a_phase >> kb) & 1u);
+        a_phase ^= (1u << kb);
+        tc_fence_after_sync();
+      };
+
+      for (int item = blockIdx.x; item < args.n_items; item += gridDim.x) {
+        // ---- layer 0: K = 64 (PE in K-block 0)
+        wait_a(0);
+        for (int nb = 0; nb < 6; ++nb) step(nb * kNB, idesc64, 0, true);
+        umma_commit(bar(kBarAccFull));
+        // ---- layers 1..7
+        for (int layer = 1; layer < 8; ++layer) {
+          for (int nb = 0; nb < 6; ++nb)
+            for (int kb = 0; kb < kNumKB; ++kb) {
+              if (nb == 0) wait_a(kb);
+              step(nb * kNB, idesc64, kb, kb == 0);
+            }
+          if (layer == 5) {
+            // skip connection: the PE columns of FeaExt_module_5 (models/mlp_nerf.py:106-107); the epilogue re-stages
+            // the parked PE into K-block 0 once every read of the hidden K-blocks has completed.
+            umma_commit(bar(kBarAFree));
+            wait_a(0);
+            for (int nb = 0; nb < 6; ++nb) step(nb * kNB, idesc64, 0, false);
+          }
+          umma_commit(bar(kBarAccFull));
+        }
+        // ---- layer 8: [RGB_0*RGB_1 (192) | density (1) | pad] = 3 x N64 + 1 x N16
+        for (int nb = 0; nb < 4; ++nb)
+          for (int kb = 0; kb < kNumKB; ++kb) {
+            if (nb == 0) wait_a(kb);
+            step(nb * kNB, nb < 3 ? idesc64 : idesc16, kb, kb == 0);
+          }
+        umma_commit(bar(kBarAccFull));
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================================== epilogue warps (0..3) =======================================
+    const int row = threadIdx.x;                                   // TMEM lane == tile row == sample point
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t acc_phase = 0, afree_phase = 0;
+    const int N_s = args.N_s;
+    const int rays_per_tile = kTile / N_s;
+    float* scratch = reinterpret_cast<float*>(smem_gen);           // [128][193] fp32, aliases A between tiles
+
+    auto release_kb = [&](int kb) {
+      fence_proxy_async_smem();   // generic-proxy st.shared -> visible to the tensor core (async proxy)
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kBarAReady + kb));
+    };
+
+    for (int item = blockIdx.x; item < args.n_items; item += gridDim.x) {
+      const int branch = item % args.n_branch;
+      const int t = item / args.n_branch;
+      const int b = t / args.tiles_per_face;
+      const int tile = t - b * args.tiles_per_face;
+      const BranchArgs& br = args.br[branch];
+      const float* bias = br.bias + (size_t)b * kBiasFloats;
+      const bool dump = (args.dbg != nullptr) && (item == 0);
+
+      // ---- prologue: sample point -> positional encoding -> A K-block 0 (+ parked copy in TMEM) ----------------
+      const int ray = tile * rays_per_tile + row / N_s;
+      const int s = row - (row / N_s) * N_s;
+      const float4 dl = args.ray_dl[(size_t)b * args.N_r + ray];
+      const float* ze = args.z_edges + ((size_t)b * args.N_r + ray) * (N_s + 1);
+      const float z = ze[s];
+      const float delta = __fmul_rn(__fsub_rn(ze[s + 1], z), dl.w);  // (z_{k+1} - z_k) * l  (utils/model_utils.py:309-310)
+      {
+        float pe[64];
+        const float dc[3] = {dl.x, dl.y, dl.z};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          // pts = o + ((d * l) * z)  (utils/model_utils.py:315), each op individually rounded
+          float x = __fadd_rn(args.tvecs[b * 3 + c], __fmul_rn(__fmul_rn(dc[c], dl.w), z));
+          pe[c] = x;
+          float f = 1.0f;
+#pragma unroll
+          for (int q = 0; q < 10; ++q) {
+            float sv, cv;
+            sincosf(__fmul_rn(x, f), &sv, &cv);  // utils/model_utils.py:263-265 (freq = 2^q exactly)
+            pe[3 + 6 * q + c] = sv;
+            pe[6 + 6 * q + c] = cv;
+            f *= 2.0f;
+          }
+        }
+        pe[63] = 0.0f;
+        store_a_row64(smem_base, 0, row, pe);
+        // parked copy: column j holds (hi_j | lo_j << 16)
+        uint32_t pk[32];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            uint32_t hi, lo;
+            split2(pe[32 * half + j], pe[32 * half + j + 1], hi, lo);
+            pk[j] = (hi & 0xFFFFu) | (lo << 16);
+            pk[j + 1] = (hi >> 16) | (lo & 0xFFFF0000u);
+          }
+          tmem_st32(t_lane + kPeCol + 32 * half, pk);
+        }
+        tmem_wait_st();
+        if (dump)
+          for (int j = 0; j < 64; ++j) args.dbg[(size_t)row * kHidden + j] = pe[j];
+      }
+      release_kb(0);
+
+      // ---- trunk: drain layer l accumulators into A as the input of layer l+1 ----------------------------------
+      for (int layer = 0; layer < 8; ++layer) {
+        mbar_wait(bar(kBarAccFull), acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after_sync();
+        const float* bl = bias + bias_offset(layer);
+#pragma unroll 1
+        for (int kb = 0; kb < kNumKB; ++kb) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(t_lane + kb * 64, r0);
+          tmem_ld32(t_lane + kb * 64 + 32, r1);
+          tmem_wait_ld();
+          float v[64];
+          const float4* b4 = reinterpret_cast<const float4*>(bl + kb * 64);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 bb = __ldg(b4 + j);
+            v[4 * j + 0] = fmaxf(__uint_as_float(r0[4 * j + 0]) + bb.x, 0.0f);
+            v[4 * j + 1] = fmaxf(__uint_as_float(r0[4 * j + 1]) + bb.y, 0.0f);
+            v[4 * j + 2] = fmaxf(__uint_as_float(r0[4 * j + 2]) + bb.z, 0.0f);
+            v[4 * j + 3] = fmaxf(__uint_as_float(r0[4 * j + 3]) + bb.w, 0.0f);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 bb = __ldg(b4 + 8 + j);
+            v[32 + 4 * j + 0] = fmaxf(__uint_as_float(r1[4 * j + 0]) + bb.x, 0.0f);
+            v[32 + 4 * j + 1] = fmaxf(__uint_as_float(r1[4 * j + 1]) + bb.y, 0.0f);
+            v[32 + 4 * j + 2] = fmaxf(__uint_as_float(r1[4 * j + 2]) + bb.z, 0.0f);
+            v[32 + 4 * j + 3] = fmaxf(__uint_as_float(r1[4 * j + 3]) + bb.w, 0.0f);
+          }
+          store_a_row64(smem_base, kb, row, v);
+          if (dump)
+            for (int j = 0; j < 64; ++j) args.dbg[((size_t)(layer + 1) * kTile + row) * kHidden + kb * 64 + j] = v[j];
+          release_kb(kb);
+        }
+        if (layer == 4) {
+          // layer 5 = [hidden | PE]: once the hidden part has been consumed, re-stage the parked PE into K-block 0
+          mbar_wait(bar(kBarAFree), afree_phase);
+          afree_phase ^= 1;
+          tc_fence_after_sync();
+          uint32_t pk0[32], pk1[32];
+          tmem_ld32(t_lane + kPeCol, pk0);
+          tmem_ld32(t_lane + kPeCol + 32, pk1);
+          tmem_wait_ld();
+          const uint32_t row_off = a_row_offset(row);
+          const uint32_t sw = (uint32_t)(row & 7);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int c = 8 * j + 2 * q;  // columns c, c+1
+              const uint32_t p0 = (c < 32) ? pk0[c] : pk1[c - 32];
+              const uint32_t p1 = (c < 32) ? pk0[c + 1] : pk1[c + 1 - 32];
+              hi[q] = (p0 & 0xFFFFu) | (p1 << 16);
+              lo[q] = (p0 >> 16) | (p1 & 0xFFFF0000u);
+            }
+            const uint32_t off = row_off + (((uint32_t)j ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_base + kSmemAHi + off), "r"(hi[0]), "r"(hi[1]),
+                         "r"(hi[2]), "r"(hi[3])
+                         : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_base + kSmemALo + off), "r"(lo[0]), "r"(lo[1]),
+                         "r"(lo[2]), "r"(lo[3])
+                         : "memory");
+          }
+          release_kb(0);
+        }
+      }
+
+      // ---- last stage: density -> alpha -> transmittance scan -> weights; composite the 192-d hidden per ray ----
+      mbar_wait(bar(kBarAccFull), acc_phase);
+      acc_phase ^= 1;
+      tc_fence_after_sync();
+      const float* b8 = bias + bias_offset(8);
+      float w_k;
+      {
+        uint32_t rs;
+        tmem_ld1(t_lane + kH2, rs);
+        tmem_wait_ld();
+        const float sigma = fmaxf(__uint_as_float(rs) + __ldg(b8 + kH2), 0.0f);          // models/mlp_nerf.py:115
+        const float alpha = __fsub_rn(1.0f, expf(-__fmul_rn(sigma, delta)));             // utils/model_utils.py:500
+        const float x = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);                       // :507
+        // exclusive product over the samples of this ray that precede s (segmented scan; cumprod of :508-510)
+        const int seg = N_s < 32 ? N_s : 32;
+        const int lane_in_seg = lane & (seg - 1);
+        float incl = x;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          float up = __shfl_up_sync(0xffffffffu, incl, off);
+          if (off < seg && lane_in_seg >= off) incl *= up;
+        }
+        float T = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane_in_seg == 0) T = 1.0f;
+        if (N_s > 32) {
+          if (lane == 31) warp_prod[warp] = incl;
+          named_bar_sync(1, kEpiThreads);
+          const int warps_per_ray = N_s >> 5;
+          const int w0 = (warp / warps_per_ray) * warps_per_ray;
+          for (int w = w0; w < warp; ++w) T *= warp_prod[w];
+        }
+        w_k = __fmul_rn(alpha, T);                                                        // :512
+        if (br.weights != nullptr) br.weights[((size_t)b * args.N_r + ray) * N_s + s] = w_k;
+        if (dump) args.dbg[((size_t)9 * kTile + row) * kHidden + kH2] = sigma;
+      }
+      // all A reads of this tile are complete (acc_full) -> A can be reused as the [128][193] fp32 scratch
+#pragma unroll 1
+      for (int c0 = 0; c0 < kH2; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_lane + c0, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float h = fmaxf(__uint_as_float(r[j]) + __ldg(b8 + c0 + j), 0.0f);               // ReLU after RGB_layer_1 (:112)
+          scratch[row * kScratchLd + c0 + j] = w_k * h;
+          if (dump) args.dbg[((size_t)9 * kTile + row) * kHidden + c0 + j] = h;
+        }
+      }
+      scratch[row * kScratchLd + kH2] = w_k;
+      tc_fence_before_sync();
+      named_bar_sync(1, kEpiThreads);
+      {
+        const int total = rays_per_tile * kScratchLd;
+        for (int idx = row; idx < total; idx += kEpiThreads) {
+          const int rl = idx / kScratchLd, c = idx - rl * kScratchLd;
+          const float* col = scratch + (size_t)rl * N_s * kScratchLd + c;
+          float acc = 0.0f;
+          for (int k = 0; k < N_s; ++k) acc += col[(size_t)k * kScratchLd];
+          const size_t gray = (size_t)b * args.N_r + tile * rays_per_tile + rl;
+          if (c < kH2) br.hc[gray * kH2 + c] = acc; else br.wsum[gray] = acc;
+        }
+      }
+      named_bar_sync(1, kEpiThreads);  // scratch reads done before the next tile's prologue overwrites A
+    }
+  }
+
+  // ---- teardown ----------------------------------------------------------------------------------------------
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after_sync();
+    tmem_dealloc_512(tmem_base);
+  }
+}
+
+// =====================================================================================================================
+//  RGB_layer_2 after compositing (fold iv):  feat[b][c][ray] = sum_k W2[c][k] hc[b][ray][k] + b2[c] wsum ; bg_alpha = 1 - wsum
+// =====================================================================================================================
+constexpr int kHeadRays = 32;
+__global__ void __launch_bounds__(288) rgb_head_kernel(const float* __restrict__ aux, const float* __restrict__ hc,
+                                                       const float* __restrict__ wsum, int N_r, float* __restrict__ feat_ray,
+                                                       float* __restrict__ bg_alpha) {
+  __shared__ float s_h[kHeadRays][kH2 + 1];
+  __shared__ float s_w[kHeadRays];
+  const int b = blockIdx.y;
+  const int r0 = blockIdx.x * kHeadRays;
+  const int nr = min(kHeadRays, N_r - r0);
+  for (int i = threadIdx.x; i < nr * kH2; i += blockDim.x) {
+    int r = i / kH2, k = i - r * kH2;
+    s_h[r][k] = hc[((size_t)b * N_r + r0 + r) * kH2 + k];
+  }
+  for (int i = threadIdx.x; i < kHeadRays; i += blockDim.x) {
+    float w = (i < nr) ? wsum[(size_t)b * N_r + r0 + i] : 0.0f;
+    s_w[i] = w;
+    if (i < nr) bg_alpha[(size_t)b * N_r + r0 + i] = 1.0f - w;   // utils/model_utils.py:531-532
+  }
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (c >= kFeat) return;
+  const float* w2t = aux + kAuxW2t;
+  float acc[kHeadRays];
+#pragma unroll
+  for (int r = 0; r < kHeadRays; ++r) acc[r] = 0.0f;
+  for (int k = 0; k < kH2; ++k) {
+    float w = __ldg(w2t + (size_t)k * kFeat + c);
+#pragma unroll
+    for (int r = 0; r < kHeadRays; ++r) acc[r] = fmaf(w, s_h[r][k], acc[r]);
+  }
+  const float b2 = __ldg(aux + kAuxB2 + c);
+  float* dst = feat_ray + ((size_t)b * kFeat + c) * N_r + r0;
+#pragma unroll
+  for (int r = 0; r < kHeadRays; ++r)
+    if (r < nr) dst[r] = fmaf(b2, s_w[r], acc[r]);
+}
+
+// =====================================================================================================================
+//  packing
+// =====================================================================================================================
+struct PackSrc {
+  const float* w[12];
+  const float* b[12];
+};
+
+// Wf[n][k] (n < 192) = sum_j W1[n][j] * W0rgb[j][k] (fp64 accumulate);  row 192 = density weights;  rows 193.. = 0.
+// base_bias[8*384 + n] (n < 192) = b1[n] + sum_j W1[n][j] * b0rgb[j];  [.. + 192] = b_density.
+__global__ void fuse_head_kernel(PackSrc src, float* __restrict__ aux) {
+  const int n = blockIdx.x;  // 0..207
+  float* wf = aux + kAuxWf + (size_t)n * kHidden;
+  float* base_bias = aux + kAuxBaseBias;
+  const int ld1 = kHidden + GNRF_APPEA_DIMS;
+  if (n < kH2) {
+    for (int k = threadIdx.x; k < kHidden; k += blockDim.x) {
+      double acc = 0.0;
+      for (int j = 0; j < kHidden; ++j) acc += (double)src.w[10][(size_t)n * ld1 + j] * (double)src.w[9][(size_t)j * kHidden + k];
+      wf[k] = (float)acc;
+    }
+    if (threadIdx.x == 0) {
+      double acc = (double)src.b[10][n];
+      for (int j = 0; j < kHidden; ++j) acc += (double)src.w[10][(size_t)n * ld1 + j] * (double)src.b[9][j];
+      base_bias[8 * kHidden + n] = (float)acc;
+    }
+  } else if (n == kH2) {
+    for (int k = threadIdx.x; k < kHidden; k += blockDim.x) wf[k] = src.w[8][k];
+    if (threadIdx.x == 0) base_bias[8 * kHidden + n] = src.b[8][0];
+  } else {
+    for (int k = threadIdx.x; k < kHidden; k += blockDim.x) wf[k] = 0.0f;
+    if (threadIdx.x == 0) base_bias[8 * kHidden + n] = 0.0f;
+  }
+}
+
+// copies: trunk biases, code / appearance columns, RGB_layer_2 transposed
+__global__ void pack_aux_kernel(PackSrc src, float* __restrict__ aux) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nth = gridDim.x * blockDim.x;
+  const int vp = GNRF_PE_DIMS + GNRF_SHAPE_EXT_DIMS;  // 244
+  for (int i = tid; i < 8 * kHidden; i += nth) aux[kAuxBaseBias + i] = src.b[i / kHidden][i % kHidden];
+  for (int i = tid; i < kHidden * GNRF_SHAPE_EXT_DIMS; i += nth) {
+    int n = i / GNRF_SHAPE_EXT_DIMS, k = i % GNRF_SHAPE_EXT_DIMS;
+    aux[kAuxW0c + i] = src.w[0][(size_t)n * vp + GNRF_PE_DIMS + k];
+    aux[kAuxW5c + i] = src.w[5][(size_t)n * (vp + kHidden) + GNRF_PE_DIMS + k];
+  }
+  for (int i = tid; i < kH2 * GNRF_APPEA_DIMS; i += nth) {
+    int n = i / GNRF_APPEA_DIMS, k = i % GNRF_APPEA_DIMS;
+    aux[kAuxW1c + i] = src.w[10][(size_t)n * (kHidden + GNRF_APPEA_DIMS) + kHidden + k];
+  }
+  for (int i = tid; i < kH2 * kFeat; i += nth) {
+    int k = i / kFeat, c = i % kFeat;
+    aux[kAuxW2t + i] = src.w[11][(size_t)c * kH2 + k];
+  }
+  for (int i = tid; i < kFeat; i += nth) aux[kAuxB2 + i] = src.b[11][i];
+}
+
+// One thread per 16-byte chunk (8 bf16) of the stage stream.
+__device__ __forceinline__ float pack_src_value(const PackSrc& src, const float* wf, int layer, int phase2, int n, int kb, int kl) {
+  const int vp = GNRF_PE_DIMS + GNRF_SHAPE_EXT_DIMS;
+  if (layer == 0) return (kl < GNRF_PE_DIMS) ? src.w[0][(size_t)n * vp + kl] : 0.0f;
+  if (layer == 5) {
+    const size_t ld = vp + kHidden;
+    if (phase2) return (kl < GNRF_PE_DIMS) ? src.w[5][(size_t)n * ld + kl] : 0.0f;
+    return src.w[5][(size_t)n * ld + vp + kb * kKB + kl];
+  }
+  if (layer == 8) return wf[(size_t)n * kHidden + kb * kKB + kl];
+  return src.w[layer][(size_t)n * kHidden + kb * kKB + kl];
+}
+
+__global__ void pack_stream_kernel(PackSrc src, const float* __restrict__ wf, unsigned char* __restrict__ stream) {
+  // enumerate stages exactly as the producer / MMA warps do
+  const size_t chunk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t byte = chunk * 16;
+  if (byte >= kStreamBytes) return;
+  size_t stage;
+  int rows, in_stage;
+  const size_t big = (size_t)kBigStages * kStageBytes;
+  if (byte < big) { stage = byte / kStageBytes; in_stage = (int)(byte % kStageBytes); rows = 64; }
+  else { stage = kBigStages + (byte - big) / kSmallStageBytes; in_stage = (int)((byte - big) % kSmallStageBytes); rows = 16; }
+  // decode stage -> (layer, phase2, nb, kb, half)
+  int layer, phase2 = 0, nb, kb, half;
+  size_t s = stage;
+  half = (int)(s & 1); s >>= 1;           // pair index
+  if (s < 6) { layer = 0; nb = (int)s; kb = 0; }
+  else {
+    s -= 6;
+    // layers 1..7: 36 pairs each, layer 5 has 6 extra (phase 2)
+    layer = 1;
+    while (true) {
+      size_t n_pairs = (layer == 5) ? 42 : 36;
+      if (layer < 8 && s >= n_pairs) { s -= n_pairs; ++layer; continue; }
+      break;
+    }
+    if (layer < 8) {
+      if (layer == 5 && s >= 36) { phase2 = 1; nb = (int)(s - 36); kb = 0; }
+      else { nb = (int)(s / 6); kb = (int)(s % 6); }
+    } else {
+      nb = (int)(s / 6); kb = (int)(s % 6);   // layer 8: nb 0..3 (nb 3 = the 16-row stages)
+    }
+  }
+  (void)rows;
+  // position inside the SW128 block: 1024-byte groups of 8 rows, 16-byte chunk index XOR (row & 7)
+  const int r_local = (in_stage >> 10) * 8 + ((in_stage >> 7) & 7);
+  const int j_phys = (in_stage >> 4) & 7;
+  const int j = j_phys ^ (r_local & 7);
+  const int n = nb * kNB + r_local;
+  uint32_t out[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float a = pack_src_value(src, wf, layer, phase2, n, kb, j * 8 + 2 * q);
+    float c = pack_src_value(src, wf, layer, phase2, n, kb, j * 8 + 2 * q + 1);
+    uint32_t hi, lo;
+    split2(a, c, hi, lo);
+    out[q] = half ? lo : hi;
+  }
+  *reinterpret_cast<uint4*>(stream + byte) = make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+// per-face biases: bias[b] = base + code / appearance contributions (fold i)
+__global__ void fold_kernel(const float* __restrict__ aux, const float* __restrict__ shape_ext, const float* __restrict__ appea,
+                            float* __restrict__ bias) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kBiasFloats) return;
+  float v = aux[kAuxBaseBias + i];
+  const int layer = i / kHidden;
+  const int n = i - layer * kHidden;
+  if (layer == 0 || layer == 5) {
+    const float* w = aux + (layer == 0 ? kAuxW0c : kAuxW5c) + (size_t)n * GNRF_SHAPE_EXT_DIMS;
+    const float* c = shape_ext + (size_t)b * GNRF_SHAPE_EXT_DIMS;
+    float acc = 0.0f;
+    for (int k = 0; k < GNRF_SHAPE_EXT_DIMS; ++k) acc = fmaf(w[k], c[k], acc);
+    v += acc;
+  } else if (layer == 8 && n < kH2) {
+    const float* w = aux + kAuxW1c + (size_t)n * GNRF_APPEA_DIMS;
+    const float* c = appea + (size_t)b * GNRF_APPEA_DIMS;
+    float acc = 0.0f;
+    for (int k = 0; k < GNRF_APPEA_DIMS; ++k) acc = fmaf(w[k], c[k], acc);
+    v += acc;
+  }
+  bias[(size_t)b * kBiasFloats + i] = v;
+}
+
+}  // namespace tc
+}  // namespace gnrf
+
 using namespace gnrf;
-extern "C" size_t gnrf_mlp_tc_packed_bytes(void) { return 0; }
-extern "C" size_t gnrf_mlp_tc_bias_floats(void) { return 0; }
-extern "C" int gnrf_mlp_tc_pack(const float* const*, void*, gnrf_stream_t) { return fail(GNRF_ERR_UNSUPPORTED, "tc path not built yet"); }
-extern "C" int gnrf_mlp_tc_fold(const void*, const float*, const float*, int, float*, gnrf_stream_t) { return fail(GNRF_ERR_UNSUPPORTED, "tc path not built yet"); }
-extern "C" size_t gnrf_mlp_tc_workspace_bytes(int, int, int) { return 0; }
-extern "C" int gnrf_mlp_tc_fwd(int, const void* const*, const float* const*, const float*, const float*, const float*, int, int, int,
-                               float* const*, float* const*, float* const*, void*, size_t, gnrf_stream_t) { return fail(GNRF_ERR_UNSUPPORTED, "tc path not built yet"); }
+using namespace gnrf::tc;
+
+extern "C" size_t gnrf_mlp_tc_packed_bytes(void) { return kPackedBytes; }
+extern "C" size_t gnrf_mlp_tc_bias_floats(void) { return kBiasFloats; }
+
+extern "C" int gnrf_mlp_tc_pack(const float* const* params, void* packed, gnrf_stream_t stream) {
+  GNRF_CHECK_ARG(params && packed);
+  GNRF_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 127) == 0);
+  PackSrc src;
+  for (int i = 0; i < 12; ++i) {
+    src.w[i] = params[2 * i];
+    src.b[i] = params[2 * i + 1];
+    GNRF_CHECK_ARG(src.w[i] && src.b[i]);
+  }
+  unsigned char* p = static_cast<unsigned char*>(packed);
+  float* aux = reinterpret_cast<float*>(p + kStreamBytes);
+  cudaStream_t st = as_stream(stream);
+  fuse_head_kernel<<<kL8N, 128, 0, st>>>(src, aux);
+  pack_aux_kernel<<<148, 256, 0, st>>>(src, aux);
+  const size_t chunks = kStreamBytes / 16;
+  pack_stream_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(src, aux + kAuxWf, p);
+  GNRF_LAUNCH_CHECK();
+  count_launches(3);
+  return GNRF_OK;
+}
+
+extern "C" int gnrf_mlp_tc_fold(const void* packed, const float* shape_ext, const float* appea, int B, float* bias,
+                                gnrf_stream_t stream) {
+  GNRF_CHECK_ARG(packed && shape_ext && appea && bias && B > 0);
+  const float* aux = reinterpret_cast<const float*>(static_cast<const unsigned char*>(packed) + kStreamBytes);
+  dim3 grid(ceil_div(kBiasFloats, 128), B);
+  fold_kernel<<<grid, 128, 0, as_stream(stream)>>>(aux, shape_ext, appea, bias);
+  GNRF_LAUNCH_CHECK();
+  count_launches(1);
+  return GNRF_OK;
+}
+
+extern "C" size_t gnrf_mlp_tc_workspace_bytes(int n_branch, int B, int N_r) {
+  if (n_branch <= 0 || B <= 0 || N_r <= 0) return 0;
+  return (size_t)n_branch * B * N_r * (kH2 + 1) * sizeof(float);
+}
+
+extern "C" int gnrf_mlp_tc_fwd(int n_branch, const void* const* packed, const float* const* bias, const float* ray_dl,
+                               const float* tvecs, const float* z_edges, int B, int N_r, int N_s, float* const* feat_ray,
+                               float* const* bg_alpha, float* const* weights, void* workspace, size_t workspace_bytes,
+                               gnrf_stream_t stream) {
+  GNRF_CHECK_ARG(packed && bias && ray_dl && tvecs && z_edges && feat_ray && bg_alpha && workspace);
+  GNRF_CHECK_ARG(n_branch == 1 || n_branch == 2);
+  GNRF_CHECK_ARG(B > 0 && N_r > 0 && N_s > 0);
+  if (N_s > kTile || (kTile % N_s) != 0 || ((long long)N_r * N_s) % kTile != 0)
+    return fail(GNRF_ERR_UNSUPPORTED, "gnrf_mlp_tc_fwd: N_s=%d must divide %d and N_r*N_s=%lld must be a multiple of %d", N_s, kTile,
+                (long long)N_r * N_s, kTile);
+  if (workspace_bytes < gnrf_mlp_tc_workspace_bytes(n_branch, B, N_r))
+    return fail(GNRF_ERR_ARG, "gnrf_mlp_tc_fwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    GNRF_CUDA(cudaGetDevice(&dev));
+    GNRF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    GNRF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  }
+  FwdArgs a;
+  float* ws = static_cast<float*>(workspace);
+  for (int i = 0; i < 2; ++i) {
+    int j = i < n_branch ? i : 0;
+    GNRF_CHECK_ARG(packed[j] && bias[j] && feat_ray[j] && bg_alpha[j]);
+    a.br[i].stream = static_cast<const unsigned char*>(packed[j]);
+    a.br[i].bias = bias[j];
+    a.br[i].hc = ws + (size_t)j * B * N_r * (kH2 + 1);
+    a.br[i].wsum = a.br[i].hc + (size_t)B * N_r * kH2;
+    a.br[i].weights = weights ? weights[j] : nullptr;
+  }
+  a.ray_dl = reinterpret_cast<const float4*>(ray_dl);
+  a.tvecs = tvecs;
+  a.z_edges = z_edges;
+  a.n_branch = n_branch;
+  a.B = B;
+  a.N_r = N_r;
+  a.N_s = N_s;
+  a.tiles_per_face = (int)(((long long)N_r * N_s) / kTile);
+  a.n_items = n_branch * B * a.tiles_per_face;
+  a.dbg = nullptr;
+  {
+    const char* e = getenv("GNRF_TC_DEBUG_PTR");  // test hook: device pointer (decimal) of a [10][128][384] fp32 dump buffer
+    if (e != nullptr) a.dbg = reinterpret_cast<float*>(strtoull(e, nullptr, 10));
+  }
+  int grid = a.n_items < n_sm ? a.n_items : n_sm;
+  mlp_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
+  GNRF_LAUNCH_CHECK();
+  for (int i = 0; i < n_branch; ++i) {
+    const float* aux = reinterpret_cast<const float*>(static_cast<const unsigned char*>(packed[i]) + kStreamBytes);
+    dim3 g(ceil_div(N_r, kHeadRays), B);
+    rgb_head_kernel<<<g, 288, 0, st>>>(aux, a.br[i].hc, a.br[i].wsum, N_r, feat_ray[i], bg_alpha[i]);
+  }
+  GNRF_LAUNCH_CHECK();
+  count_launches(1 + n_branch);
+  return GNRF_OK;
+}

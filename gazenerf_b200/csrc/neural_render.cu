@@ -261,6 +261,7 @@ extern "C" int gnrf_neural_render_fwd(const float* const* params, const float* f
   launch_rgb(rgb_w(0), rgb_bi(0), featmap, C, s * s, nullptr, 0, rgb_a);
   launch_up(rgb_a, s, rgb_b);
   GNRF_LAUNCH_CHECK();
+  count_launches(2);
   const float* net = featmap;
   float* rgb_up = rgb_b;   // upsampled running rgb
   float* rgb_cur = rgb_a;  // scratch for the next sum
@@ -297,6 +298,7 @@ extern "C" int gnrf_neural_render_fwd(const float* const* params, const float* f
     }
     net = net_out;
     GNRF_LAUNCH_CHECK();
+    count_launches(last ? 5 : 6);
   }
   return GNRF_OK;
 }

@@ -46,6 +46,8 @@ int gnrf_abi_version(void);
 const char* gnrf_last_error(void);
 /* 0 if the current device is sm_100 (B200) and the kernels can run, else GNRF_ERR_UNSUPPORTED. */
 int gnrf_device_check(void);
+/* Number of libgnrf kernels launched by this process so far (monotonic; used for bench.py's "gpu_launches"). */
+unsigned long long gnrf_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Ray generation.  Replaces GenSamplePoints.forward, utils/model_utils.py:364-372.
