@@ -18,13 +18,14 @@
 //
 // On-chip layout per CTA (1 CTA / SM, 192 threads = 4 epilogue warps + 1 TMA warp + 1 MMA warp):
 //   smem  A_hi, A_lo : 6 K-blocks x [128 rows x 64 bf16], SWIZZLE_128B K-major (UMMA canonical)      2 x 96 KB
-//         W ring     : 4 x 8 KB stages, each one [64 rows x 64 bf16] SW128 block of W_hi or W_lo, streamed from the
-//                      pre-swizzled packed image in HBM/L2 by cp.async.bulk (TMA bulk copy) + mbarrier complete_tx
-//   TMEM  columns 0..383 : fp32 accumulators (6 N-blocks of 64);  384..447 : the tile's positional encoding, parked as
-//                      packed (hi,lo) bf16 pairs for the skip connection of layer 5.
+//         W ring     : 4 x 8 KB stages, each a K16/K32 slice of one accumulator block of W_hi or W_lo (no-swizzle K-major
+//                      core-matrix layout), streamed from the pre-arranged packed image in L2 by cp.async.bulk (TMA bulk
+//                      copy) + mbarrier complete_tx
+//   TMEM  columns 0..383 : fp32 accumulators (block 0 = cols 0..127, block 1 = cols 128..383);  384..447 : the tile's
+//                      positional encoding, parked as packed (hi,lo) bf16 pairs for the skip connection of layer 5.
 // Layer pipeline: the epilogue warps drain an N=384 accumulator K-block by K-block (64 columns: +bias, ReLU, hi/lo split,
 // swizzled st.shared) and release each K-block to the MMA warp through its own mbarrier, so the next layer's first
-// N-block runs while the drain is still in progress; N-blocks 1..5 then run at full rate.
+// accumulator block (N=128) runs while the drain is still in progress; the N=256 block then runs at full rate.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -40,11 +41,9 @@ constexpr int kFeat = 258;
 constexpr int kH2 = 192;                 // RGB_layer_1 width
 constexpr int kTile = 128;               // points per tile == UMMA M
 constexpr int kKB = 64;                  // K-block (bf16 elements) == 128-byte swizzle span
-constexpr int kNB = 64;                  // N-block (accumulator columns per UMMA)
 constexpr int kNumKB = kHidden / kKB;    // 6
-constexpr int kNumLayers = 9;            // L0..L7 trunk, L8 = fused (RGB_0*RGB_1 | density)
 constexpr int kL8N = 208;                // 192 + 1 density + 15 zero rows
-constexpr int kStageBytes = kNB * 128;   // 8192
+constexpr int kSlotBytes = 8192;         // W ring slot
 constexpr int kStages = 4;
 constexpr int kABlockBytes = kTile * 128;            // 16384: one K-block of A (hi or lo)
 constexpr int kABytes = kNumKB * kABlockBytes;       // 98304
@@ -53,16 +52,58 @@ constexpr int kThreads = 192;
 constexpr int kPeCol = 384;              // TMEM column where the PE is parked
 constexpr int kScratchLd = 193;          // composite scratch row stride (floats): conflict-free for both phases
 
-// ---- packed parameter image ----------------------------------------------------------------------------------------
-// bf16 stage stream, in exactly the order the MMA warp consumes it:
-//   layer 0      : nb 0..5               x {hi, lo}                       (K = 64: PE + zero pad)
-//   layer 1-4,6,7: nb 0..5 x kb 0..5     x {hi, lo}
-//   layer 5      : nb 0..5 x kb 0..5 x {hi,lo} (hidden columns)  then  nb 0..5 x {hi, lo} (PE columns)
-//   layer 8      : nb 0..2 x kb 0..5 x {hi,lo} (64 rows)  then  nb 3 x kb 0..5 x {hi,lo} (16 rows, 2 KB stages)
-constexpr int kBigStages = 6 * 2 + 7 * 36 * 2 + 6 * 2 + 3 * 6 * 2;   // 564 stages of 8 KB
-constexpr int kSmallStages = 6 * 2;                                     // 12 stages of 2 KB (the 16-row block of layer 8)
-constexpr int kSmallStageBytes = 16 * 128;
-constexpr size_t kStreamBytes = (size_t)kBigStages * kStageBytes + (size_t)kSmallStages * kSmallStageBytes;
+// ---- weight stage schedule -------------------------------------------------------------------------------------------
+// Every layer's N is split into two accumulator blocks: blk 0 = outputs [0,128) (TMEM cols 0..127, UMMA N=128) and
+// blk 1 = outputs [128,384) (cols 128..383, N=256; layer 8: [128,208), N=80).  blk 0 goes first: it only needs its own
+// 128 columns drained, so it overlaps the epilogue's drain of the previous layer; each UMMA then covers 64..128 tensor
+// cycles, which hides the ~100-cycle scalar cost of issuing one tcgen05.mma from a single thread (measured, profiles/).
+// A ring stage is a K-slice of one block: [nrows x 16] bf16 per K16 step in the no-swizzle K-major core-matrix layout
+// (8 rows x 16 B contiguous, K-halves 128 B apart, 8-row groups 256 B apart), hi and lo as separate stages; blk 0 stages
+// carry two K16 steps so that all stages are 8 KB (layer 8's N=80 block: 2.5 KB).  Stream order == consumption order:
+//   for layer: for phase (layer 5 only: hidden columns, then PE columns): for blk: for K-slice: {W_hi stage, W_lo stage}
+struct StageInfo {
+  int layer, phase2, blk, ks, nk16, half, n0, nrows;
+  uint32_t bytes;
+};
+template <class F>
+__host__ __device__ inline void for_each_stage(F&& f) {
+  for (int layer = 0; layer < 9; ++layer) {
+    const int n_phase = (layer == 5) ? 2 : 1;
+    for (int ph = 0; ph < n_phase; ++ph) {
+      const int k16n = (layer == 0 || ph == 1) ? 4 : 24;
+      for (int blk = 0; blk < 2; ++blk) {
+        const int n0 = blk ? 128 : 0;
+        const int nrows = blk ? (layer == 8 ? 80 : 256) : 128;
+        const int step = blk ? 1 : 2;
+        for (int ks = 0; ks < k16n; ks += step)
+          for (int half = 0; half < 2; ++half) {
+            StageInfo st{layer, ph, blk, ks, step, half, n0, nrows, (uint32_t)(nrows * 32 * step)};
+            f(st);
+          }
+      }
+    }
+  }
+}
+constexpr int stage_count() {
+  int n = 0;
+  for (int layer = 0; layer < 9; ++layer)
+    for (int ph = 0; ph < ((layer == 5) ? 2 : 1); ++ph) {
+      const int k16n = (layer == 0 || ph == 1) ? 4 : 24;
+      n += (k16n / 2) * 2 + k16n * 2;
+    }
+  return n;
+}
+constexpr size_t stream_bytes() {
+  size_t n = 0;
+  for (int layer = 0; layer < 9; ++layer)
+    for (int ph = 0; ph < ((layer == 5) ? 2 : 1); ++ph) {
+      const int k16n = (layer == 0 || ph == 1) ? 4 : 24;
+      n += (size_t)k16n * 2 * 32 * (128 + (layer == 8 ? 80 : 256));
+    }
+  return n;
+}
+constexpr int kNumStagesPerTile = stage_count();   // 600
+constexpr size_t kStreamBytes = stream_bytes();
 // fp32 auxiliary block (float offsets from aux base)
 constexpr int kBiasFloats = 8 * kHidden + kL8N;                       // 3280 per face
 constexpr size_t kAuxBaseBias = 0;                                    // [3280] face-independent part of every bias
@@ -81,7 +122,7 @@ __host__ __device__ inline int bias_offset(int layer) { return layer * kHidden; 
 constexpr int kSmemAHi = 0;
 constexpr int kSmemALo = kABytes;
 constexpr int kSmemRing = 2 * kABytes;                       // 196608
-constexpr int kSmemBars = kSmemRing + kStages * kStageBytes; // 229376
+constexpr int kSmemBars = kSmemRing + kStages * kSlotBytes;  // 229376
 constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarAReady = 2 * kStages, kBarAccFull = kBarAReady + kNumKB,
               kBarAFree = kBarAccFull + 1, kNumBars = kBarAFree + 1;
 constexpr int kSmemMisc = kSmemBars + kNumBars * 8;          // tmem ptr, scan scratch
@@ -163,15 +204,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
       for (int item = blockIdx.x; item < args.n_items; item += gridDim.x) {
         const int branch = item % args.n_branch;
         const unsigned char* src = args.br[branch].stream;
-        // 564 full stages + 12 small ones, consumed strictly in order
-        for (int s = 0; s < kBigStages + kSmallStages; ++s) {
-          const uint32_t bytes = (s < kBigStages) ? (uint32_t)kStageBytes : (uint32_t)kSmallStageBytes;
+        for_each_stage([&](const StageInfo& st) {  // strictly in consumption order
           mbar_wait(bar(kBarWEmpty + slot), phase ^ 1);
-          mbar_arrive_expect_tx(bar(kBarWFull + slot), bytes);
-          bulk_g2s(smem_base + kSmemRing + slot * kStageBytes, src, bytes, bar(kBarWFull + slot));
-          src += bytes;
+          mbar_arrive_expect_tx(bar(kBarWFull + slot), st.bytes);
+          bulk_g2s(smem_base + kSmemRing + slot * kSlotBytes, src, st.bytes, bar(kBarWFull + slot));
+          src += st.bytes;
           if (++slot == kStages) { slot = 0; phase ^= 1; }
-        }
+        });
       }
     }
     __syncwarp();
@@ -180,68 +219,72 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
     if (lane == 0) {
       uint32_t slot = 0, wphase = 0;
       uint32_t a_phase = 0;  // bit kb = parity of the next completion of a_ready[kb]
-      constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64);
-      constexpr uint32_t idesc16 = umma_idesc_bf16(128, 16);
       const uint64_t a_hi_desc0 = umma_desc_sw128(smem_base + kSmemAHi);
       const uint64_t a_lo_desc0 = umma_desc_sw128(smem_base + kSmemALo);
 
-      // one (nb, kb) step = two ring stages: W_hi block (A_hi*W_hi + A_lo*W_hi), then W_lo block (A_hi*W_lo)
-      auto step = [&](int nb_col, uint32_t idesc, int a_kb, bool fresh) {
-        const uint64_t a_hi = a_hi_desc0 + (uint64_t)((a_kb * kABlockBytes) >> 4);
-        const uint64_t a_lo = a_lo_desc0 + (uint64_t)((a_kb * kABlockBytes) >> 4);
-        const uint32_t d = tmem_base + (uint32_t)nb_col;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          mbar_wait(bar(kBarWFull + slot), wphase);
-          tc_fence_after_sync();
-          const uint64_t b = umma_desc_sw128(smem_base + kSmemRing + slot * kStageBytes);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 4 x K16 inside the 128-byte swizzle span: +32 B per step
-            if (half == 0) {
-              umma_ss(d, a_hi + 2 * k, b + 2 * k, idesc, (fresh && k == 0) ? 0u : 1u);
-              umma_ss(d, a_lo + 2 * k, b + 2 * k, idesc, 1u);
-            } else {
-              umma_ss(d, a_hi + 2 * k, b + 2 * k, idesc, 1u);
-            }
+      // One ring stage: nk16 K16-steps of one accumulator block.  W_hi stage -> A_hi*W_hi + A_lo*W_hi ; W_lo stage -> A_hi*W_lo.
+      auto do_stage = [&](uint32_t d_col, uint32_t idesc, int a_k16, int nk16, int nrows, int half, bool fresh) {
+        mbar_wait(bar(kBarWFull + slot), wphase);
+        tc_fence_after_sync();
+        const uint32_t b_addr = smem_base + kSmemRing + slot * kSlotBytes;
+        const uint32_t d = tmem_base + d_col;
+        for (int i = 0; i < nk16; ++i) {
+          const int k16 = a_k16 + i;
+          // A: SW128 K-block (k16 >> 2), +32 B per K16 step inside the 128-byte swizzle span
+          const uint64_t a_off = (uint64_t)(((k16 >> 2) * kABlockBytes + (k16 & 3) * 32) >> 4);
+          const uint64_t b = umma_desc_nosw(b_addr + (uint32_t)(i * nrows * 32));
+          if (half == 0) {
+            umma_ss(d, a_hi_desc0 + a_off, b, idesc, (fresh && i == 0) ? 0u : 1u);
+            umma_ss(d, a_lo_desc0 + a_off, b, idesc, 1u);
+          } else {
+            umma_ss(d, a_hi_desc0 + a_off, b, idesc, 1u);
           }
-          umma_commit(bar(kBarWEmpty + slot));
-          if (++slot == kStages) { slot = 0; wphase ^= 1; }
         }
+        umma_commit(bar(kBarWEmpty + slot));
+        if (++slot == kStages) { slot = 0; wphase ^= 1; }
       };
       auto wait_a = [&](int kb) {
         mbar_wait(bar(kBarAReady + kb), (a_phase >> kb) & 1u);
         a_phase ^= (1u << kb);
         tc_fence_after_sync();
       };
+      // all K-slices of both accumulator blocks; a_kb0 >= 0 pins the A operand to one K-block (the PE passes)
+      auto run_pass = [&](int layer, int k16n, bool pe_pass, bool fresh_start) {
+        for (int blk = 0; blk < 2; ++blk) {
+          const int nrows = blk ? (layer == 8 ? 80 : 256) : 128;
+          const uint32_t idesc = umma_idesc_bf16(128, nrows);
+          const uint32_t d_col = blk ? 128u : 0u;
+          const int step = blk ? 1 : 2;
+          for (int ks = 0; ks < k16n; ks += step) {
+            // blk 0 touches each A K-block first; blk 0's first UMMA overwrites columns 0..127 = K-blocks 0 and 1 of the
+            // previous accumulator, so both must have been drained before it is issued.
+            if (blk == 0 && !pe_pass && (ks & 3) == 0) {
+              if (ks == 0) { wait_a(0); wait_a(1); }
+              else if (ks >= 8) wait_a(ks >> 2);
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) do_stage(d_col, idesc, ks, step, nrows, half, fresh_start && ks == 0);
+          }
+        }
+      };
 
       for (int item = blockIdx.x; item < args.n_items; item += gridDim.x) {
         // ---- layer 0: K = 64 (PE in K-block 0)
         wait_a(0);
-        for (int nb = 0; nb < 6; ++nb) step(nb * kNB, idesc64, 0, true);
+        run_pass(0, 4, true, true);
         umma_commit(bar(kBarAccFull));
-        // ---- layers 1..7
-        for (int layer = 1; layer < 8; ++layer) {
-          for (int nb = 0; nb < 6; ++nb)
-            for (int kb = 0; kb < kNumKB; ++kb) {
-              if (nb == 0) wait_a(kb);
-              step(nb * kNB, idesc64, kb, kb == 0);
-            }
+        // ---- layers 1..8 (layer 8: [RGB_0*RGB_1 (192) | density (1) | pad] = N 128 + 80)
+        for (int layer = 1; layer < 9; ++layer) {
+          run_pass(layer, 24, false, true);
           if (layer == 5) {
             // skip connection: the PE columns of FeaExt_module_5 (models/mlp_nerf.py:106-107); the epilogue re-stages
             // the parked PE into K-block 0 once every read of the hidden K-blocks has completed.
             umma_commit(bar(kBarAFree));
             wait_a(0);
-            for (int nb = 0; nb < 6; ++nb) step(nb * kNB, idesc64, 0, false);
+            run_pass(5, 4, true, false);
           }
           umma_commit(bar(kBarAccFull));
         }
-        // ---- layer 8: [RGB_0*RGB_1 (192) | density (1) | pad] = 3 x N64 + 1 x N16
-        for (int nb = 0; nb < 4; ++nb)
-          for (int kb = 0; kb < kNumKB; ++kb) {
-            if (nb == 0) wait_a(kb);
-            step(nb * kNB, nb < 3 ? idesc64 : idesc16, kb, kb == 0);
-          }
-        umma_commit(bar(kBarAccFull));
       }
     }
     __syncwarp();
@@ -557,66 +600,51 @@ __global__ void pack_aux_kernel(PackSrc src, float* __restrict__ aux) {
   for (int i = tid; i < kFeat; i += nth) aux[kAuxB2 + i] = src.b[11][i];
 }
 
-// One thread per 16-byte chunk (8 bf16) of the stage stream.
-__device__ __forceinline__ float pack_src_value(const PackSrc& src, const float* wf, int layer, int phase2, int n, int kb, int kl) {
+// Stage table (built on the host from for_each_stage, uploaded once per process).
+struct StageRec {
+  uint32_t byte_off;
+  uint16_t ks, nk16, n0, nrows;
+  uint8_t layer, phase2, half, pad;
+};
+__device__ StageRec g_stage_table[kNumStagesPerTile];
+
+__device__ __forceinline__ float pack_src_value(const PackSrc& src, const float* wf, int layer, int phase2, int n, int k) {
   const int vp = GNRF_PE_DIMS + GNRF_SHAPE_EXT_DIMS;
-  if (layer == 0) return (kl < GNRF_PE_DIMS) ? src.w[0][(size_t)n * vp + kl] : 0.0f;
+  if (layer == 0) return (k < GNRF_PE_DIMS) ? src.w[0][(size_t)n * vp + k] : 0.0f;
   if (layer == 5) {
     const size_t ld = vp + kHidden;
-    if (phase2) return (kl < GNRF_PE_DIMS) ? src.w[5][(size_t)n * ld + kl] : 0.0f;
-    return src.w[5][(size_t)n * ld + vp + kb * kKB + kl];
+    if (phase2) return (k < GNRF_PE_DIMS) ? src.w[5][(size_t)n * ld + k] : 0.0f;
+    return src.w[5][(size_t)n * ld + vp + k];
   }
-  if (layer == 8) return wf[(size_t)n * kHidden + kb * kKB + kl];
-  return src.w[layer][(size_t)n * kHidden + kb * kKB + kl];
+  if (layer == 8) return wf[(size_t)n * kHidden + k];
+  return src.w[layer][(size_t)n * kHidden + k];
 }
 
+// One CTA per stage, one thread per 16-byte chunk (8 bf16 along K of one row).
+// Chunk order inside a K16 slice of `nrows` rows = the no-swizzle K-major core-matrix layout:
+//   chunk = (row / 8) * 16 + k_half * 8 + (row % 8)        (8 rows x 16 B contiguous; K-halves 128 B apart; groups 256 B apart)
 __global__ void pack_stream_kernel(PackSrc src, const float* __restrict__ wf, unsigned char* __restrict__ stream) {
-  // enumerate stages exactly as the producer / MMA warps do
-  const size_t chunk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t byte = chunk * 16;
-  if (byte >= kStreamBytes) return;
-  size_t stage;
-  int rows, in_stage;
-  const size_t big = (size_t)kBigStages * kStageBytes;
-  if (byte < big) { stage = byte / kStageBytes; in_stage = (int)(byte % kStageBytes); rows = 64; }
-  else { stage = kBigStages + (byte - big) / kSmallStageBytes; in_stage = (int)((byte - big) % kSmallStageBytes); rows = 16; }
-  // decode stage -> (layer, phase2, nb, kb, half)
-  int layer, phase2 = 0, nb, kb, half;
-  size_t s = stage;
-  half = (int)(s & 1); s >>= 1;           // pair index
-  if (s < 6) { layer = 0; nb = (int)s; kb = 0; }
-  else {
-    s -= 6;
-    // layers 1..7: 36 pairs each, layer 5 has 6 extra (phase 2)
-    layer = 1;
-    while (true) {
-      size_t n_pairs = (layer == 5) ? 42 : 36;
-      if (layer < 8 && s >= n_pairs) { s -= n_pairs; ++layer; continue; }
-      break;
-    }
-    if (layer < 8) {
-      if (layer == 5 && s >= 36) { phase2 = 1; nb = (int)(s - 36); kb = 0; }
-      else { nb = (int)(s / 6); kb = (int)(s % 6); }
-    } else {
-      nb = (int)(s / 6); kb = (int)(s % 6);   // layer 8: nb 0..3 (nb 3 = the 16-row stages)
-    }
-  }
-  (void)rows;
-  // position inside the SW128 block: 1024-byte groups of 8 rows, 16-byte chunk index XOR (row & 7)
-  const int r_local = (in_stage >> 10) * 8 + ((in_stage >> 7) & 7);
-  const int j_phys = (in_stage >> 4) & 7;
-  const int j = j_phys ^ (r_local & 7);
-  const int n = nb * kNB + r_local;
-  uint32_t out[4];
+  const StageRec st = g_stage_table[blockIdx.x];
+  const int chunks_per_slice = st.nrows * 2;
+  const int n_chunks = chunks_per_slice * st.nk16;
+  for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) {
+    const int slice = c / chunks_per_slice;
+    const int rem = c - slice * chunks_per_slice;
+    const int row = (rem >> 4) * 8 + (rem & 7);
+    const int k_half = (rem >> 3) & 1;
+    const int n = st.n0 + row;
+    const int k0 = (st.ks + slice) * 16 + k_half * 8;
+    uint32_t out[4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float a = pack_src_value(src, wf, layer, phase2, n, kb, j * 8 + 2 * q);
-    float c = pack_src_value(src, wf, layer, phase2, n, kb, j * 8 + 2 * q + 1);
-    uint32_t hi, lo;
-    split2(a, c, hi, lo);
-    out[q] = half ? lo : hi;
+    for (int q = 0; q < 4; ++q) {
+      float a = pack_src_value(src, wf, st.layer, st.phase2, n, k0 + 2 * q);
+      float b = pack_src_value(src, wf, st.layer, st.phase2, n, k0 + 2 * q + 1);
+      uint32_t hi, lo;
+      split2(a, b, hi, lo);
+      out[q] = st.half ? lo : hi;
+    }
+    *reinterpret_cast<uint4*>(stream + st.byte_off + (size_t)c * 16) = make_uint4(out[0], out[1], out[2], out[3]);
   }
-  *reinterpret_cast<uint4*>(stream + byte) = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
 // per-face biases: bias[b] = base + code / appearance contributions (fold i)
@@ -665,10 +693,25 @@ extern "C" int gnrf_mlp_tc_pack(const float* const* params, void* packed, gnrf_s
   unsigned char* p = static_cast<unsigned char*>(packed);
   float* aux = reinterpret_cast<float*>(p + kStreamBytes);
   cudaStream_t st = as_stream(stream);
+  static bool table_ready = false;
+  if (!table_ready) {
+    static StageRec host_table[kNumStagesPerTile];
+    int i = 0;
+    uint32_t off = 0;
+    for_each_stage([&](const StageInfo& si) {
+      StageRec& r = host_table[i++];
+      r.byte_off = off;
+      r.ks = (uint16_t)si.ks; r.nk16 = (uint16_t)si.nk16; r.n0 = (uint16_t)si.n0; r.nrows = (uint16_t)si.nrows;
+      r.layer = (uint8_t)si.layer; r.phase2 = (uint8_t)si.phase2; r.half = (uint8_t)si.half; r.pad = 0;
+      off += si.bytes;
+    });
+    if (i != kNumStagesPerTile || off != kStreamBytes) return fail(GNRF_ERR_CUDA, "gnrf_mlp_tc_pack: stage table mismatch (%d, %u)", i, off);
+    GNRF_CUDA(cudaMemcpyToSymbolAsync(g_stage_table, host_table, sizeof(host_table), 0, cudaMemcpyHostToDevice, st));
+    table_ready = true;
+  }
   fuse_head_kernel<<<kL8N, 128, 0, st>>>(src, aux);
   pack_aux_kernel<<<148, 256, 0, st>>>(src, aux);
-  const size_t chunks = kStreamBytes / 16;
-  pack_stream_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(src, aux + kAuxWf, p);
+  pack_stream_kernel<<<kNumStagesPerTile, 256, 0, st>>>(src, aux + kAuxWf, p);
   GNRF_LAUNCH_CHECK();
   count_launches(3);
   return GNRF_OK;

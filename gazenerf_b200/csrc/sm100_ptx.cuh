@@ -113,6 +113,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// No-swizzle ("interleave") K-major operand: 8-row x 16-byte core matrices stored contiguously (128 B); the two K-halves of a
+// K16 step are LBO = 128 B apart, consecutive 8-row groups SBO = 256 B apart  => a dense [rows x 16] bf16 slice of rows*32 B.
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(128 >> 4) << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
 // Instruction descriptor for kind::f16 with bf16 A/B (both K-major), fp32 accumulate, shape M x N (x16).
 //   [4,6) D fmt = 1 (f32) | [7,10) A fmt = 1 (bf16) | [10,13) B fmt = 1 (bf16) | [15] A major = 0 | [16] B major = 0
 //   [17,23) N >> 3 | [24,29) M >> 4

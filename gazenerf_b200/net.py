@@ -191,6 +191,8 @@ class GazeNeRFNet(nn.Module):
         self._tvals_cache: Dict[Tuple[int, str], torch.Tensor] = {}
         self.last_stages: Optional[Dict[str, torch.Tensor]] = None
         self.keep_stages = False
+        # bench hook: when a list, (start, end) CUDA events bracketing the radiance-MLP launches are appended per forward
+        self.mlp_events: Optional[list] = None
 
     # ------------------------------------------------------------------ helpers
     def _tc_supported(self, n_s: int) -> bool:
@@ -308,8 +310,14 @@ class GazeNeRFNet(nn.Module):
 
             impl = self.mlp_impl or "tc"
             impl_c = impl if (impl != "tc" or self._tc_supported(n_s)) else "simt"
+            if self.mlp_events is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
             feat, alpha, wts = self._render_branches(ray_dl, tvecs, z_edges, shape_ext, appea, n_s, impl_c,
                                                      want_weights=self.hier_sampling or self.keep_stages)
+            if self.mlp_events is not None:
+                ev1.record()
+                self.mlp_events.append((ev0, ev1))
             if self.keep_stages:
                 self.last_stages.update({"ray_dl": ray_dl, "z_edges": z_edges, "feat_face": feat[0], "feat_eyes": feat[1],
                                          "bg_alpha_face": alpha[0], "bg_alpha_eyes": alpha[1], "w_face": wts[0], "w_eyes": wts[1]})
