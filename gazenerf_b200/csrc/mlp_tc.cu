@@ -17,16 +17,22 @@
 //         is composited per ray and RGB_layer_2 is applied once per ray by rgb_head_kernel (fp32 FMA).
 //
 // On-chip layout per CTA (1 CTA / SM, 192 threads = 4 epilogue warps + 1 TMA warp + 1 MMA warp):
-//   smem  A_hi, A_lo : 6 K-blocks x [128 rows x 64 bf16], SWIZZLE_128B K-major (UMMA canonical)      2 x 96 KB
-//         W ring     : 4 x 8 KB stages, each a K16/K32 slice of one accumulator block of W_hi or W_lo (no-swizzle K-major
-//                      core-matrix layout), streamed from the pre-arranged packed image in L2 by cp.async.bulk (TMA bulk
-//                      copy) + mbarrier complete_tx
-//   TMEM  columns 0..383 : fp32 accumulators (block 0 = cols 0..127, block 1 = cols 128..383);  384..447 : the tile's
-//                      positional encoding, parked as packed (hi,lo) bf16 pairs for the skip connection of layer 5.
+//   smem  A_hi       : 6 K-blocks x [128 rows x 64 bf16], SWIZZLE_128B K-major (UMMA canonical)          96 KB
+//         A_lo[4..5] : K-blocks 4,5 of the low halves, same layout                                        32 KB
+//         W ring     : 6 x 16 KB stages; a stage = one K-slice of one accumulator block, W_hi then W_lo (no-swizzle
+//                      K-major core-matrix layout), streamed from the pre-arranged packed image in L2 by cp.async.bulk
+//                      (TMA bulk copy) + mbarrier complete_tx                                              96 KB
+//   TMEM  columns 0..383   : fp32 accumulators (block 0 = cols 0..127, block 1 = cols 128..383)
+//         columns 384..511 : A_lo K-blocks 0..3 as packed bf16 pairs (32 columns per K-block) -> TS-mode UMMA reads the A
+//                      operand straight from tensor memory; this is what frees 64 KB of smem for a ring deep enough to
+//                      cover the L2 -> smem latency (profiles/: the 32 KB ring version was latency/issue bound at 39 %).
 // Layer pipeline: the epilogue warps drain an N=384 accumulator K-block by K-block (64 columns: +bias, ReLU, hi/lo split,
-// swizzled st.shared) and release each K-block to the MMA warp through its own mbarrier, so the next layer's first
-// accumulator block (N=128) runs while the drain is still in progress; the N=256 block then runs at full rate.
+// swizzled st.shared / tcgen05.st) and release each K-block to the MMA warp through its own mbarrier, so the next layer's
+// first accumulator block (N=128) runs while the drain is still in progress; the N=256 block then runs at full rate.
+// The positional encoding needed again by layer 5 (skip connection) is recomputed by the epilogue warps while they would
+// otherwise wait for layer 5's first pass.
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -43,13 +49,14 @@ constexpr int kTile = 128;               // points per tile == UMMA M
 constexpr int kKB = 64;                  // K-block (bf16 elements) == 128-byte swizzle span
 constexpr int kNumKB = kHidden / kKB;    // 6
 constexpr int kL8N = 208;                // 192 + 1 density + 15 zero rows
-constexpr int kSlotBytes = 8192;         // W ring slot
-constexpr int kStages = 4;
+constexpr int kSlotBytes = 16384;        // W ring slot (W_hi slice + W_lo slice)
+constexpr int kStages = 6;
+constexpr int kALoTmemKB = 4;            // A_lo K-blocks 0..3 live in TMEM, 4..5 in smem
+constexpr int kALoCol = 384;             // first TMEM column of A_lo
 constexpr int kABlockBytes = kTile * 128;            // 16384: one K-block of A (hi or lo)
 constexpr int kABytes = kNumKB * kABlockBytes;       // 98304
 constexpr int kEpiThreads = 128;
 constexpr int kThreads = 192;
-constexpr int kPeCol = 384;              // TMEM column where the PE is parked
 constexpr int kScratchLd = 193;          // composite scratch row stride (floats): conflict-free for both phases
 
 // ---- weight stage schedule -------------------------------------------------------------------------------------------
@@ -58,12 +65,13 @@ constexpr int kScratchLd = 193;          // composite scratch row stride (floats
 // 128 columns drained, so it overlaps the epilogue's drain of the previous layer; each UMMA then covers 64..128 tensor
 // cycles, which hides the ~100-cycle scalar cost of issuing one tcgen05.mma from a single thread (measured, profiles/).
 // A ring stage is a K-slice of one block: [nrows x 16] bf16 per K16 step in the no-swizzle K-major core-matrix layout
-// (8 rows x 16 B contiguous, K-halves 128 B apart, 8-row groups 256 B apart), hi and lo as separate stages; blk 0 stages
-// carry two K16 steps so that all stages are 8 KB (layer 8's N=80 block: 2.5 KB).  Stream order == consumption order:
-//   for layer: for phase (layer 5 only: hidden columns, then PE columns): for blk: for K-slice: {W_hi stage, W_lo stage}
+// (8 rows x 16 B contiguous, K-halves 128 B apart, 8-row groups 256 B apart), the W_hi slice followed by the W_lo slice;
+// blk 0 stages carry two K16 steps so that all stages are 16 KB = 384 tensor cycles of work (layer 8's N=80 block: 5 KB),
+// enough to hide the ~200-cycle scalar cost of one stage (mbarrier try_wait, fences, issue).  Stream == consumption order:
+//   for layer: for phase (layer 5 only: hidden columns, then PE columns): for blk: for K-slice: one stage
 struct StageInfo {
-  int layer, phase2, blk, ks, nk16, half, n0, nrows;
-  uint32_t bytes;
+  int layer, phase2, blk, ks, nk16, n0, nrows;
+  uint32_t bytes;  // hi + lo
 };
 template <class F>
 __host__ __device__ inline void for_each_stage(F&& f) {
@@ -75,11 +83,10 @@ __host__ __device__ inline void for_each_stage(F&& f) {
         const int n0 = blk ? 128 : 0;
         const int nrows = blk ? (layer == 8 ? 80 : 256) : 128;
         const int step = blk ? 1 : 2;
-        for (int ks = 0; ks < k16n; ks += step)
-          for (int half = 0; half < 2; ++half) {
-            StageInfo st{layer, ph, blk, ks, step, half, n0, nrows, (uint32_t)(nrows * 32 * step)};
-            f(st);
-          }
+        for (int ks = 0; ks < k16n; ks += step) {
+          StageInfo st{layer, ph, blk, ks, step, n0, nrows, (uint32_t)(2 * nrows * 32 * step)};
+          f(st);
+        }
       }
     }
   }
@@ -89,7 +96,7 @@ constexpr int stage_count() {
   for (int layer = 0; layer < 9; ++layer)
     for (int ph = 0; ph < ((layer == 5) ? 2 : 1); ++ph) {
       const int k16n = (layer == 0 || ph == 1) ? 4 : 24;
-      n += (k16n / 2) * 2 + k16n * 2;
+      n += (k16n / 2) + k16n;
     }
   return n;
 }
@@ -102,7 +109,7 @@ constexpr size_t stream_bytes() {
     }
   return n;
 }
-constexpr int kNumStagesPerTile = stage_count();   // 600
+constexpr int kNumStagesPerTile = stage_count();   // 300
 constexpr size_t kStreamBytes = stream_bytes();
 // fp32 auxiliary block (float offsets from aux base)
 constexpr int kBiasFloats = 8 * kHidden + kL8N;                       // 3280 per face
@@ -120,9 +127,9 @@ __host__ __device__ inline int bias_offset(int layer) { return layer * kHidden; 
 
 // ---- shared memory map ---------------------------------------------------------------------------------------------
 constexpr int kSmemAHi = 0;
-constexpr int kSmemALo = kABytes;
-constexpr int kSmemRing = 2 * kABytes;                       // 196608
-constexpr int kSmemBars = kSmemRing + kStages * kSlotBytes;  // 229376
+constexpr int kSmemALo45 = kABytes;                                         // A_lo K-blocks 4,5
+constexpr int kSmemRing = kABytes + (kNumKB - kALoTmemKB) * kABlockBytes;   // 131072
+constexpr int kSmemBars = kSmemRing + kStages * kSlotBytes;                 // 229376
 constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarAReady = 2 * kStages, kBarAccFull = kBarAReady + kNumKB,
               kBarAFree = kBarAccFull + 1, kNumBars = kBarAFree + 1;
 constexpr int kSmemMisc = kSmemBars + kNumBars * 8;          // tmem ptr, scan scratch
@@ -142,7 +149,8 @@ struct FwdArgs {
   const float* tvecs;
   const float* z_edges;
   int n_branch, B, N_r, N_s, tiles_per_face, n_items;
-  float* dbg;  // optional [9][128][384] dump of tile 0 activations
+  float* dbg;        // optional [10][128][384] dump of tile 0 activations
+  long long* prof;   // optional timeline of CTA 0: [item < 4][layer 0..9][16] clock64 stamps / stall sums
 };
 
 // =====================================================================================================================
@@ -150,23 +158,51 @@ struct FwdArgs {
 // =====================================================================================================================
 __device__ __forceinline__ uint32_t a_row_offset(int row) { return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128); }
 
-// Write 64 consecutive K values of one row (as hi/lo bf16) into K-block `kb` of A.  v[] already activated.
-__device__ __forceinline__ void store_a_row64(uint32_t smem_base, int kb, int row, const float (&v)[64]) {
-  const uint32_t row_off = (uint32_t)kb * kABlockBytes + a_row_offset(row);
+// Write 64 consecutive K values of one row (already activated) into K-block `kb` of the A operand:
+// hi halves -> smem (SW128 K-major); lo halves -> TMEM columns (kb < 4, packed pairs, TS-mode operand) or smem (kb 4,5).
+__device__ __forceinline__ void split_row64(const float (&v)[64], uint32_t (&hi)[32], uint32_t (&lo)[32]) {
+#pragma unroll
+  for (int q = 0; q < 32; ++q) split2(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
+}
+__device__ __forceinline__ void st_shared_row128(uint32_t addr_row, uint32_t sw, const uint32_t (&w)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr_row + (((uint32_t)j ^ sw) << 4)), "r"(w[4 * j]),
+                 "r"(w[4 * j + 1]), "r"(w[4 * j + 2]), "r"(w[4 * j + 3])
+                 : "memory");
+}
+__device__ __forceinline__ void store_a_kblock(uint32_t smem_base, uint32_t t_lane, int kb, int row, const uint32_t (&hi)[32],
+                                               const uint32_t (&lo)[32]) {
+  const uint32_t row_off = a_row_offset(row);
   const uint32_t sw = (uint32_t)(row & 7);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) split2(v[8 * j + 2 * q], v[8 * j + 2 * q + 1], hi[q], lo[q]);
-    const uint32_t off = row_off + (((uint32_t)j ^ sw) << 4);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_base + kSmemAHi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
-                 "r"(hi[3])
-                 : "memory");
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_base + kSmemALo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]),
-                 "r"(lo[3])
-                 : "memory");
+  st_shared_row128(smem_base + kSmemAHi + (uint32_t)kb * kABlockBytes + row_off, sw, hi);
+  if (kb < kALoTmemKB) {
+    tmem_st32(t_lane + kALoCol + kb * 32, lo);
+    tmem_wait_st();
+  } else {
+    st_shared_row128(smem_base + kSmemALo45 + (uint32_t)(kb - kALoTmemKB) * kABlockBytes + row_off, sw, lo);
   }
+}
+
+// Positional encoding of one sample point, K order = [x,y,z, f0: sin xyz, cos xyz, f1: ...] + zero pad (63 -> 64).
+// utils/model_utils.py:263-280; pts = o + ((d * l) * z) with individually rounded ops (:315).
+__device__ __forceinline__ void compute_pe(const float* __restrict__ tvec, const float4 dl, float z, float (&pe)[64]) {
+  const float dc[3] = {dl.x, dl.y, dl.z};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float x = __fadd_rn(tvec[c], __fmul_rn(__fmul_rn(dc[c], dl.w), z));
+    pe[c] = x;
+    float f = 1.0f;
+#pragma unroll
+    for (int q = 0; q < 10; ++q) {
+      float sv, cv;
+      sincosf(__fmul_rn(x, f), &sv, &cv);  // freq = 2^q exactly
+      pe[3 + 6 * q + c] = sv;
+      pe[6 + 6 * q + c] = cv;
+      f *= 2.0f;
+    }
+  }
+  pe[63] = 0.0f;
 }
 
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args) {
@@ -216,78 +252,117 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
     __syncwarp();
   } else if (warp == 5) {
     // =============================================== MMA issuer =================================================
-    if (lane == 0) {
+    // The whole warp runs this loop converged on warp-uniform values; one elected lane issues the tcgen05 instructions.
+    {
       uint32_t slot = 0, wphase = 0;
       uint32_t a_phase = 0;  // bit kb = parity of the next completion of a_ready[kb]
-      const uint64_t a_hi_desc0 = umma_desc_sw128(smem_base + kSmemAHi);
-      const uint64_t a_lo_desc0 = umma_desc_sw128(smem_base + kSmemALo);
-
-      // One ring stage: nk16 K16-steps of one accumulator block.  W_hi stage -> A_hi*W_hi + A_lo*W_hi ; W_lo stage -> A_hi*W_lo.
-      auto do_stage = [&](uint32_t d_col, uint32_t idesc, int a_k16, int nk16, int nrows, int half, bool fresh) {
-        mbar_wait(bar(kBarWFull + slot), wphase);
-        tc_fence_after_sync();
-        const uint32_t b_addr = smem_base + kSmemRing + slot * kSlotBytes;
-        const uint32_t d = tmem_base + d_col;
-        for (int i = 0; i < nk16; ++i) {
-          const int k16 = a_k16 + i;
-          // A: SW128 K-block (k16 >> 2), +32 B per K16 step inside the 128-byte swizzle span
-          const uint64_t a_off = (uint64_t)(((k16 >> 2) * kABlockBytes + (k16 & 3) * 32) >> 4);
-          const uint64_t b = umma_desc_nosw(b_addr + (uint32_t)(i * nrows * 32));
-          if (half == 0) {
-            umma_ss(d, a_hi_desc0 + a_off, b, idesc, (fresh && i == 0) ? 0u : 1u);
-            umma_ss(d, a_lo_desc0 + a_off, b, idesc, 1u);
-          } else {
-            umma_ss(d, a_hi_desc0 + a_off, b, idesc, 1u);
-          }
+      bool prof_on = false;
+      long long w_stall = 0, a_stall = 0;
+      int prof_item = 0;
+      auto stamp = [&](int layer, int k) {
+        if (prof_on && lane == 0) {
+          long long* p = args.prof + ((size_t)prof_item * 10 + layer) * 16;
+          p[k] = clock64(); p[k + 1] = w_stall; p[k + 2] = a_stall;
         }
-        umma_commit(bar(kBarWEmpty + slot));
+      };
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t sbase_u = __shfl_sync(0xffffffffu, smem_base, 0);
+      constexpr uint32_t kDescHiSw128 = (uint32_t)((1024 >> 4) | (1u << 14) | (2u << 29));   // SBO, version, SWIZZLE_128B
+      constexpr uint32_t kDescHiNoSw = (uint32_t)((256 >> 4) | (1u << 14));                  // SBO, version, no swizzle
+      constexpr uint32_t kDescLoLboSw = 1u << 16, kDescLoLboNo = (128u >> 4) << 16;
+      const uint32_t a_hi_lo0 = (((sbase_u + kSmemAHi) >> 4) & 0x3FFFu) | kDescLoLboSw;
+      const uint32_t a_lo45_lo0 = (((sbase_u + kSmemALo45) >> 4) & 0x3FFFu) | kDescLoLboSw;
+      auto mk = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
+
+      // One ring stage = NK16 K16-steps of one accumulator block: per step  A_hi*W_hi + A_lo*W_hi + A_hi*W_lo.
+      auto do_stage = [&](auto nrows_c, auto nk16_c, uint32_t d_col, int a_k16, bool fresh) {
+        constexpr int NROWS = decltype(nrows_c)::value, NK16 = decltype(nk16_c)::value;
+        constexpr uint32_t idesc = umma_idesc_bf16(128, NROWS);
+        constexpr uint32_t kSliceU = (uint32_t)((NROWS * 32) >> 4);  // one K16 slice, in 16-byte units
+        const long long tw0 = prof_on ? clock64() : 0;
+        mbar_wait(bar(kBarWFull + slot), wphase);
+        if (prof_on) w_stall += clock64() - tw0;
+        tc_fence_after_sync();
+        const uint32_t b_hi0 = (((sbase_u + kSmemRing + slot * kSlotBytes) >> 4) & 0x3FFFu) | kDescLoLboNo;
+        const uint32_t b_lo0 = b_hi0 + NK16 * kSliceU;
+        const uint32_t d = tmem_u + d_col;
+        if (elect_one()) {
+#pragma unroll
+          for (int i = 0; i < NK16; ++i) {
+            const int k16 = a_k16 + i;
+            const int kb = k16 >> 2;
+            // A_hi: SW128 K-block kb, +32 B per K16 step inside the 128-byte swizzle span
+            const uint64_t a_hi = mk(a_hi_lo0 + (uint32_t)((kb * kABlockBytes + (k16 & 3) * 32) >> 4), kDescHiSw128);
+            const uint64_t b_hi = mk(b_hi0 + i * kSliceU, kDescHiNoSw);
+            const uint64_t b_lo = mk(b_lo0 + i * kSliceU, kDescHiNoSw);
+            umma_ss(d, a_hi, b_hi, idesc, (fresh && i == 0) ? 0u : 1u);
+            if (kb < kALoTmemKB)
+              umma_ts(d, tmem_u + (uint32_t)(kALoCol + kb * 32 + (k16 & 3) * 8), b_hi, idesc, 1u);
+            else
+              umma_ss(d, mk(a_lo45_lo0 + (uint32_t)(((kb - kALoTmemKB) * kABlockBytes + (k16 & 3) * 32) >> 4), kDescHiSw128), b_hi,
+                      idesc, 1u);
+            umma_ss(d, a_hi, b_lo, idesc, 1u);
+          }
+          umma_commit(bar(kBarWEmpty + slot));
+        }
+        __syncwarp();
         if (++slot == kStages) { slot = 0; wphase ^= 1; }
       };
       auto wait_a = [&](int kb) {
+        const long long ta0 = prof_on ? clock64() : 0;
         mbar_wait(bar(kBarAReady + kb), (a_phase >> kb) & 1u);
+        if (prof_on) a_stall += clock64() - ta0;
         a_phase ^= (1u << kb);
         tc_fence_after_sync();
       };
-      // all K-slices of both accumulator blocks; a_kb0 >= 0 pins the A operand to one K-block (the PE passes)
-      auto run_pass = [&](int layer, int k16n, bool pe_pass, bool fresh_start) {
-        for (int blk = 0; blk < 2; ++blk) {
-          const int nrows = blk ? (layer == 8 ? 80 : 256) : 128;
-          const uint32_t idesc = umma_idesc_bf16(128, nrows);
-          const uint32_t d_col = blk ? 128u : 0u;
-          const int step = blk ? 1 : 2;
-          for (int ks = 0; ks < k16n; ks += step) {
-            // blk 0 touches each A K-block first; blk 0's first UMMA overwrites columns 0..127 = K-blocks 0 and 1 of the
-            // previous accumulator, so both must have been drained before it is issued.
-            if (blk == 0 && !pe_pass && (ks & 3) == 0) {
-              if (ks == 0) { wait_a(0); wait_a(1); }
-              else if (ks >= 8) wait_a(ks >> 2);
-            }
-#pragma unroll
-            for (int half = 0; half < 2; ++half) do_stage(d_col, idesc, ks, step, nrows, half, fresh_start && ks == 0);
+      auto commit_bar = [&](int which) {
+        if (elect_one()) umma_commit(bar(which));
+        __syncwarp();
+      };
+      // all K-slices of both accumulator blocks (blk 0: N=128, two K16 steps per stage; blk 1: N=256 / 80, one step)
+      auto run_pass = [&](auto n1_c, int k16n, bool pe_pass, bool fresh_start) {
+        for (int ks = 0; ks < k16n; ks += 2) {
+          // blk 0 touches each A K-block first; its first UMMA overwrites columns 0..127 = K-blocks 0 and 1 of the previous
+          // accumulator, so both must have been drained before it is issued.
+          if (!pe_pass && (ks & 3) == 0) {
+            if (ks == 0) { wait_a(0); wait_a(1); }
+            else if (ks >= 8) wait_a(ks >> 2);
           }
+          do_stage(std::integral_constant<int, 128>{}, std::integral_constant<int, 2>{}, 0u, ks, fresh_start && ks == 0);
         }
+        for (int ks = 0; ks < k16n; ++ks) do_stage(n1_c, std::integral_constant<int, 1>{}, 128u, ks, fresh_start && ks == 0);
       };
 
       for (int item = blockIdx.x; item < args.n_items; item += gridDim.x) {
+        prof_item = item / (int)gridDim.x;
+        prof_on = (args.prof != nullptr) && blockIdx.x == 0 && prof_item < 4;
         // ---- layer 0: K = 64 (PE in K-block 0)
+        stamp(0, 0);
         wait_a(0);
-        run_pass(0, 4, true, true);
-        umma_commit(bar(kBarAccFull));
-        // ---- layers 1..8 (layer 8: [RGB_0*RGB_1 (192) | density (1) | pad] = N 128 + 80)
-        for (int layer = 1; layer < 9; ++layer) {
-          run_pass(layer, 24, false, true);
+        run_pass(std::integral_constant<int, 256>{}, 4, true, true);
+        commit_bar(kBarAccFull);
+        stamp(0, 3);
+        // ---- layers 1..7
+        for (int layer = 1; layer < 8; ++layer) {
+          stamp(layer, 0);
+          run_pass(std::integral_constant<int, 256>{}, 24, false, true);
           if (layer == 5) {
             // skip connection: the PE columns of FeaExt_module_5 (models/mlp_nerf.py:106-107); the epilogue re-stages
             // the parked PE into K-block 0 once every read of the hidden K-blocks has completed.
-            umma_commit(bar(kBarAFree));
+            commit_bar(kBarAFree);
             wait_a(0);
-            run_pass(5, 4, true, false);
+            run_pass(std::integral_constant<int, 256>{}, 4, true, false);
           }
-          umma_commit(bar(kBarAccFull));
+          commit_bar(kBarAccFull);
+          stamp(layer, 3);
         }
+        // ---- layer 8: [RGB_0*RGB_1 (192) | density (1) | pad] = N 128 + 80
+        stamp(8, 0);
+        run_pass(std::integral_constant<int, 80>{}, 24, false, true);
+        commit_bar(kBarAccFull);
+        stamp(8, 3);
       }
     }
-    __syncwarp();
   } else {
     // =============================================== epilogue warps (0..3) =======================================
     const int row = threadIdx.x;                                   // TMEM lane == tile row == sample point
@@ -322,46 +397,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
       const float delta = __fmul_rn(__fsub_rn(ze[s + 1], z), dl.w);  // (z_{k+1} - z_k) * l  (utils/model_utils.py:309-310)
       {
         float pe[64];
-        const float dc[3] = {dl.x, dl.y, dl.z};
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          // pts = o + ((d * l) * z)  (utils/model_utils.py:315), each op individually rounded
-          float x = __fadd_rn(args.tvecs[b * 3 + c], __fmul_rn(__fmul_rn(dc[c], dl.w), z));
-          pe[c] = x;
-          float f = 1.0f;
-#pragma unroll
-          for (int q = 0; q < 10; ++q) {
-            float sv, cv;
-            sincosf(__fmul_rn(x, f), &sv, &cv);  // utils/model_utils.py:263-265 (freq = 2^q exactly)
-            pe[3 + 6 * q + c] = sv;
-            pe[6 + 6 * q + c] = cv;
-            f *= 2.0f;
-          }
-        }
-        pe[63] = 0.0f;
-        store_a_row64(smem_base, 0, row, pe);
-        // parked copy: column j holds (hi_j | lo_j << 16)
-        uint32_t pk[32];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            uint32_t hi, lo;
-            split2(pe[32 * half + j], pe[32 * half + j + 1], hi, lo);
-            pk[j] = (hi & 0xFFFFu) | (lo << 16);
-            pk[j + 1] = (hi >> 16) | (lo & 0xFFFF0000u);
-          }
-          tmem_st32(t_lane + kPeCol + 32 * half, pk);
-        }
-        tmem_wait_st();
+        compute_pe(args.tvecs + b * 3, dl, z, pe);
+        uint32_t hi[32], lo[32];
+        split_row64(pe, hi, lo);
+        store_a_kblock(smem_base, t_lane, 0, row, hi, lo);
         if (dump)
           for (int j = 0; j < 64; ++j) args.dbg[(size_t)row * kHidden + j] = pe[j];
       }
       release_kb(0);
 
       // ---- trunk: drain layer l accumulators into A as the input of layer l+1 ----------------------------------
+      const bool eprof = (args.prof != nullptr) && blockIdx.x == 0 && (item / (int)gridDim.x) < 4 && threadIdx.x == 0;
+      long long* ep = eprof ? args.prof + ((size_t)(item / (int)gridDim.x) * 10) * 16 : nullptr;
+      if (eprof) ep[6] = clock64();  // layer-0 row: prologue (PE) done
       for (int layer = 0; layer < 8; ++layer) {
         mbar_wait(bar(kBarAccFull), acc_phase);
+        if (eprof) ep[layer * 16 + 7] = clock64();  // accumulator of `layer` complete
         acc_phase ^= 1;
         tc_fence_after_sync();
         const float* bl = bias + bias_offset(layer);
@@ -389,47 +440,34 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
             v[32 + 4 * j + 2] = fmaxf(__uint_as_float(r1[4 * j + 2]) + bb.z, 0.0f);
             v[32 + 4 * j + 3] = fmaxf(__uint_as_float(r1[4 * j + 3]) + bb.w, 0.0f);
           }
-          store_a_row64(smem_base, kb, row, v);
+          {
+            uint32_t hi[32], lo[32];
+            split_row64(v, hi, lo);
+            store_a_kblock(smem_base, t_lane, kb, row, hi, lo);
+          }
           if (dump)
             for (int j = 0; j < 64; ++j) args.dbg[((size_t)(layer + 1) * kTile + row) * kHidden + kb * 64 + j] = v[j];
           release_kb(kb);
+          if (eprof && (kb == 1 || kb == 5)) ep[layer * 16 + (kb == 1 ? 8 : 9)] = clock64();  // K-blocks 0..1 / all released
         }
         if (layer == 4) {
-          // layer 5 = [hidden | PE]: once the hidden part has been consumed, re-stage the parked PE into K-block 0
+          // layer 5 = [hidden | PE] (skip connection, models/mlp_nerf.py:106-107): recompute the PE while the MMA warp runs
+          // the hidden part, then re-stage it into K-block 0 once every read of the hidden K-blocks has completed.
+          float pe[64];
+          compute_pe(args.tvecs + b * 3, dl, z, pe);
+          uint32_t hi[32], lo[32];
+          split_row64(pe, hi, lo);
           mbar_wait(bar(kBarAFree), afree_phase);
           afree_phase ^= 1;
           tc_fence_after_sync();
-          uint32_t pk0[32], pk1[32];
-          tmem_ld32(t_lane + kPeCol, pk0);
-          tmem_ld32(t_lane + kPeCol + 32, pk1);
-          tmem_wait_ld();
-          const uint32_t row_off = a_row_offset(row);
-          const uint32_t sw = (uint32_t)(row & 7);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int c = 8 * j + 2 * q;  // columns c, c+1
-              const uint32_t p0 = (c < 32) ? pk0[c] : pk1[c - 32];
-              const uint32_t p1 = (c < 32) ? pk0[c + 1] : pk1[c + 1 - 32];
-              hi[q] = (p0 & 0xFFFFu) | (p1 << 16);
-              lo[q] = (p0 >> 16) | (p1 & 0xFFFF0000u);
-            }
-            const uint32_t off = row_off + (((uint32_t)j ^ sw) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_base + kSmemAHi + off), "r"(hi[0]), "r"(hi[1]),
-                         "r"(hi[2]), "r"(hi[3])
-                         : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_base + kSmemALo + off), "r"(lo[0]), "r"(lo[1]),
-                         "r"(lo[2]), "r"(lo[3])
-                         : "memory");
-          }
+          store_a_kblock(smem_base, t_lane, 0, row, hi, lo);
           release_kb(0);
         }
       }
 
       // ---- last stage: density -> alpha -> transmittance scan -> weights; composite the 192-d hidden per ray ----
       mbar_wait(bar(kBarAccFull), acc_phase);
+      if (eprof) ep[8 * 16 + 7] = clock64();
       acc_phase ^= 1;
       tc_fence_after_sync();
       const float* b8 = bias + bias_offset(8);
@@ -491,6 +529,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
         }
       }
       named_bar_sync(1, kEpiThreads);  // scratch reads done before the next tile's prologue overwrites A
+      if (eprof) ep[8 * 16 + 9] = clock64();  // composite done
     }
   }
 
@@ -604,7 +643,7 @@ __global__ void pack_aux_kernel(PackSrc src, float* __restrict__ aux) {
 struct StageRec {
   uint32_t byte_off;
   uint16_t ks, nk16, n0, nrows;
-  uint8_t layer, phase2, half, pad;
+  uint8_t layer, phase2, pad0, pad1;
 };
 __device__ StageRec g_stage_table[kNumStagesPerTile];
 
@@ -626,10 +665,12 @@ __device__ __forceinline__ float pack_src_value(const PackSrc& src, const float*
 __global__ void pack_stream_kernel(PackSrc src, const float* __restrict__ wf, unsigned char* __restrict__ stream) {
   const StageRec st = g_stage_table[blockIdx.x];
   const int chunks_per_slice = st.nrows * 2;
-  const int n_chunks = chunks_per_slice * st.nk16;
-  for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) {
-    const int slice = c / chunks_per_slice;
-    const int rem = c - slice * chunks_per_slice;
+  const int chunks_per_half = chunks_per_slice * st.nk16;   // W_hi slices first, then the W_lo slices
+  for (int c = threadIdx.x; c < 2 * chunks_per_half; c += blockDim.x) {
+    const int half = c >= chunks_per_half;
+    const int ch = c - half * chunks_per_half;
+    const int slice = ch / chunks_per_slice;
+    const int rem = ch - slice * chunks_per_slice;
     const int row = (rem >> 4) * 8 + (rem & 7);
     const int k_half = (rem >> 3) & 1;
     const int n = st.n0 + row;
@@ -641,7 +682,7 @@ __global__ void pack_stream_kernel(PackSrc src, const float* __restrict__ wf, un
       float b = pack_src_value(src, wf, st.layer, st.phase2, n, k0 + 2 * q + 1);
       uint32_t hi, lo;
       split2(a, b, hi, lo);
-      out[q] = st.half ? lo : hi;
+      out[q] = half ? lo : hi;
     }
     *reinterpret_cast<uint4*>(stream + st.byte_off + (size_t)c * 16) = make_uint4(out[0], out[1], out[2], out[3]);
   }
@@ -702,7 +743,7 @@ extern "C" int gnrf_mlp_tc_pack(const float* const* params, void* packed, gnrf_s
       StageRec& r = host_table[i++];
       r.byte_off = off;
       r.ks = (uint16_t)si.ks; r.nk16 = (uint16_t)si.nk16; r.n0 = (uint16_t)si.n0; r.nrows = (uint16_t)si.nrows;
-      r.layer = (uint8_t)si.layer; r.phase2 = (uint8_t)si.phase2; r.half = (uint8_t)si.half; r.pad = 0;
+      r.layer = (uint8_t)si.layer; r.phase2 = (uint8_t)si.phase2; r.pad0 = 0; r.pad1 = 0;
       off += si.bytes;
     });
     if (i != kNumStagesPerTile || off != kStreamBytes) return fail(GNRF_ERR_CUDA, "gnrf_mlp_tc_pack: stage table mismatch (%d, %u)", i, off);
@@ -777,6 +818,11 @@ extern "C" int gnrf_mlp_tc_fwd(int n_branch, const void* const* packed, const fl
   {
     const char* e = getenv("GNRF_TC_DEBUG_PTR");  // test hook: device pointer (decimal) of a [10][128][384] fp32 dump buffer
     if (e != nullptr) a.dbg = reinterpret_cast<float*>(strtoull(e, nullptr, 10));
+  }
+  a.prof = nullptr;
+  {
+    const char* e = getenv("GNRF_TC_PROF_PTR");  // test hook: device pointer (decimal) of a [4][10][16] int64 timeline buffer
+    if (e != nullptr) a.prof = reinterpret_cast<long long*>(strtoull(e, nullptr, 10));
   }
   int grid = a.n_items < n_sm ? a.n_items : n_sm;
   mlp_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(a);

@@ -193,6 +193,10 @@ class GazeNeRFNet(nn.Module):
         self.keep_stages = False
         # bench hook: when a list, (start, end) CUDA events bracketing the radiance-MLP launches are appended per forward
         self.mlp_events: Optional[list] = None
+        # bg_img = NeuralRenderer(bg_featmap) depends on parameters only (models/gaze_nerf.py:175-176); in no-grad inference it
+        # is cached per parameter version instead of being re-rendered on every call (set False to re-render every call).
+        self.cache_bg_img = True
+        self._bg_cache: Optional[Tuple[tuple, torch.Tensor]] = None
 
     # ------------------------------------------------------------------ helpers
     def _tc_supported(self, n_s: int) -> bool:
@@ -262,15 +266,23 @@ class GazeNeRFNet(nn.Module):
         C, S = self.featmap_nc, self.featmap_size
         P = S * S
         dev = feat[0].device
-        fm = torch.empty((3 * B + 1, C, S, S), device=dev, dtype=torch.float32)
         bg = _dev_f32(self.neural_render.bg_featmap.detach(), "bg_featmap")
+        key = tuple((p.data_ptr(), p._version) for p in self.neural_render.parameters())
+        bg_img = self._bg_cache[1] if (self.cache_bg_img and self._bg_cache is not None and self._bg_cache[0] == key) else None
+        n_img = 3 * B + (0 if bg_img is not None else 1)
+        fm = torch.empty((n_img, C, S, S), device=dev, dtype=torch.float32)
         _lib.check(L.gnrf_compose_fwd(feat[0].data_ptr(), alpha[0].data_ptr(), feat[1].data_ptr(), alpha[1].data_ptr(), bg.data_ptr(),
                                       gaze.data_ptr(), B, C, P, fm.data_ptr(), _stream()), "gnrf_compose_fwd")
-        fm[3 * B].copy_(bg[0])
-        imgs = neural_render(self.neural_render, fm)
+        if bg_img is None:
+            fm[3 * B].copy_(bg[0])
+        imgs = neural_render(self.neural_render, fm)  # ONE batched call over [face | eyes | merge (| bg)]
+        if bg_img is None:
+            bg_img = imgs[3 * B:]
+            if self.cache_bg_img:
+                self._bg_cache = (key, bg_img.clone())
         if self.keep_stages:
             self.last_stages.update({"merge_face": fm[:B], "eyes_planes": fm[B:2 * B], "merge": fm[2 * B:3 * B]})
-        return {"merge_img_face": imgs[:B], "merge_img_eyes": imgs[B:2 * B], "merge_img": imgs[2 * B:3 * B], "bg_img": imgs[3 * B:]}
+        return {"merge_img_face": imgs[:B], "merge_img_eyes": imgs[B:2 * B], "merge_img": imgs[2 * B:3 * B], "bg_img": bg_img}
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()

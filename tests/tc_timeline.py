@@ -1,0 +1,30 @@
+"""Debug helper (not a test): per-layer timeline of CTA 0 of the fused MLP kernel, from in-kernel clock64 stamps.
+usage on the GPU box:  python tests/tc_timeline.py"""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import gazenerf_b200 as G
+sys.argv = [sys.argv[0]]
+import bench
+
+dev = torch.device("cuda:0")
+prof = torch.zeros(4 * 10 * 16, dtype=torch.int64, device=dev)
+os.environ["GNRF_TC_PROF_PTR"] = str(prof.data_ptr())
+opt = G.BaseOptions()
+torch.manual_seed(45)
+net = G.GazeNeRFNet(opt, include_vd=False, hier_sampling=False).to(dev).eval()
+kw = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in bench.synthetic_inputs(torch, G, opt, 1, 0).items()}
+for _ in range(3):
+    net("test", **kw)
+torch.cuda.synchronize()
+p = prof.cpu().view(4, 10, 16)
+for item in (1, 2):
+    t0 = int(p[item, 0, 0])
+    print("item", item, "(cycles relative to the tile's first MMA-warp stamp)")
+    print(" layer | mma_start   mma_end  dur   w_stall a_stall | acc_full  kb01_rel  all_rel ")
+    for l in range(9):
+        r = p[item, l]
+        ws = int(r[4] - r[1]); as_ = int(r[5] - r[2])
+        print("  %d    | %8d %8d %6d  %6d %6d | %8d %8d %8d" % (l, int(r[0]) - t0, int(r[3]) - t0, int(r[3] - r[0]), ws, as_,
+              int(r[7]) - t0, int(r[8]) - t0 if l < 8 else 0, int(r[9]) - t0))
+    print("  prologue done:", int(p[item, 0, 6]) - t0, " next tile start:", int(p[item + 1, 0, 0]) - t0)

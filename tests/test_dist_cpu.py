@@ -1,0 +1,56 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU plumbing: batch sharding and the single all-gather of rendered images."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gazenerf_b200.dist import all_gather_images, shard_inputs, shard_range
+
+
+def test_shard_range_partitions_batch():
+    for gb in (1, 2, 7, 8, 45):
+        for world in (1, 2, 4, 8):
+            spans = [shard_range(gb, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == gb
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, gb, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        P = 8
+        full = {k: torch.arange(gb * 3 * P * P, dtype=torch.float32).view(gb, 3, P, P) + 1000 * i
+                for i, k in enumerate(["merge_img_face", "merge_img_eyes", "merge_img"])}
+        kw = {"batch_xy": torch.zeros(gb, 2, 4), "shape_code": torch.arange(gb).float().view(gb, 1).expand(gb, 179).contiguous(), "batch_uv": None}
+        mine = shard_inputs(kw, rank, world)
+        lo, hi = shard_range(gb, rank, world)
+        assert mine["shape_code"].shape[0] == hi - lo and mine["batch_uv"] is None
+        assert float(mine["shape_code"][0, 0]) == lo if hi > lo else True
+        local = {k: v[lo:hi].clone() for k, v in full.items()}
+        local["bg_img"] = torch.ones(1, 3, P, P)
+        out = all_gather_images(local, gb)
+        ok = all(torch.equal(out[k], full[k]) for k in full) and out["bg_img"].shape == (1, 3, P, P)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("gb", [2, 4, 5])
+def test_all_gather_images_world2_gloo(gb):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + gb
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, gb, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=10) for _ in range(2))
+    assert res == [(0, True), (1, True)]
