@@ -18,7 +18,7 @@ CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(_ROOT, "include")
 LIB_PATH = os.path.join(_HERE, "libgnrf.so")
 
-SOURCES = ["abi.cu", "geometry.cu", "mlp_simt.cu", "mlp_tc.cu", "compose.cu", "neural_render.cu"]
+SOURCES = ["abi.cu", "geometry.cu", "mlp_simt.cu", "mlp_tc.cu", "compose.cu", "neural_render.cu", "conv_tc.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -34,6 +34,7 @@ SYMBOLS = [
     "gnrf_mlp_tc_packed_bytes", "gnrf_mlp_tc_bias_floats", "gnrf_mlp_tc_pack", "gnrf_mlp_tc_fold",
     "gnrf_mlp_tc_workspace_bytes", "gnrf_mlp_tc_fwd",
     "gnrf_compose_fwd", "gnrf_nr_workspace_bytes", "gnrf_neural_render_fwd",
+    "gnrf_nr_tc_packed_bytes", "gnrf_nr_tc_pack", "gnrf_neural_render_tc_fwd",
 ]
 
 
@@ -108,6 +109,10 @@ def lib() -> ctypes.CDLL:
     L.gnrf_nr_workspace_bytes.restype = sz
     L.gnrf_nr_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
     L.gnrf_neural_render_fwd.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, sz, vp]
+    L.gnrf_nr_tc_packed_bytes.restype = sz
+    L.gnrf_nr_tc_packed_bytes.argtypes = [i32, i32, i32]
+    L.gnrf_nr_tc_pack.argtypes = [vp, i32, i32, i32, vp, vp]
+    L.gnrf_neural_render_tc_fwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, sz, vp]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is c.c_int and name not in ("gnrf_abi_version",):

@@ -36,6 +36,7 @@
 
 #include "common.cuh"
 #include "sm100_ptx.cuh"
+#include "tc_common.cuh"
 
 namespace gnrf {
 namespace tc {
@@ -156,21 +157,6 @@ struct FwdArgs {
 // =====================================================================================================================
 //  main kernel
 // =====================================================================================================================
-__device__ __forceinline__ uint32_t a_row_offset(int row) { return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128); }
-
-// Write 64 consecutive K values of one row (already activated) into K-block `kb` of the A operand:
-// hi halves -> smem (SW128 K-major); lo halves -> TMEM columns (kb < 4, packed pairs, TS-mode operand) or smem (kb 4,5).
-__device__ __forceinline__ void split_row64(const float (&v)[64], uint32_t (&hi)[32], uint32_t (&lo)[32]) {
-#pragma unroll
-  for (int q = 0; q < 32; ++q) split2(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
-}
-__device__ __forceinline__ void st_shared_row128(uint32_t addr_row, uint32_t sw, const uint32_t (&w)[32]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr_row + (((uint32_t)j ^ sw) << 4)), "r"(w[4 * j]),
-                 "r"(w[4 * j + 1]), "r"(w[4 * j + 2]), "r"(w[4 * j + 3])
-                 : "memory");
-}
 __device__ __forceinline__ void store_a_kblock(uint32_t smem_base, uint32_t t_lane, int kb, int row, const uint32_t (&hi)[32],
                                                const uint32_t (&lo)[32]) {
   const uint32_t row_off = a_row_offset(row);

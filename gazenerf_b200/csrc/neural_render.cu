@@ -2,6 +2,7 @@
 // Reference: models/neural_renderer.py:98-113 (NeuralRenderer.forward),
 //            models/pixel_shuffle_upsample.py:7-42 (Blur -> kornia.filters.filter2d, PixelShuffleUpsample).
 #include "common.cuh"
+#include "conv_tc.cuh"
 
 namespace gnrf {
 
@@ -221,8 +222,9 @@ extern "C" size_t gnrf_nr_workspace_bytes(int N, int C, int S, int n_blocks, int
   return nr_plan(N, C, S, n_blocks, min_feat).total;
 }
 
-extern "C" int gnrf_neural_render_fwd(const float* const* params, const float* featmap, int N, int C, int S, int n_blocks,
-                                      int min_feat, float* img, void* workspace, size_t workspace_bytes, gnrf_stream_t stream) {
+// packed == nullptr: fp32 CUDA-core GEMMs; else: tcgen05 bf16x3 GEMMs on the packed weight streams (3 layers per block)
+static int nr_forward(const float* const* params, const unsigned char* packed, const float* featmap, int N, int C, int S, int n_blocks,
+                      int min_feat, float* img, void* workspace, size_t workspace_bytes, gnrf_stream_t stream) {
   GNRF_CHECK_ARG(params && featmap && img && workspace);
   GNRF_CHECK_ARG(N > 0 && C > 0 && S >= 2 && n_blocks >= 1 && n_blocks <= 6);
   GNRF_CHECK_ARG(S % 4 == 0);
@@ -263,19 +265,29 @@ extern "C" int gnrf_neural_render_fwd(const float* const* params, const float* f
   GNRF_LAUNCH_CHECK();
   count_launches(2);
   const float* net = featmap;
+  size_t pk_off = 0;
   float* rgb_up = rgb_b;   // upsampled running rgb
   float* rgb_cur = rgb_a;  // scratch for the next sum
   for (int i = 0; i < n_blocks; ++i) {
     int ci = (C >> i) > min_feat ? (C >> i) : min_feat;
     int co = (C >> (i + 1)) > min_feat ? (C >> (i + 1)) : min_feat;
     int HW = s * s;
-    {  // PSU layer_1: ci -> 2ci, LeakyReLU
-      dim3 grid(ceil_div(HW, BN), ceil_div(2 * ci, BM), N);
-      conv1x1_kernel<EPI_LRELU><<<grid, kGemmThreads, 0, st>>>(psu_w(i, 0), psu_b(i, 0), net, 2 * ci, ci, HW, s, nullptr, 1, t1);
-    }
-    {  // PSU layer_2: 2ci -> 4ci, LeakyReLU, + repeat(x,4), pixel_shuffle(2)
-      dim3 grid(ceil_div(HW, BN), ceil_div(4 * ci, BM), N);
-      conv1x1_kernel<EPI_PSU><<<grid, kGemmThreads, 0, st>>>(psu_w(i, 1), psu_b(i, 1), t1, 4 * ci, 2 * ci, HW, s, net, ci, sh);
+    tc::ConvLayerPlan pl1 = tc::conv_layer_plan(2 * ci, ci), pl2 = tc::conv_layer_plan(4 * ci, 2 * ci), pl3 = tc::conv_layer_plan(co, ci);
+    if (packed != nullptr) {
+      int rc = tc::conv_tc_launch(pl1, packed + pk_off, net, t1, nullptr, 1, N, HW, s, tc::CONV_EPI_LRELU, st);
+      if (rc != GNRF_OK) return rc;
+      rc = tc::conv_tc_launch(pl2, packed + pk_off + pl1.total_bytes, t1, sh, net, ci, N, HW, s, tc::CONV_EPI_PSU, st);
+      if (rc != GNRF_OK) return rc;
+    } else {
+      {  // PSU layer_1: ci -> 2ci, LeakyReLU
+        dim3 grid(ceil_div(HW, BN), ceil_div(2 * ci, BM), N);
+        conv1x1_kernel<EPI_LRELU><<<grid, kGemmThreads, 0, st>>>(psu_w(i, 0), psu_b(i, 0), net, 2 * ci, ci, HW, s, nullptr, 1, t1);
+      }
+      {  // PSU layer_2: 2ci -> 4ci, LeakyReLU, + repeat(x,4), pixel_shuffle(2)
+        dim3 grid(ceil_div(HW, BN), ceil_div(4 * ci, BM), N);
+        conv1x1_kernel<EPI_PSU><<<grid, kGemmThreads, 0, st>>>(psu_w(i, 1), psu_b(i, 1), t1, 4 * ci, 2 * ci, HW, s, net, ci, sh);
+      }
+      count_launches(2);
     }
     s *= 2;
     HW = s * s;
@@ -284,10 +296,16 @@ extern "C" int gnrf_neural_render_fwd(const float* const* params, const float* f
       blur3x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sh, s, s, total, bl);
     }
     float* net_out = netbuf[i & 1];
-    {  // feat_layers[i]: ci -> co, LeakyReLU
+    if (packed != nullptr) {
+      int rc = tc::conv_tc_launch(pl3, packed + pk_off + pl1.total_bytes + pl2.total_bytes, bl, net_out, nullptr, 1, N, HW, s,
+                                  tc::CONV_EPI_LRELU, st);
+      if (rc != GNRF_OK) return rc;
+    } else {  // feat_layers[i]: ci -> co, LeakyReLU
       dim3 grid(ceil_div(HW, BN), ceil_div(co, BM), N);
       conv1x1_kernel<EPI_LRELU><<<grid, kGemmThreads, 0, st>>>(feat_w(i), feat_b(i), bl, co, ci, HW, s, nullptr, 1, net_out);
+      count_launches(1);
     }
+    pk_off += pl1.total_bytes + pl2.total_bytes + pl3.total_bytes;
     bool last = (i == n_blocks - 1);
     launch_rgb(rgb_w(i + 1), rgb_bi(i + 1), net_out, co, HW, rgb_up, last ? 1 : 0, last ? img : rgb_cur);
     if (!last) {
@@ -298,7 +316,50 @@ extern "C" int gnrf_neural_render_fwd(const float* const* params, const float* f
     }
     net = net_out;
     GNRF_LAUNCH_CHECK();
-    count_launches(last ? 5 : 6);
+    count_launches(last ? 2 : 3);  // blur, to_rgb (+ rgb_up_blur); the conv launches are counted where they are issued
   }
   return GNRF_OK;
+}
+
+extern "C" int gnrf_neural_render_fwd(const float* const* params, const float* featmap, int N, int C, int S, int n_blocks,
+                                      int min_feat, float* img, void* workspace, size_t workspace_bytes, gnrf_stream_t stream) {
+  return nr_forward(params, nullptr, featmap, N, C, S, n_blocks, min_feat, img, workspace, workspace_bytes, stream);
+}
+
+extern "C" size_t gnrf_nr_tc_packed_bytes(int C, int n_blocks, int min_feat) {
+  size_t tot = 0;
+  for (int i = 0; i < n_blocks; ++i) {
+    int ci = (C >> i) > min_feat ? (C >> i) : min_feat;
+    int co = (C >> (i + 1)) > min_feat ? (C >> (i + 1)) : min_feat;
+    tot += tc::conv_layer_plan(2 * ci, ci).total_bytes + tc::conv_layer_plan(4 * ci, 2 * ci).total_bytes + tc::conv_layer_plan(co, ci).total_bytes;
+  }
+  return tot;
+}
+
+extern "C" int gnrf_nr_tc_pack(const float* const* params, int C, int n_blocks, int min_feat, void* packed, gnrf_stream_t stream) {
+  GNRF_CHECK_ARG(params && packed && C > 0 && n_blocks >= 1 && n_blocks <= 6);
+  GNRF_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 127) == 0);
+  unsigned char* dst = static_cast<unsigned char*>(packed);
+  for (int i = 0; i < n_blocks; ++i) {
+    int ci = (C >> i) > min_feat ? (C >> i) : min_feat;
+    int co = (C >> (i + 1)) > min_feat ? (C >> (i + 1)) : min_feat;
+    tc::ConvLayerPlan pl[3] = {tc::conv_layer_plan(2 * ci, ci), tc::conv_layer_plan(4 * ci, 2 * ci), tc::conv_layer_plan(co, ci)};
+    const float* w[3] = {params[4 * i], params[4 * i + 2], params[4 * n_blocks + 2 * (n_blocks + 1) + 2 * i]};
+    const float* b[3] = {params[4 * i + 1], params[4 * i + 3], params[4 * n_blocks + 2 * (n_blocks + 1) + 2 * i + 1]};
+    for (int l = 0; l < 3; ++l) {
+      GNRF_CHECK_ARG(w[l] && b[l]);
+      int rc = tc::conv_tc_pack(pl[l], w[l], b[l], dst, as_stream(stream));
+      if (rc != GNRF_OK) return rc;
+      dst += pl[l].total_bytes;
+    }
+  }
+  return GNRF_OK;
+}
+
+extern "C" int gnrf_neural_render_tc_fwd(const float* const* params, const void* packed, const float* featmap, int N, int C, int S,
+                                         int n_blocks, int min_feat, float* img, void* workspace, size_t workspace_bytes,
+                                         gnrf_stream_t stream) {
+  GNRF_CHECK_ARG(packed);
+  return nr_forward(params, static_cast<const unsigned char*>(packed), featmap, N, C, S, n_blocks, min_feat, img, workspace,
+                    workspace_bytes, stream);
 }

@@ -92,6 +92,7 @@ class NeuralRendererParams(nn.Module):
         assert out_dim == 3 and final_actvn
         self.bg_type, self.featmap_size, self.n_feat, self.min_feat = bg_type, featmap_size, feat_nc, min_feat
         self.n_blocks = int(math.log2(img_size) - math.log2(featmap_size))
+        self.impl = "tc"  # "tc": tcgen05 bf16x3 convs (default) | "simt": fp32 CUDA-core convs
         w = lambda i: max(feat_nc // (2 ** i), min_feat)
         self.feat_upsample_list = nn.ModuleList([_PixelShuffleUpsampleParams(w(i)) for i in range(self.n_blocks)])
         self.rgb_upsample = nn.Sequential(nn.Identity(), _Blur())  # index 1 carries the "f" buffer
@@ -122,6 +123,20 @@ class NeuralRendererParams(nn.Module):
         """[N,C,S,S] -> [N,3,P,P] through libgnrf (same call shape as the reference's NeuralRenderer.forward)."""
         return neural_render(self, x)
 
+    def packed_tc(self) -> torch.Tensor:
+        """bf16 hi/lo weight streams for the tcgen05 convs; a derived cache keyed on parameter versions, never saved."""
+        L = _lib.lib()
+        params = [p.detach() for p in self.param_list()]
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        hit = getattr(self, "_tc_pack", None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        nbytes = L.gnrf_nr_tc_packed_bytes(self.n_feat, self.n_blocks, self.min_feat)
+        packed = torch.empty((nbytes,), device=params[0].device, dtype=torch.uint8)
+        _lib.check(L.gnrf_nr_tc_pack(_ptrs(params), self.n_feat, self.n_blocks, self.min_feat, packed.data_ptr(), _stream()), "gnrf_nr_tc_pack")
+        object.__setattr__(self, "_tc_pack", (key, packed))
+        return packed
+
 
 def _dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
     if not t.is_cuda:
@@ -150,8 +165,13 @@ def neural_render(nr: NeuralRendererParams, x: torch.Tensor) -> torch.Tensor:
     ws_bytes = L.gnrf_nr_workspace_bytes(n, c, s, nr.n_blocks, nr.min_feat)
     ws = torch.empty((ws_bytes,), device=x.device, dtype=torch.uint8)
     params = [p.detach() for p in nr.param_list()]
-    _lib.check(L.gnrf_neural_render_fwd(_ptrs(params), x.data_ptr(), n, c, s, nr.n_blocks, nr.min_feat, img.data_ptr(),
-                                        ws.data_ptr(), ws_bytes, _stream()), "gnrf_neural_render_fwd")
+    if nr.impl == "tc":
+        packed = nr.packed_tc()
+        _lib.check(L.gnrf_neural_render_tc_fwd(_ptrs(params), packed.data_ptr(), x.data_ptr(), n, c, s, nr.n_blocks, nr.min_feat,
+                                               img.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "gnrf_neural_render_tc_fwd")
+    else:
+        _lib.check(L.gnrf_neural_render_fwd(_ptrs(params), x.data_ptr(), n, c, s, nr.n_blocks, nr.min_feat, img.data_ptr(),
+                                            ws.data_ptr(), ws_bytes, _stream()), "gnrf_neural_render_fwd")
     return img
 
 

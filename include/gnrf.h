@@ -131,6 +131,16 @@ size_t gnrf_nr_workspace_bytes(int N, int C, int S, int n_blocks, int min_feat);
 int gnrf_neural_render_fwd(const float* const* params, const float* featmap, int N, int C, int S, int n_blocks,
                            int min_feat, float* img, void* workspace, size_t workspace_bytes, gnrf_stream_t stream);
 
+/* Same computation with the 1x1 convolutions of the PixelShuffleUpsample blocks and feat_layers on tcgen05 tensor cores
+ * (bf16x3 split precision, fp32 accumulate in TMEM; csrc/conv_tc.cu).  gnrf_nr_tc_pack re-arranges those 3*n_blocks weight
+ * matrices (hi/lo split, UMMA core-matrix K-slices) into `packed` (gnrf_nr_tc_packed_bytes, 128-byte aligned); redo after
+ * every weight update.  params / workspace as for gnrf_neural_render_fwd (the to-RGB heads stay fp32). */
+size_t gnrf_nr_tc_packed_bytes(int C, int n_blocks, int min_feat);
+int gnrf_nr_tc_pack(const float* const* params, int C, int n_blocks, int min_feat, void* packed, gnrf_stream_t stream);
+int gnrf_neural_render_tc_fwd(const float* const* params, const void* packed, const float* featmap, int N, int C, int S,
+                              int n_blocks, int min_feat, float* img, void* workspace, size_t workspace_bytes,
+                              gnrf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
