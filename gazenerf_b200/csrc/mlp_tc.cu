@@ -58,6 +58,7 @@ constexpr int kABlockBytes = kTile * 128;            // 16384: one K-block of A 
 constexpr int kABytes = kNumKB * kABlockBytes;       // 98304
 constexpr int kEpiThreads = 128;
 constexpr int kThreads = 192;
+constexpr int kMaxGrid = 160;            // persistent grid upper bound (>= SM count of a B200: 148)
 constexpr int kScratchLd = 193;          // composite scratch row stride (floats): conflict-free for both phases
 
 // ---- weight stage schedule -------------------------------------------------------------------------------------------
@@ -150,6 +151,7 @@ struct FwdArgs {
   const float* tvecs;
   const float* z_edges;
   int n_branch, B, N_r, N_s, tiles_per_face, n_items;
+  uint32_t* pe_stash; // [grid][65][128] u32 per-CTA stash of the tile's packed positional encoding (+ delta), L2 resident
   float* dbg;        // optional [10][128][384] dump of tile 0 activations
   long long* prof;   // optional timeline of CTA 0: [item < 4][layer 0..9][16] clock64 stamps / stall sums
 };
@@ -356,7 +358,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
     uint32_t acc_phase = 0, afree_phase = 0;
     const int N_s = args.N_s;
     const int rays_per_tile = kTile / N_s;
-    float* scratch = reinterpret_cast<float*>(smem_gen);           // [128][193] fp32, aliases A between tiles
+    // per-ray composite scratch [128][193] fp32: aliases A K-blocks 1.. (K-block 0 stays free for the next tile's PE)
+    float* scratch = reinterpret_cast<float*>(smem_gen + kABlockBytes);
+    // per-CTA stash of the tile's positional encoding (packed hi/lo words) + delta, L2 resident: [65][128] u32, thread == row
+    uint32_t* stash = args.pe_stash + (size_t)blockIdx.x * (65 * kTile) + row;
 
     auto release_kb = [&](int kb) {
       fence_proxy_async_smem();   // generic-proxy st.shared -> visible to the tensor core (async proxy)
@@ -364,7 +369,46 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(kBarAReady + kb));
     };
+    // sample point of (item, row) -> positional encoding + delta, written to the stash (read back by the same thread)
+    auto stash_pe = [&](int item) {
+      const int t = item / args.n_branch;
+      const int b = t / args.tiles_per_face;
+      const int tile = t - b * args.tiles_per_face;
+      const int ray = tile * rays_per_tile + row / N_s;
+      const int s = row - (row / N_s) * N_s;
+      const float4 dl = args.ray_dl[(size_t)b * args.N_r + ray];
+      const float* ze = args.z_edges + ((size_t)b * args.N_r + ray) * (N_s + 1);
+      const float z = ze[s];
+      const float delta = __fmul_rn(__fsub_rn(ze[s + 1], z), dl.w);  // (z_{k+1} - z_k) * l  (utils/model_utils.py:309-310)
+      float pe[64];
+      compute_pe(args.tvecs + b * 3, dl, z, pe);
+      uint32_t hi[32], lo[32];
+      split_row64(pe, hi, lo);
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        stash[(size_t)q * kTile] = hi[q];
+        stash[(size_t)(32 + q) * kTile] = lo[q];
+      }
+      stash[(size_t)64 * kTile] = __float_as_uint(delta);
+      if (args.dbg != nullptr && item == 0)
+        for (int j = 0; j < 64; ++j) args.dbg[(size_t)row * kHidden + j] = pe[j];
+    };
+    // stash -> A K-block 0 (hi: smem, lo: TMEM), then release it to the MMA warp
+    auto stage_pe = [&]() {
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        hi[q] = stash[(size_t)q * kTile];
+        lo[q] = stash[(size_t)(32 + q) * kTile];
+      }
+      store_a_kblock(smem_base, t_lane, 0, row, hi, lo);
+      release_kb(0);
+    };
 
+    if ((int)blockIdx.x < args.n_items) {
+      stash_pe(blockIdx.x);
+      stage_pe();
+    }
     for (int item = blockIdx.x; item < args.n_items; item += gridDim.x) {
       const int branch = item % args.n_branch;
       const int t = item / args.n_branch;
@@ -373,29 +417,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
       const BranchArgs& br = args.br[branch];
       const float* bias = br.bias + (size_t)b * kBiasFloats;
       const bool dump = (args.dbg != nullptr) && (item == 0);
-
-      // ---- prologue: sample point -> positional encoding -> A K-block 0 (+ parked copy in TMEM) ----------------
+      const int next_item = item + (int)gridDim.x;
       const int ray = tile * rays_per_tile + row / N_s;
       const int s = row - (row / N_s) * N_s;
-      const float4 dl = args.ray_dl[(size_t)b * args.N_r + ray];
-      const float* ze = args.z_edges + ((size_t)b * args.N_r + ray) * (N_s + 1);
-      const float z = ze[s];
-      const float delta = __fmul_rn(__fsub_rn(ze[s + 1], z), dl.w);  // (z_{k+1} - z_k) * l  (utils/model_utils.py:309-310)
-      {
-        float pe[64];
-        compute_pe(args.tvecs + b * 3, dl, z, pe);
-        uint32_t hi[32], lo[32];
-        split_row64(pe, hi, lo);
-        store_a_kblock(smem_base, t_lane, 0, row, hi, lo);
-        if (dump)
-          for (int j = 0; j < 64; ++j) args.dbg[(size_t)row * kHidden + j] = pe[j];
-      }
-      release_kb(0);
+      const float delta = __uint_as_float(stash[(size_t)64 * kTile]);
 
       // ---- trunk: drain layer l accumulators into A as the input of layer l+1 ----------------------------------
       const bool eprof = (args.prof != nullptr) && blockIdx.x == 0 && (item / (int)gridDim.x) < 4 && threadIdx.x == 0;
       long long* ep = eprof ? args.prof + ((size_t)(item / (int)gridDim.x) * 10) * 16 : nullptr;
-      if (eprof) ep[6] = clock64();  // layer-0 row: prologue (PE) done
+      if (eprof) ep[6] = clock64();  // layer-0 row: K-block 0 (PE) of this tile released
       for (int layer = 0; layer < 8; ++layer) {
         mbar_wait(bar(kBarAccFull), acc_phase);
         if (eprof) ep[layer * 16 + 7] = clock64();  // accumulator of `layer` complete
@@ -437,18 +467,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
           if (eprof && (kb == 1 || kb == 5)) ep[layer * 16 + (kb == 1 ? 8 : 9)] = clock64();  // K-blocks 0..1 / all released
         }
         if (layer == 4) {
-          // layer 5 = [hidden | PE] (skip connection, models/mlp_nerf.py:106-107): recompute the PE while the MMA warp runs
-          // the hidden part, then re-stage it into K-block 0 once every read of the hidden K-blocks has completed.
-          float pe[64];
-          compute_pe(args.tvecs + b * 3, dl, z, pe);
-          uint32_t hi[32], lo[32];
-          split_row64(pe, hi, lo);
+          // layer 5 = [hidden | PE] (skip connection, models/mlp_nerf.py:106-107): once the MMA warp has consumed the hidden
+          // K-blocks, re-stage the tile's PE (from the stash) into K-block 0.
           mbar_wait(bar(kBarAFree), afree_phase);
           afree_phase ^= 1;
           tc_fence_after_sync();
-          store_a_kblock(smem_base, t_lane, 0, row, hi, lo);
-          release_kb(0);
+          stage_pe();
         }
+        // idle window (the MMA warp is busy with layer 7): prepare the next tile's positional encoding
+        if (layer == 6 && next_item < args.n_items) stash_pe(next_item);
       }
 
       // ---- last stage: density -> alpha -> transmittance scan -> weights; composite the 192-d hidden per ray ----
@@ -487,7 +514,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
         if (br.weights != nullptr) br.weights[((size_t)b * args.N_r + ray) * N_s + s] = w_k;
         if (dump) args.dbg[((size_t)9 * kTile + row) * kHidden + kH2] = sigma;
       }
-      // all A reads of this tile are complete (acc_full) -> A can be reused as the [128][193] fp32 scratch
+      // all A reads of this tile are complete (acc_full): move w * ReLU(hidden) out of TMEM into the smem scratch
 #pragma unroll 1
       for (int c0 = 0; c0 < kH2; c0 += 32) {
         uint32_t r[32];
@@ -501,7 +528,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
         }
       }
       scratch[row * kScratchLd + kH2] = w_k;
-      tc_fence_before_sync();
+      // the accumulators are drained: hand the next tile's layer 0 to the MMA warp BEFORE the cross-row reduction
+      if (next_item < args.n_items) stage_pe();
+      else tc_fence_before_sync();
       named_bar_sync(1, kEpiThreads);
       {
         const int total = rays_per_tile * kScratchLd;
@@ -514,7 +543,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
           if (c < kH2) br.hc[gray * kH2 + c] = acc; else br.wsum[gray] = acc;
         }
       }
-      named_bar_sync(1, kEpiThreads);  // scratch reads done before the next tile's prologue overwrites A
+      named_bar_sync(1, kEpiThreads);  // scratch reads done before the next tile's layer-0 drain overwrites A K-blocks 1..
       if (eprof) ep[8 * 16 + 9] = clock64();  // composite done
     }
   }
@@ -757,7 +786,8 @@ extern "C" int gnrf_mlp_tc_fold(const void* packed, const float* shape_ext, cons
 
 extern "C" size_t gnrf_mlp_tc_workspace_bytes(int n_branch, int B, int N_r) {
   if (n_branch <= 0 || B <= 0 || N_r <= 0) return 0;
-  return (size_t)n_branch * B * N_r * (kH2 + 1) * sizeof(float);
+  size_t hc = ((size_t)n_branch * B * N_r * (kH2 + 1) * sizeof(float) + 255) & ~(size_t)255;
+  return hc + (size_t)kMaxGrid * 65 * kTile * sizeof(uint32_t);
 }
 
 extern "C" int gnrf_mlp_tc_fwd(int n_branch, const void* const* packed, const float* const* bias, const float* ray_dl,
@@ -800,6 +830,8 @@ extern "C" int gnrf_mlp_tc_fwd(int n_branch, const void* const* packed, const fl
   a.N_s = N_s;
   a.tiles_per_face = (int)(((long long)N_r * N_s) / kTile);
   a.n_items = n_branch * B * a.tiles_per_face;
+  a.pe_stash = reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(workspace) +
+                                           (((size_t)n_branch * B * N_r * (kH2 + 1) * sizeof(float) + 255) & ~(size_t)255));
   a.dbg = nullptr;
   {
     const char* e = getenv("GNRF_TC_DEBUG_PTR");  // test hook: device pointer (decimal) of a [10][128][384] fp32 dump buffer
@@ -811,6 +843,7 @@ extern "C" int gnrf_mlp_tc_fwd(int n_branch, const void* const* packed, const fl
     if (e != nullptr) a.prof = reinterpret_cast<long long*>(strtoull(e, nullptr, 10));
   }
   int grid = a.n_items < n_sm ? a.n_items : n_sm;
+  if (grid > kMaxGrid) grid = kMaxGrid;
   mlp_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
   GNRF_LAUNCH_CHECK();
   for (int i = 0; i < n_branch; ++i) {
