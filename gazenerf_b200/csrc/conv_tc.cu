@@ -117,11 +117,15 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const ConvArgs a
           if (lane == 0) mbar_arrive(bar(kCvBarAccEmpty + buf));
         }
         if (!p_ok) continue;
-        if (args.mode == CONV_EPI_LRELU) {
+        if (args.mode != CONV_EPI_PSU) {
           float* o = args.out + ((size_t)img * args.N + n0 + c0) * args.HW + p;
+          const bool act = args.mode == CONV_EPI_LRELU;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (j < ncols && n0 + c0 + j < args.N) o[(size_t)j * args.HW] = lrelu02(__uint_as_float(r[j]) + bv[j]);
+            if (j < ncols && n0 + c0 + j < args.N) {
+              const float v = __uint_as_float(r[j]) + bv[j];
+              o[(size_t)j * args.HW] = act ? lrelu02(v) : v;
+            }
         } else {
           // + x.repeat(1,4,1,1), then pixel_shuffle(2): out[c][2h+i][2w+j] = in[4c+2i+j][h][w]  (pixel_shuffle_upsample.py:34-40)
           // n0 + c0 is a multiple of 16, so the 32 columns are 8 complete groups of 4 = (si, sj) in {0,1}^2 of channel c.

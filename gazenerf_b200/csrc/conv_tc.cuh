@@ -6,7 +6,7 @@
 namespace gnrf {
 namespace tc {
 
-enum ConvEpilogue { CONV_EPI_LRELU = 0, CONV_EPI_PSU = 1 };
+enum ConvEpilogue { CONV_EPI_LRELU = 0, CONV_EPI_PSU = 1, CONV_EPI_LINEAR = 2 };  // LINEAR: bias only
 
 struct ConvLayerPlan {
   int N, K;            // output / input channels

@@ -561,22 +561,32 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
 //  RGB_layer_2 after compositing (fold iv):  feat[b][c][ray] = sum_k W2[c][k] hc[b][ray][k] + b2[c] wsum ; bg_alpha = 1 - wsum
 // =====================================================================================================================
 constexpr int kHeadRays = 32;
-__global__ void __launch_bounds__(288) rgb_head_kernel(const float* __restrict__ aux, const float* __restrict__ hc,
-                                                       const float* __restrict__ wsum, int N_r, float* __restrict__ feat_ray,
-                                                       float* __restrict__ bg_alpha) {
-  __shared__ float s_h[kHeadRays][kH2 + 1];
+struct HeadArgs {
+  const float* aux[2];
+  const float* hc[2];
+  const float* wsum[2];
+  float* feat_ray[2];
+  float* bg_alpha[2];
+};
+// grid (ray tiles, B, n_branch); thread = output channel, 32 rays per CTA; hidden rows staged in smem and read as float4 (4 k per LDS)
+__global__ void __launch_bounds__(288) rgb_head_kernel(const HeadArgs ha, int N_r) {
+  __shared__ __align__(16) float s_h[kHeadRays][kH2 + 4];
   __shared__ float s_w[kHeadRays];
+  const int br = blockIdx.z;
+  const float* __restrict__ aux = ha.aux[br];
+  const float* __restrict__ hc = ha.hc[br];
+  const float* __restrict__ wsum = ha.wsum[br];
   const int b = blockIdx.y;
   const int r0 = blockIdx.x * kHeadRays;
   const int nr = min(kHeadRays, N_r - r0);
-  for (int i = threadIdx.x; i < nr * kH2; i += blockDim.x) {
+  for (int i = threadIdx.x; i < kHeadRays * kH2; i += blockDim.x) {
     int r = i / kH2, k = i - r * kH2;
-    s_h[r][k] = hc[((size_t)b * N_r + r0 + r) * kH2 + k];
+    s_h[r][k] = (r < nr) ? hc[((size_t)b * N_r + r0 + r) * kH2 + k] : 0.0f;
   }
   for (int i = threadIdx.x; i < kHeadRays; i += blockDim.x) {
     float w = (i < nr) ? wsum[(size_t)b * N_r + r0 + i] : 0.0f;
     s_w[i] = w;
-    if (i < nr) bg_alpha[(size_t)b * N_r + r0 + i] = 1.0f - w;   // utils/model_utils.py:531-532
+    if (i < nr) ha.bg_alpha[br][(size_t)b * N_r + r0 + i] = 1.0f - w;   // utils/model_utils.py:531-532
   }
   __syncthreads();
   const int c = threadIdx.x;
@@ -585,13 +595,17 @@ __global__ void __launch_bounds__(288) rgb_head_kernel(const float* __restrict__
   float acc[kHeadRays];
 #pragma unroll
   for (int r = 0; r < kHeadRays; ++r) acc[r] = 0.0f;
-  for (int k = 0; k < kH2; ++k) {
-    float w = __ldg(w2t + (size_t)k * kFeat + c);
+  for (int k = 0; k < kH2; k += 4) {
+    const float w0 = __ldg(w2t + (size_t)(k + 0) * kFeat + c), w1 = __ldg(w2t + (size_t)(k + 1) * kFeat + c);
+    const float w2 = __ldg(w2t + (size_t)(k + 2) * kFeat + c), w3 = __ldg(w2t + (size_t)(k + 3) * kFeat + c);
 #pragma unroll
-    for (int r = 0; r < kHeadRays; ++r) acc[r] = fmaf(w, s_h[r][k], acc[r]);
+    for (int r = 0; r < kHeadRays; ++r) {
+      const float4 h = *reinterpret_cast<const float4*>(&s_h[r][k]);
+      acc[r] = fmaf(w3, h.w, fmaf(w2, h.z, fmaf(w1, h.y, fmaf(w0, h.x, acc[r]))));
+    }
   }
   const float b2 = __ldg(aux + kAuxB2 + c);
-  float* dst = feat_ray + ((size_t)b * kFeat + c) * N_r + r0;
+  float* dst = ha.feat_ray[br] + ((size_t)b * kFeat + c) * N_r + r0;
 #pragma unroll
   for (int r = 0; r < kHeadRays; ++r)
     if (r < nr) dst[r] = fmaf(b2, s_w[r], acc[r]);
@@ -846,12 +860,20 @@ extern "C" int gnrf_mlp_tc_fwd(int n_branch, const void* const* packed, const fl
   if (grid > kMaxGrid) grid = kMaxGrid;
   mlp_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
   GNRF_LAUNCH_CHECK();
-  for (int i = 0; i < n_branch; ++i) {
-    const float* aux = reinterpret_cast<const float*>(static_cast<const unsigned char*>(packed[i]) + kStreamBytes);
-    dim3 g(ceil_div(N_r, kHeadRays), B);
-    rgb_head_kernel<<<g, 288, 0, st>>>(aux, a.br[i].hc, a.br[i].wsum, N_r, feat_ray[i], bg_alpha[i]);
+  {
+    HeadArgs ha;
+    for (int i = 0; i < 2; ++i) {
+      int j = i < n_branch ? i : 0;
+      ha.aux[i] = reinterpret_cast<const float*>(static_cast<const unsigned char*>(packed[j]) + kStreamBytes);
+      ha.hc[i] = a.br[j].hc;
+      ha.wsum[i] = a.br[j].wsum;
+      ha.feat_ray[i] = feat_ray[j];
+      ha.bg_alpha[i] = bg_alpha[j];
+    }
+    dim3 g(ceil_div(N_r, kHeadRays), B, n_branch);
+    rgb_head_kernel<<<g, 288, 0, st>>>(ha, N_r);
   }
   GNRF_LAUNCH_CHECK();
-  count_launches(1 + n_branch);
+  count_launches(2);
   return GNRF_OK;
 }

@@ -151,6 +151,76 @@ __global__ void to_rgb_kernel(const float* __restrict__ W, const float* __restri
   }
 }
 
+
+// net = LeakyReLU(Blur(pre)) and rgb = rgb_prev + feat_2_rgb(net) (+ sigmoid) in one pass.
+// Used after an UN-activated feat conv: Blur (depthwise, weights sum to 1, reflect border) commutes with the 1x1 conv and its bias,
+// so LeakyReLU(conv(Blur(x))) == LeakyReLU(Blur(conv(x)))  (neural_renderer.py:103-106, pixel_shuffle_upsample.py:7-16, 41).
+// One thread = 4 consecutive x of one row, all channels (float4 loads/stores; edge taps come from the neighbours' cache lines).
+__global__ void __launch_bounds__(256) blur_lrelu_rgb_kernel(const float* __restrict__ pre, int C, int H, int Wd,
+                                                            const float* __restrict__ rgb_w, const float* __restrict__ rgb_b,
+                                                            const float* __restrict__ rgb_prev, int do_sigmoid,
+                                                            float* __restrict__ net, float* __restrict__ rgb) {
+  extern __shared__ float s_w[];  // [3][C]
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_w[i] = rgb_w[i];
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int W4 = Wd >> 2;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= H * W4) return;
+  const int y = q / W4, x0 = (q - y * W4) * 4;
+  const int ym = reflect(y - 1, H), yp = reflect(y + 1, H);
+  const int xl = reflect(x0 - 1, Wd), xr = reflect(x0 + 4, Wd);
+  const size_t HW = (size_t)H * Wd;
+  const float* pl = pre + (size_t)n * C * HW;
+  float* po = net + (size_t)n * C * HW;
+  float acc[3][4];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[j][i] = 0.0f;
+#pragma unroll 2
+  for (int c = 0; c < C; ++c) {
+    const float* pc = pl + (size_t)c * HW;
+    float col[6];  // vertically blurred columns x0-1 .. x0+4 (weights 1,2,1)
+    {
+      const float4 a = *reinterpret_cast<const float4*>(pc + (size_t)ym * Wd + x0);
+      const float4 b = *reinterpret_cast<const float4*>(pc + (size_t)y * Wd + x0);
+      const float4 d = *reinterpret_cast<const float4*>(pc + (size_t)yp * Wd + x0);
+      col[1] = a.x + 2.0f * b.x + d.x; col[2] = a.y + 2.0f * b.y + d.y;
+      col[3] = a.z + 2.0f * b.z + d.z; col[4] = a.w + 2.0f * b.w + d.w;
+      col[0] = pc[(size_t)ym * Wd + xl] + 2.0f * pc[(size_t)y * Wd + xl] + pc[(size_t)yp * Wd + xl];
+      col[5] = pc[(size_t)ym * Wd + xr] + 2.0f * pc[(size_t)y * Wd + xr] + pc[(size_t)yp * Wd + xr];
+    }
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = lrelu((col[i] + 2.0f * col[i + 1] + col[i + 2]) * 0.0625f);
+    *reinterpret_cast<float4*>(po + (size_t)c * HW + (size_t)y * Wd + x0) = make_float4(o[0], o[1], o[2], o[3]);
+    const float w0 = s_w[c], w1 = s_w[C + c], w2 = s_w[2 * C + c];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[0][i] = fmaf(w0, o[i], acc[0][i]);
+      acc[1][i] = fmaf(w1, o[i], acc[1][i]);
+      acc[2][i] = fmaf(w2, o[i], acc[2][i]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const size_t o = ((size_t)n * 3 + j) * HW + (size_t)y * Wd + x0;
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = acc[j][i] + rgb_b[j];
+    if (rgb_prev != nullptr) {
+      const float4 pr = *reinterpret_cast<const float4*>(rgb_prev + o);
+      v[0] += pr.x; v[1] += pr.y; v[2] += pr.z; v[3] += pr.w;
+    }
+    if (do_sigmoid) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = 1.0f / (1.0f + expf(-v[i]));
+    }
+    *reinterpret_cast<float4*>(rgb + o) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 // out = Blur(bilinear_up2(in)), in [planes,H,W] -> out [planes,2H,2W]  (neural_renderer.py:65-67).
 __device__ __forceinline__ float up2_at(const float* pl, int H, int Wd, int Y, int X) {
   // bilinear, align_corners=False, scale 2: src = (dst + .5)/2 - .5, clamped at 0 (PyTorch semantics)
@@ -291,32 +361,39 @@ static int nr_forward(const float* const* params, const unsigned char* packed, c
     }
     s *= 2;
     HW = s * s;
-    {
-      long long total = (long long)N * ci * HW;
-      blur3x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sh, s, s, total, bl);
-    }
     float* net_out = netbuf[i & 1];
+    bool last = (i == n_blocks - 1);
     if (packed != nullptr) {
-      int rc = tc::conv_tc_launch(pl3, packed + pk_off + pl1.total_bytes + pl2.total_bytes, bl, net_out, nullptr, 1, N, HW, s,
-                                  tc::CONV_EPI_LRELU, st);
+      // feat_layers[i] un-activated on tensor cores (into `bl`), then ONE pass: net = LeakyReLU(Blur(.)), rgb += feat_2_rgb(net)
+      int rc = tc::conv_tc_launch(pl3, packed + pk_off + pl1.total_bytes + pl2.total_bytes, sh, bl, nullptr, 1, N, HW, s,
+                                  tc::CONV_EPI_LINEAR, st);
       if (rc != GNRF_OK) return rc;
-    } else {  // feat_layers[i]: ci -> co, LeakyReLU
-      dim3 grid(ceil_div(HW, BN), ceil_div(co, BM), N);
-      conv1x1_kernel<EPI_LRELU><<<grid, kGemmThreads, 0, st>>>(feat_w(i), feat_b(i), bl, co, ci, HW, s, nullptr, 1, net_out);
+      dim3 grid(ceil_div(HW / 4, 256), N);
+      blur_lrelu_rgb_kernel<<<grid, 256, 3 * co * sizeof(float), st>>>(bl, co, s, s, rgb_w(i + 1), rgb_bi(i + 1), rgb_up, last ? 1 : 0,
+                                                                      net_out, last ? img : rgb_cur);
       count_launches(1);
+    } else {
+      {
+        long long total = (long long)N * ci * HW;
+        blur3x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sh, s, s, total, bl);
+      }
+      {  // feat_layers[i]: ci -> co, LeakyReLU
+        dim3 grid(ceil_div(HW, BN), ceil_div(co, BM), N);
+        conv1x1_kernel<EPI_LRELU><<<grid, kGemmThreads, 0, st>>>(feat_w(i), feat_b(i), bl, co, ci, HW, s, nullptr, 1, net_out);
+      }
+      launch_rgb(rgb_w(i + 1), rgb_bi(i + 1), net_out, co, HW, rgb_up, last ? 1 : 0, last ? img : rgb_cur);
+      count_launches(3);
     }
     pk_off += pl1.total_bytes + pl2.total_bytes + pl3.total_bytes;
-    bool last = (i == n_blocks - 1);
-    launch_rgb(rgb_w(i + 1), rgb_bi(i + 1), net_out, co, HW, rgb_up, last ? 1 : 0, last ? img : rgb_cur);
     if (!last) {
       float* dst = (rgb_cur == rgb_a) ? rgb_b : rgb_a;  // == rgb_up's buffer, whose contents are now consumed
       launch_up(rgb_cur, s, dst);
       rgb_up = dst;
       rgb_cur = (dst == rgb_a) ? rgb_b : rgb_a;
+      count_launches(1);
     }
     net = net_out;
     GNRF_LAUNCH_CHECK();
-    count_launches(last ? 2 : 3);  // blur, to_rgb (+ rgb_up_blur); the conv launches are counted where they are issued
   }
   return GNRF_OK;
 }
