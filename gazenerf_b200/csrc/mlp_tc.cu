@@ -19,7 +19,7 @@
 // On-chip layout per CTA (1 CTA / SM, 192 threads = 4 epilogue warps + 1 TMA warp + 1 MMA warp):
 //   smem  A_hi       : 6 K-blocks x [128 rows x 64 bf16], SWIZZLE_128B K-major (UMMA canonical)          96 KB
 //         A_lo[4..5] : K-blocks 4,5 of the low halves, same layout                                        32 KB
-//         W ring     : 6 x 16 KB stages; a stage = one K-slice of one accumulator block, W_hi then W_lo (no-swizzle
+//         W ring     : 3 x 32 KB stages; a stage = one K-slice of one accumulator block, W_hi then W_lo (no-swizzle
 //                      K-major core-matrix layout), streamed from the pre-arranged packed image in L2 by cp.async.bulk
 //                      (TMA bulk copy) + mbarrier complete_tx                                              96 KB
 //   TMEM  columns 0..383   : fp32 accumulators (block 0 = cols 0..127, block 1 = cols 128..383)
@@ -50,8 +50,8 @@ constexpr int kTile = 128;               // points per tile == UMMA M
 constexpr int kKB = 64;                  // K-block (bf16 elements) == 128-byte swizzle span
 constexpr int kNumKB = kHidden / kKB;    // 6
 constexpr int kL8N = 208;                // 192 + 1 density + 15 zero rows
-constexpr int kSlotBytes = 16384;        // W ring slot (W_hi slice + W_lo slice)
-constexpr int kStages = 6;
+constexpr int kSlotBytes = 32768;        // W ring slot (W_hi slices + W_lo slices of one stage)
+constexpr int kStages = 3;
 constexpr int kALoTmemKB = 4;            // A_lo K-blocks 0..3 live in TMEM, 4..5 in smem
 constexpr int kALoCol = 384;             // first TMEM column of A_lo
 constexpr int kABlockBytes = kTile * 128;            // 16384: one K-block of A (hi or lo)
@@ -68,8 +68,9 @@ constexpr int kScratchLd = 193;          // composite scratch row stride (floats
 // cycles, which hides the ~100-cycle scalar cost of issuing one tcgen05.mma from a single thread (measured, profiles/).
 // A ring stage is a K-slice of one block: [nrows x 16] bf16 per K16 step in the no-swizzle K-major core-matrix layout
 // (8 rows x 16 B contiguous, K-halves 128 B apart, 8-row groups 256 B apart), the W_hi slice followed by the W_lo slice;
-// blk 0 stages carry two K16 steps so that all stages are 16 KB = 384 tensor cycles of work (layer 8's N=80 block: 5 KB),
-// enough to hide the ~200-cycle scalar cost of one stage (mbarrier try_wait, fences, issue).  Stream == consumption order:
+// a stage is 4 K16 steps of blk 0 or 2 of blk 1 = 32 KB = 768 tensor cycles (layer 8's N=80 block: 10 KB): the UMMA queue is
+// shallow, so the ~150-300 cycles of scalar work between bursts (try_wait, fence, descriptors) are only hidden when bursts are
+// long (measured, tests/ubench/ub_mix.cu: 6-UMMA bursts of N=128 ran at 525-680 cycles instead of 384).  Stream == consumption order:
 //   for layer: for phase (layer 5 only: hidden columns, then PE columns): for blk: for K-slice: one stage
 struct StageInfo {
   int layer, phase2, blk, ks, nk16, n0, nrows;
@@ -84,7 +85,7 @@ __host__ __device__ inline void for_each_stage(F&& f) {
       for (int blk = 0; blk < 2; ++blk) {
         const int n0 = blk ? 128 : 0;
         const int nrows = blk ? (layer == 8 ? 80 : 256) : 128;
-        const int step = blk ? 1 : 2;
+        const int step = blk ? 2 : 4;   // K16 steps per stage
         for (int ks = 0; ks < k16n; ks += step) {
           StageInfo st{layer, ph, blk, ks, step, n0, nrows, (uint32_t)(2 * nrows * 32 * step)};
           f(st);
@@ -98,7 +99,7 @@ constexpr int stage_count() {
   for (int layer = 0; layer < 9; ++layer)
     for (int ph = 0; ph < ((layer == 5) ? 2 : 1); ++ph) {
       const int k16n = (layer == 0 || ph == 1) ? 4 : 24;
-      n += (k16n / 2) + k16n;
+      n += (k16n / 4) + (k16n / 2);
     }
   return n;
 }
@@ -111,7 +112,7 @@ constexpr size_t stream_bytes() {
     }
   return n;
 }
-constexpr int kNumStagesPerTile = stage_count();   // 300
+constexpr int kNumStagesPerTile = stage_count();   // 150
 constexpr size_t kStreamBytes = stream_bytes();
 // fp32 auxiliary block (float offsets from aux base)
 constexpr int kBiasFloats = 8 * kHidden + kL8N;                       // 3280 per face
@@ -204,11 +205,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // Thread-block cluster (1, 2 or 4 CTAs): the CTAs of a cluster work on tiles of the SAME branch in lockstep; each loads 1/csize
+  // of every weight stage from L2 and multicasts it to all of them (the weight feed was L2-bandwidth bound, profiles/).
+  const int csize = (int)cluster_nctarank();
+  const int crank = (int)cluster_ctarank();
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
+  const int n_citems = args.n_items / csize;           // cluster work items
+  const int cluster_id = (int)blockIdx.x / csize, n_clusters = (int)gridDim.x / csize;
+  // cluster item -> (branch, face, tile) of THIS CTA
+  auto decode_item = [&](int ci, int& branch, int& b, int& tile) {
+    branch = ci % args.n_branch;
+    const int t = (ci / args.n_branch) * csize + crank;
+    b = t / args.tiles_per_face;
+    tile = t - b * args.tiles_per_face;
+  };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(bar(kBarWFull + i), 1);
-      mbar_init(bar(kBarWEmpty + i), 1);
+      mbar_init(bar(kBarWEmpty + i), (uint32_t)csize);   // released by the MMA warp of every CTA of the cluster
     }
     for (int i = 0; i < kNumKB; ++i) mbar_init(bar(kBarAReady + i), 4);  // one arrive per epilogue warp
     mbar_init(bar(kBarAccFull), 1);
@@ -218,20 +233,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
   if (warp == 5) tmem_alloc_512(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)));
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();   // every CTA's barriers are initialised before any peer signals them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 4) {
     // =============================================== TMA producer ===============================================
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t slot = 0, phase = 0;
-      for (int item = blockIdx.x; item < args.n_items; item += gridDim.x) {
-        const int branch = item % args.n_branch;
+      for (int ci = cluster_id; ci < n_citems; ci += n_clusters) {
+        const int branch = ci % args.n_branch;
         const unsigned char* src = args.br[branch].stream;
         for_each_stage([&](const StageInfo& st) {  // strictly in consumption order
-          mbar_wait(bar(kBarWEmpty + slot), phase ^ 1);
-          mbar_arrive_expect_tx(bar(kBarWFull + slot), st.bytes);
-          bulk_g2s(smem_base + kSmemRing + slot * kSlotBytes, src, st.bytes, bar(kBarWFull + slot));
+          mbar_wait_spin(bar(kBarWEmpty + slot), phase ^ 1);           // slot free in EVERY CTA of the cluster
+          mbar_arrive_expect_tx(bar(kBarWFull + slot), st.bytes);       // the whole stage: own slice + the peers' multicasts
+          const uint32_t part = st.bytes / (uint32_t)csize;
+          const uint32_t dst = smem_base + kSmemRing + slot * kSlotBytes + (uint32_t)crank * part;
+          if (csize == 1) bulk_g2s(dst, src, part, bar(kBarWFull + slot));
+          else bulk_g2s_multicast(dst, src + (size_t)crank * part, part, bar(kBarWFull + slot), cmask);
           src += st.bytes;
           if (++slot == kStages) { slot = 0; phase ^= 1; }
         });
@@ -240,21 +259,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
     __syncwarp();
   } else if (warp == 5) {
     // =============================================== MMA issuer =================================================
-    // The whole warp runs this loop converged on warp-uniform values; one elected lane issues the tcgen05 instructions.
-    {
+    // ONE elected lane runs the whole issue loop (measured, tests/ubench/ub_stage.cu: a per-stage elect + __syncwarp in a
+    // converged-warp loop costs ~136 cycles per stage, which bursts of 64-cycle N=128 UMMAs cannot hide; inside a single
+    // elect.sync region the compiler keeps descriptors in uniform registers and the loop runs at the tensor-pipe rate).
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t sbase_u = __shfl_sync(0xffffffffu, smem_base, 0);
+    if (elect_one()) {
       uint32_t slot = 0, wphase = 0;
       uint32_t a_phase = 0;  // bit kb = parity of the next completion of a_ready[kb]
       bool prof_on = false;
       long long w_stall = 0, a_stall = 0;
-      int prof_item = 0;
+      int prof_item = 0, prof_layer = 0;
       auto stamp = [&](int layer, int k) {
-        if (prof_on && lane == 0) {
+        prof_layer = layer;
+        if (prof_on) {
           long long* p = args.prof + ((size_t)prof_item * 10 + layer) * 16;
           p[k] = clock64(); p[k + 1] = w_stall; p[k + 2] = a_stall;
         }
       };
-      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint32_t sbase_u = __shfl_sync(0xffffffffu, smem_base, 0);
       constexpr uint32_t kDescHiSw128 = (uint32_t)((1024 >> 4) | (1u << 14) | (2u << 29));   // SBO, version, SWIZZLE_128B
       constexpr uint32_t kDescHiNoSw = (uint32_t)((256 >> 4) | (1u << 14));                  // SBO, version, no swizzle
       constexpr uint32_t kDescLoLboSw = 1u << 16, kDescLoLboNo = (128u >> 4) << 16;
@@ -262,73 +284,71 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
       const uint32_t a_lo45_lo0 = (((sbase_u + kSmemALo45) >> 4) & 0x3FFFu) | kDescLoLboSw;
       auto mk = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
 
-      // One ring stage = NK16 K16-steps of one accumulator block: per step  A_hi*W_hi + A_lo*W_hi + A_hi*W_lo.
+      // One ring stage = NK16 K16-steps of one accumulator block: per step  A_hi*W_hi, A_hi*W_lo, A_lo*W_hi.
       auto do_stage = [&](auto nrows_c, auto nk16_c, uint32_t d_col, int a_k16, bool fresh) {
         constexpr int NROWS = decltype(nrows_c)::value, NK16 = decltype(nk16_c)::value;
         constexpr uint32_t idesc = umma_idesc_bf16(128, NROWS);
         constexpr uint32_t kSliceU = (uint32_t)((NROWS * 32) >> 4);  // one K16 slice, in 16-byte units
         const long long tw0 = prof_on ? clock64() : 0;
-        mbar_wait(bar(kBarWFull + slot), wphase);
+        mbar_wait_spin(bar(kBarWFull + slot), wphase);
         if (prof_on) w_stall += clock64() - tw0;
         tc_fence_after_sync();
         const uint32_t b_hi0 = (((sbase_u + kSmemRing + slot * kSlotBytes) >> 4) & 0x3FFFu) | kDescLoLboNo;
         const uint32_t b_lo0 = b_hi0 + NK16 * kSliceU;
         const uint32_t d = tmem_u + d_col;
-        if (elect_one()) {
 #pragma unroll
-          for (int i = 0; i < NK16; ++i) {
-            const int k16 = a_k16 + i;
-            const int kb = k16 >> 2;
-            // A_hi: SW128 K-block kb, +32 B per K16 step inside the 128-byte swizzle span
-            const uint64_t a_hi = mk(a_hi_lo0 + (uint32_t)((kb * kABlockBytes + (k16 & 3) * 32) >> 4), kDescHiSw128);
-            const uint64_t b_hi = mk(b_hi0 + i * kSliceU, kDescHiNoSw);
-            const uint64_t b_lo = mk(b_lo0 + i * kSliceU, kDescHiNoSw);
-            umma_ss(d, a_hi, b_hi, idesc, (fresh && i == 0) ? 0u : 1u);
-            if (kb < kALoTmemKB)
-              umma_ts(d, tmem_u + (uint32_t)(kALoCol + kb * 32 + (k16 & 3) * 8), b_hi, idesc, 1u);
-            else
-              umma_ss(d, mk(a_lo45_lo0 + (uint32_t)(((kb - kALoTmemKB) * kABlockBytes + (k16 & 3) * 32) >> 4), kDescHiSw128), b_hi,
-                      idesc, 1u);
-            umma_ss(d, a_hi, b_lo, idesc, 1u);
-          }
-          umma_commit(bar(kBarWEmpty + slot));
+        for (int i = 0; i < NK16; ++i) {
+          const int k16 = a_k16 + i;
+          const int kb = k16 >> 2;
+          // A_hi: SW128 K-block kb, +32 B per K16 step inside the 128-byte swizzle span
+          const uint64_t a_hi = mk(a_hi_lo0 + (uint32_t)((kb * kABlockBytes + (k16 & 3) * 32) >> 4), kDescHiSw128);
+          const uint64_t b_hi = mk(b_hi0 + i * kSliceU, kDescHiNoSw);
+          const uint64_t b_lo = mk(b_lo0 + i * kSliceU, kDescHiNoSw);
+          // A_hi is used by two consecutive UMMAs: read it from smem once (A collector fill / lastuse)
+          umma_ss_a_fill(d, a_hi, b_hi, idesc, (fresh && i == 0) ? 0u : 1u);
+          umma_ss_a_lastuse(d, a_hi, b_lo, idesc, 1u);
+          if (kb < kALoTmemKB)
+            umma_ts(d, tmem_u + (uint32_t)(kALoCol + kb * 32 + (k16 & 3) * 8), b_hi, idesc, 1u);
+          else
+            umma_ss(d, mk(a_lo45_lo0 + (uint32_t)(((kb - kALoTmemKB) * kABlockBytes + (k16 & 3) * 32) >> 4), kDescHiSw128), b_hi,
+                    idesc, 1u);
         }
-        __syncwarp();
+        if (csize == 1) umma_commit(bar(kBarWEmpty + slot));
+        else umma_commit_multicast(bar(kBarWEmpty + slot), cmask);
         if (++slot == kStages) { slot = 0; wphase ^= 1; }
       };
       auto wait_a = [&](int kb) {
         const long long ta0 = prof_on ? clock64() : 0;
-        mbar_wait(bar(kBarAReady + kb), (a_phase >> kb) & 1u);
+        mbar_wait_spin(bar(kBarAReady + kb), (a_phase >> kb) & 1u);
         if (prof_on) a_stall += clock64() - ta0;
         a_phase ^= (1u << kb);
         tc_fence_after_sync();
       };
-      auto commit_bar = [&](int which) {
-        if (elect_one()) umma_commit(bar(which));
-        __syncwarp();
-      };
       // all K-slices of both accumulator blocks (blk 0: N=128, two K16 steps per stage; blk 1: N=256 / 80, one step)
       auto run_pass = [&](auto n1_c, int k16n, bool pe_pass, bool fresh_start) {
-        for (int ks = 0; ks < k16n; ks += 2) {
+        for (int ks = 0; ks < k16n; ks += 4) {   // blk 0: one stage = one A K-block (4 K16 steps, 12 UMMAs of N=128)
           // blk 0 touches each A K-block first; its first UMMA overwrites columns 0..127 = K-blocks 0 and 1 of the previous
           // accumulator, so both must have been drained before it is issued.
-          if (!pe_pass && (ks & 3) == 0) {
+          if (!pe_pass) {
             if (ks == 0) { wait_a(0); wait_a(1); }
             else if (ks >= 8) wait_a(ks >> 2);
           }
-          do_stage(std::integral_constant<int, 128>{}, std::integral_constant<int, 2>{}, 0u, ks, fresh_start && ks == 0);
+          do_stage(std::integral_constant<int, 128>{}, std::integral_constant<int, 4>{}, 0u, ks, fresh_start && ks == 0);
+          if (prof_on && k16n == 24 && ks >= 4) args.prof[((size_t)prof_item * 10 + prof_layer) * 16 + 10 + (ks >> 2)] = clock64();
         }
-        for (int ks = 0; ks < k16n; ++ks) do_stage(n1_c, std::integral_constant<int, 1>{}, 128u, ks, fresh_start && ks == 0);
+        if (prof_on && k16n == 24) args.prof[((size_t)prof_item * 10 + prof_layer) * 16 + 10] = clock64();  // blk 0 issued
+        for (int ks = 0; ks < k16n; ks += 2)     // blk 1: 2 K16 steps, 6 UMMAs of N=256 (80 for layer 8)
+          do_stage(n1_c, std::integral_constant<int, 2>{}, 128u, ks, fresh_start && ks == 0);
       };
 
-      for (int item = blockIdx.x; item < args.n_items; item += gridDim.x) {
-        prof_item = item / (int)gridDim.x;
+      for (int ci = cluster_id; ci < n_citems; ci += n_clusters) {
+        prof_item = ci / n_clusters;
         prof_on = (args.prof != nullptr) && blockIdx.x == 0 && prof_item < 4;
         // ---- layer 0: K = 64 (PE in K-block 0)
         stamp(0, 0);
         wait_a(0);
         run_pass(std::integral_constant<int, 256>{}, 4, true, true);
-        commit_bar(kBarAccFull);
+        umma_commit(bar(kBarAccFull));
         stamp(0, 3);
         // ---- layers 1..7
         for (int layer = 1; layer < 8; ++layer) {
@@ -336,21 +356,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
           run_pass(std::integral_constant<int, 256>{}, 24, false, true);
           if (layer == 5) {
             // skip connection: the PE columns of FeaExt_module_5 (models/mlp_nerf.py:106-107); the epilogue re-stages
-            // the parked PE into K-block 0 once every read of the hidden K-blocks has completed.
-            commit_bar(kBarAFree);
+            // the tile's PE into K-block 0 once every read of the hidden K-blocks has completed.
+            umma_commit(bar(kBarAFree));
             wait_a(0);
             run_pass(std::integral_constant<int, 256>{}, 4, true, false);
           }
-          commit_bar(kBarAccFull);
+          umma_commit(bar(kBarAccFull));
           stamp(layer, 3);
         }
         // ---- layer 8: [RGB_0*RGB_1 (192) | density (1) | pad] = N 128 + 80
         stamp(8, 0);
         run_pass(std::integral_constant<int, 80>{}, 24, false, true);
-        commit_bar(kBarAccFull);
+        umma_commit(bar(kBarAccFull));
         stamp(8, 3);
       }
     }
+    __syncwarp();
   } else {
     // =============================================== epilogue warps (0..3) =======================================
     const int row = threadIdx.x;                                   // TMEM lane == tile row == sample point
@@ -370,10 +391,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
       if (lane == 0) mbar_arrive(bar(kBarAReady + kb));
     };
     // sample point of (item, row) -> positional encoding + delta, written to the stash (read back by the same thread)
-    auto stash_pe = [&](int item) {
-      const int t = item / args.n_branch;
-      const int b = t / args.tiles_per_face;
-      const int tile = t - b * args.tiles_per_face;
+    auto stash_pe = [&](int ci) {
+      int branch_, b, tile;
+      decode_item(ci, branch_, b, tile);
       const int ray = tile * rays_per_tile + row / N_s;
       const int s = row - (row / N_s) * N_s;
       const float4 dl = args.ray_dl[(size_t)b * args.N_r + ray];
@@ -390,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
         stash[(size_t)(32 + q) * kTile] = lo[q];
       }
       stash[(size_t)64 * kTile] = __float_as_uint(delta);
-      if (args.dbg != nullptr && item == 0)
+      if (args.dbg != nullptr && ci == 0 && blockIdx.x == 0)
         for (int j = 0; j < 64; ++j) args.dbg[(size_t)row * kHidden + j] = pe[j];
     };
     // stash -> A K-block 0 (hi: smem, lo: TMEM), then release it to the MMA warp
@@ -405,26 +425,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
       release_kb(0);
     };
 
-    if ((int)blockIdx.x < args.n_items) {
-      stash_pe(blockIdx.x);
+    if (cluster_id < n_citems) {
+      stash_pe(cluster_id);
       stage_pe();
     }
-    for (int item = blockIdx.x; item < args.n_items; item += gridDim.x) {
-      const int branch = item % args.n_branch;
-      const int t = item / args.n_branch;
-      const int b = t / args.tiles_per_face;
-      const int tile = t - b * args.tiles_per_face;
+    for (int item = cluster_id; item < n_citems; item += n_clusters) {
+      int branch, b, tile;
+      decode_item(item, branch, b, tile);
       const BranchArgs& br = args.br[branch];
       const float* bias = br.bias + (size_t)b * kBiasFloats;
-      const bool dump = (args.dbg != nullptr) && (item == 0);
-      const int next_item = item + (int)gridDim.x;
+      const bool dump = (args.dbg != nullptr) && (item == 0) && blockIdx.x == 0;
+      const int next_item = item + n_clusters;
       const int ray = tile * rays_per_tile + row / N_s;
       const int s = row - (row / N_s) * N_s;
       const float delta = __uint_as_float(stash[(size_t)64 * kTile]);
 
       // ---- trunk: drain layer l accumulators into A as the input of layer l+1 ----------------------------------
-      const bool eprof = (args.prof != nullptr) && blockIdx.x == 0 && (item / (int)gridDim.x) < 4 && threadIdx.x == 0;
-      long long* ep = eprof ? args.prof + ((size_t)(item / (int)gridDim.x) * 10) * 16 : nullptr;
+      const bool eprof = (args.prof != nullptr) && blockIdx.x == 0 && (item / n_clusters) < 4 && threadIdx.x == 0;
+      long long* ep = eprof ? args.prof + ((size_t)(item / n_clusters) * 10) * 16 : nullptr;
       if (eprof) ep[6] = clock64();  // layer-0 row: K-block 0 (PE) of this tile released
       for (int layer = 0; layer < 8; ++layer) {
         mbar_wait(bar(kBarAccFull), acc_phase);
@@ -465,6 +483,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
             for (int j = 0; j < 64; ++j) args.dbg[((size_t)(layer + 1) * kTile + row) * kHidden + kb * 64 + j] = v[j];
           release_kb(kb);
           if (eprof && (kb == 1 || kb == 5)) ep[layer * 16 + (kb == 1 ? 8 : 9)] = clock64();  // K-blocks 0..1 / all released
+          if (eprof && kb == 3 && layer > 0) ep[layer * 16 + 6] = clock64();
         }
         if (layer == 4) {
           // layer 5 = [hidden | PE] (skip connection, models/mlp_nerf.py:106-107): once the MMA warp has consumed the hidden
@@ -475,7 +494,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
           stage_pe();
         }
         // idle window (the MMA warp is busy with layer 7): prepare the next tile's positional encoding
-        if (layer == 6 && next_item < args.n_items) stash_pe(next_item);
+        if (layer == 6 && next_item < n_citems) stash_pe(next_item);
       }
 
       // ---- last stage: density -> alpha -> transmittance scan -> weights; composite the 192-d hidden per ray ----
@@ -529,7 +548,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
       }
       scratch[row * kScratchLd + kH2] = w_k;
       // the accumulators are drained: hand the next tile's layer 0 to the MMA warp BEFORE the cross-row reduction
-      if (next_item < args.n_items) stage_pe();
+      if (next_item < n_citems) stage_pe();
       else tc_fence_before_sync();
       named_bar_sync(1, kEpiThreads);
       {
@@ -551,6 +570,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
   // ---- teardown ----------------------------------------------------------------------------------------------
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();   // no CTA may exit while a peer can still multicast into its smem or signal its barriers
   if (warp == 5) {
     tc_fence_after_sync();
     tmem_dealloc_512(tmem_base);
@@ -856,9 +876,32 @@ extern "C" int gnrf_mlp_tc_fwd(int n_branch, const void* const* packed, const fl
     const char* e = getenv("GNRF_TC_PROF_PTR");  // test hook: device pointer (decimal) of a [4][10][16] int64 timeline buffer
     if (e != nullptr) a.prof = reinterpret_cast<long long*>(strtoull(e, nullptr, 10));
   }
-  int grid = a.n_items < n_sm ? a.n_items : n_sm;
+  // cluster size: CTAs of a cluster share every weight stage through TMA multicast (default 2; GNRF_TC_CLUSTER=1|2|4)
+  int csize = 2;
+  {
+    const char* e = getenv("GNRF_TC_CLUSTER");
+    if (e != nullptr) csize = atoi(e);
+    if (csize != 1 && csize != 2 && csize != 4) csize = 2;
+    while (csize > 1 && ((B * a.tiles_per_face) % csize != 0 || a.n_items / csize < 1)) csize >>= 1;
+  }
+  int grid = (a.n_items / csize) * csize < n_sm ? (a.n_items / csize) * csize : n_sm;
   if (grid > kMaxGrid) grid = kMaxGrid;
-  mlp_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(a);
+  grid -= grid % csize;
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GNRF_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel, a));
+  }
   GNRF_LAUNCH_CHECK();
   {
     HeadArgs ha;
