@@ -315,3 +315,129 @@ def test_errors_raise_not_abort(dev):
     assert b"argument check failed" in L.gnrf_last_error()
     with pytest.raises(RuntimeError, match="libgnrf"):
         _lib.check(L.gnrf_compose_fwd(1, 1, 1, 1, 1, 1, 1, 4, 4, 1, S()), "gnrf_compose_fwd")
+
+
+# ----------------------------------------------------------------------------------------------- full-size / edge configurations
+def _default_net(dev, hier=False, n_s=64, n_fine=64):
+    opt = G.BaseOptions()
+    opt.num_sample_coarse = n_s
+    opt.num_sample_fine = n_fine
+    torch.manual_seed(45)
+    net = G.GazeNeRFNet(opt, include_vd=False, hier_sampling=hier)
+    return opt, net
+
+
+def _full_inputs(opt, B, cams_idx):
+    ru = G.RenderUtils(45, "cpu", opt)
+    shape, appea, gaze = O.synthetic_codes(B)
+    cams = [ru.cam_info_list[i] for i in cams_idx]
+    cam = {k: torch.cat([c[k] for c in cams], 0) for k in cams[0]}
+    return ru, dict(batch_xy=ru.ray_xy.expand(B, -1, -1), batch_uv=None, bg_code=None, shape_code=shape, appea_code=appea, gaze_code=gaze, **cam)
+
+
+def test_full_size_config2_tc_vs_simt_and_oracle_rays(dev):
+    """BASELINE config[1] size (64x64 rays x 64 samples -> 512x512), B=2 with two different orbit cameras:
+    (a) the folded bf16x3 tcgen05 kernel and the literal fp32 kernel agree on every ray / every output pixel;
+    (b) rays are independent, so the CPU oracle on every 32nd ray must match those rays of the full GPU render."""
+    opt, net = _default_net(dev)
+    B = 2
+    ru, kw = _full_inputs(opt, B, [5, 31])
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    oo = O.OracleOptions()
+    bf, be = O.calibrate_dense_bias(sd, oo, kw["batch_xy"], kw["shape_code"], kw["appea_code"], kw["gaze_code"], kw["batch_Rmats"],
+                                    kw["batch_Tvecs"], kw["batch_inv_inmats"], scale=4.0)
+    sd = O.densify(sd, bf, be, scale=4.0)
+    net.load_state_dict(sd)
+    net = net.to(dev).eval()
+    net.keep_stages = True
+    dkw = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in kw.items()}
+    outs, stages = {}, {}
+    for impl in ("tc", "simt"):
+        net.mlp_impl = impl
+        net.neural_render.impl = impl
+        outs[impl] = {k: v.clone() for k, v in net("test", **dkw)["coarse_dict"].items()}
+        stages[impl] = {k: net.last_stages[k].clone() for k in ("feat_face", "feat_eyes", "bg_alpha_face", "bg_alpha_eyes", "w_face")}
+    for k in stages["tc"]:
+        assert rel_l2(stages["tc"][k].cpu(), stages["simt"][k].cpu()) < TOL_TIGHT, k
+    for k in outs["tc"]:
+        assert outs["tc"][k].shape[-1] == 512
+        assert float((outs["tc"][k] - outs["simt"][k]).abs().max()) < TOL_TIGHT, k
+    a = stages["tc"]["bg_alpha_face"]
+    assert 0.05 < float(a.mean()) < 0.95 and float(a.min()) < 0.2 and float(a.max()) > 0.5  # non-vacuous: mixed opacity
+    # (b) oracle on a ray subset
+    step = 32
+    sub = O.sample_points(kw["batch_xy"][:, :, ::step].contiguous(), kw["batch_Rmats"], kw["batch_Tvecs"], kw["batch_inv_inmats"], 64, 2.5, -3.5)
+    br = O.render_branches(sd, oo, sub["pts"], sub["z_dists"], sub["zvals"], kw["shape_code"], kw["appea_code"], kw["gaze_code"])
+    for name in ("face", "eyes"):
+        got = stages["tc"]["feat_" + name].cpu()[:, :, ::step]
+        assert rel_l2(got, br[name][0]) < TOL_TIGHT, name
+        assert max_rel(stages["tc"]["bg_alpha_" + name].cpu()[:, ::step], br[name][1][:, 0]) < TOL_TIGHT, name
+
+
+def test_unsupported_sample_count_uses_fp32_cuda_path(dev):
+    """N_s = 24 does not divide the 128-row tile of the tcgen05 kernel: the module must run the literal fp32 CUDA kernels (still
+    libgnrf, never a CPU path) and match the oracle."""
+    opt = G.BaseOptions({"featmap_size": 8, "featmap_nc": 258, "pred_img_size": 64})
+    opt.num_sample_coarse = 24
+    torch.manual_seed(45)
+    net = G.GazeNeRFNet(opt, include_vd=False, hier_sampling=False)
+    assert not net._tc_supported(24)
+    ru, kw = _full_inputs(opt, 1, [9])
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    oo = O.OracleOptions(featmap_size=8, featmap_nc=258, pred_img_size=64, num_sample_coarse=24)
+    ref = O.forward(sd, oo, "test", kw["batch_xy"], kw["shape_code"], kw["appea_code"], kw["gaze_code"], kw["batch_Rmats"], kw["batch_Tvecs"],
+                    kw["batch_inv_inmats"])
+    net = net.to(dev).eval()
+    n0 = _lib.lib().gnrf_launch_count()
+    out = net("test", **{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in kw.items()})
+    assert _lib.lib().gnrf_launch_count() > n0
+    for k, v in ref["coarse_dict"].items():
+        assert float((out["coarse_dict"][k].cpu() - v).abs().max()) < TOL_TIGHT, k
+
+
+def test_hier_config3_sizes_one_ray_per_tile(dev):
+    """coarse 64 + fine 64 -> 128 sorted samples per ray (1 ray per 128-row tile), 16x16 rays: fused kernel vs the oracle pipeline."""
+    opt = G.BaseOptions({"featmap_size": 16, "featmap_nc": 258, "pred_img_size": 64})
+    opt.num_sample_coarse = 64
+    opt.num_sample_fine = 64
+    torch.manual_seed(45)
+    net = G.GazeNeRFNet(opt, include_vd=False, hier_sampling=True)
+    ru, kw = _full_inputs(opt, 1, [14])
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    oo = O.OracleOptions(featmap_size=16, featmap_nc=258, pred_img_size=64, num_sample_coarse=64, num_sample_fine=64)
+    bf, be = O.calibrate_dense_bias(sd, oo, kw["batch_xy"], kw["shape_code"], kw["appea_code"], kw["gaze_code"], kw["batch_Rmats"],
+                                    kw["batch_Tvecs"], kw["batch_inv_inmats"], scale=4.0)
+    sd = O.densify(sd, bf, be, scale=4.0)
+    net.load_state_dict(sd)
+    ref = O.forward_hier(sd, oo, kw["batch_xy"], kw["shape_code"], kw["appea_code"], kw["gaze_code"], kw["batch_Rmats"], kw["batch_Tvecs"],
+                         kw["batch_inv_inmats"], n_fine=64)
+    net = net.to(dev).eval()
+    net.keep_stages = True
+    assert net._tc_supported(128)
+    out = net("test", **{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in kw.items()})
+    st = net.last_stages
+    assert st["z_fine"].shape[-1] == 64 + 65 and "fine_dict" in out
+    assert (st["fine_inds"].cpu() != ref["fine_sample"]["inds"]).float().mean().item() < 0.01
+    assert bool((st["z_fine"][..., 1:] >= st["z_fine"][..., :-1]).all())
+    for br in ("face", "eyes"):
+        assert rel_l2(st["fine_feat_" + br].cpu(), ref["fine"][br][0]) < 5e-3, br
+
+
+def test_repeat_calls_and_weight_update_refresh_packed_cache(dev):
+    """Packed weights are a cache keyed on parameter versions: an in-place optimizer-style update must be picked up."""
+    g = load_golden("std_dense_test")
+    opt, net = _net_from_golden(g, dev, "tc")
+    kw = _inputs(g, dev)
+    a = net("test", **kw)["coarse_dict"]["merge_img"].clone()
+    b = net("test", **kw)["coarse_dict"]["merge_img"].clone()
+    assert torch.equal(a, b)  # deterministic
+    with torch.no_grad():
+        net.fg_CD_predictor_face.RGB_layer_2.bias.add_(0.5)
+        net.neural_render.feat_layers[0].bias.add_(0.1)
+    c = net("test", **kw)["coarse_dict"]["merge_img"]
+    assert float((c - a).abs().max()) > 1e-3
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    oo = O.OracleOptions(featmap_size=8, featmap_nc=258, pred_img_size=64, num_sample_coarse=8)
+    t = lambda k: torch.from_numpy(g[k])
+    ref = O.forward(sd, oo, "test", t("in_xy"), t("in_shape"), t("in_appea"), t("in_gaze"), t("in_R"), t("in_T"), t("in_Kinv"))
+    assert float((c.cpu() - ref["coarse_dict"]["merge_img"]).abs().max()) < TOL_TIGHT
