@@ -16,7 +16,7 @@
 //   (iv)  RGB_layer_2 is linear and un-activated: sum_s w_s (W h_s + b) = W (sum_s w_s h_s) + b sum_s w_s, so the 192-d hidden
 //         is composited per ray and RGB_layer_2 is applied once per ray by rgb_head_kernel (fp32 FMA).
 //
-// On-chip layout per CTA (1 CTA / SM, 192 threads = 4 epilogue warps + 1 TMA warp + 1 MMA warp):
+// On-chip layout per CTA (1 CTA / SM, 320 threads = 8 epilogue warps + 1 TMA warp + 1 MMA warp):
 //   smem  A_hi       : 6 K-blocks x [128 rows x 64 bf16], SWIZZLE_128B K-major (UMMA canonical)          96 KB
 //         A_lo[4..5] : K-blocks 4,5 of the low halves, same layout                                        32 KB
 //         W ring     : 3 x 32 KB stages; a stage = one K-slice of one accumulator block, W_hi then W_lo (no-swizzle
@@ -56,8 +56,8 @@ constexpr int kALoTmemKB = 4;            // A_lo K-blocks 0..3 live in TMEM, 4..
 constexpr int kALoCol = 384;             // first TMEM column of A_lo
 constexpr int kABlockBytes = kTile * 128;            // 16384: one K-block of A (hi or lo)
 constexpr int kABytes = kNumKB * kABlockBytes;       // 98304
-constexpr int kEpiThreads = 128;
-constexpr int kThreads = 192;
+constexpr int kEpiThreads = 256;         // 8 epilogue warps: warp w drains TMEM lanes 32*(w%4).. and column half (w/4) of each K-block
+constexpr int kThreads = 320;            // + 1 TMA producer warp (8) + 1 MMA issue warp (9)
 constexpr int kMaxGrid = 160;            // persistent grid upper bound (>= SM count of a B200: 148)
 constexpr int kScratchLd = 193;          // composite scratch row stride (floats): conflict-free for both phases
 
@@ -160,16 +160,24 @@ struct FwdArgs {
 // =====================================================================================================================
 //  main kernel
 // =====================================================================================================================
-__device__ __forceinline__ void store_a_kblock(uint32_t smem_base, uint32_t t_lane, int kb, int row, const uint32_t (&hi)[32],
-                                               const uint32_t (&lo)[32]) {
+// One thread writes HALF a row (32 K values = 64 bytes hi + 64 bytes lo) of K-block kb: hi -> smem chunks 4*half..4*half+3
+// (16-byte chunk index XOR (row & 7)); lo -> TMEM columns (kb < 4; 16 packed columns) or smem (kb 4,5).
+__device__ __forceinline__ void st_shared_row64(uint32_t addr_row, uint32_t sw, int half, const uint32_t (&w)[16]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr_row + ((((uint32_t)(4 * half + j)) ^ sw) << 4)), "r"(w[4 * j]),
+                 "r"(w[4 * j + 1]), "r"(w[4 * j + 2]), "r"(w[4 * j + 3])
+                 : "memory");
+}
+__device__ __forceinline__ void store_a_half(uint32_t smem_base, uint32_t t_lane, int kb, int row, int half, const uint32_t (&hi)[16],
+                                             const uint32_t (&lo)[16]) {
   const uint32_t row_off = a_row_offset(row);
   const uint32_t sw = (uint32_t)(row & 7);
-  st_shared_row128(smem_base + kSmemAHi + (uint32_t)kb * kABlockBytes + row_off, sw, hi);
+  st_shared_row64(smem_base + kSmemAHi + (uint32_t)kb * kABlockBytes + row_off, sw, half, hi);
   if (kb < kALoTmemKB) {
-    tmem_st32(t_lane + kALoCol + kb * 32, lo);
-    tmem_wait_st();
+    tmem_st16(t_lane + kALoCol + kb * 32 + half * 16, lo);   // completion is awaited once per release (tcgen05.wait::st)
   } else {
-    st_shared_row128(smem_base + kSmemALo45 + (uint32_t)(kb - kALoTmemKB) * kABlockBytes + row_off, sw, lo);
+    st_shared_row64(smem_base + kSmemALo45 + (uint32_t)(kb - kALoTmemKB) * kABlockBytes + row_off, sw, half, lo);
   }
 }
 
@@ -194,6 +202,7 @@ __device__ __forceinline__ void compute_pe(const float* __restrict__ tvec, const
   pe[63] = 0.0f;
 }
 
+template <int CSIZE, bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -207,8 +216,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
   const int lane = threadIdx.x & 31;
   // Thread-block cluster (1, 2 or 4 CTAs): the CTAs of a cluster work on tiles of the SAME branch in lockstep; each loads 1/csize
   // of every weight stage from L2 and multicasts it to all of them (the weight feed was L2-bandwidth bound, profiles/).
-  const int csize = (int)cluster_nctarank();
-  const int crank = (int)cluster_ctarank();
+  constexpr int csize = CSIZE;
+  const int crank = (CSIZE > 1) ? (int)cluster_ctarank() : 0;
   const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
   const int n_citems = args.n_items / csize;           // cluster work items
   const int cluster_id = (int)blockIdx.x / csize, n_clusters = (int)gridDim.x / csize;
@@ -225,19 +234,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
       mbar_init(bar(kBarWFull + i), 1);
       mbar_init(bar(kBarWEmpty + i), (uint32_t)csize);   // released by the MMA warp of every CTA of the cluster
     }
-    for (int i = 0; i < kNumKB; ++i) mbar_init(bar(kBarAReady + i), 4);  // one arrive per epilogue warp
+    for (int i = 0; i < kNumKB; ++i) mbar_init(bar(kBarAReady + i), 8);  // one arrive per epilogue warp
     mbar_init(bar(kBarAccFull), 1);
     mbar_init(bar(kBarAFree), 1);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc_512(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)));
+  if (warp == 9) tmem_alloc_512(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)));
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();   // every CTA's barriers are initialised before any peer signals them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // =============================================== TMA producer ===============================================
     if (elect_one()) {
       uint32_t slot = 0, phase = 0;
@@ -257,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // =============================================== MMA issuer =================================================
     // ONE elected lane runs the whole issue loop (measured, tests/ubench/ub_stage.cu: a per-stage elect + __syncwarp in a
     // converged-warp loop costs ~136 cycles per stage, which bursts of 64-cycle N=128 UMMAs cannot hide; inside a single
@@ -265,16 +274,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t sbase_u = __shfl_sync(0xffffffffu, smem_base, 0);
     if (elect_one()) {
-      uint32_t slot = 0, wphase = 0;
+      uint32_t wp = 0;       // ring-wrap parity at the start of the current pass
       uint32_t a_phase = 0;  // bit kb = parity of the next completion of a_ready[kb]
       bool prof_on = false;
       long long w_stall = 0, a_stall = 0;
       int prof_item = 0, prof_layer = 0;
       auto stamp = [&](int layer, int k) {
-        prof_layer = layer;
-        if (prof_on) {
-          long long* p = args.prof + ((size_t)prof_item * 10 + layer) * 16;
-          p[k] = clock64(); p[k + 1] = w_stall; p[k + 2] = a_stall;
+        if (PROF) {
+          prof_layer = layer;
+          if (prof_on) {
+            long long* p = args.prof + ((size_t)prof_item * 10 + layer) * 16;
+            p[k] = clock64(); p[k + 1] = w_stall; p[k + 2] = a_stall;
+          }
         }
       };
       constexpr uint32_t kDescHiSw128 = (uint32_t)((1024 >> 4) | (1u << 14) | (2u << 29));   // SBO, version, SWIZZLE_128B
@@ -282,18 +293,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
       constexpr uint32_t kDescLoLboSw = 1u << 16, kDescLoLboNo = (128u >> 4) << 16;
       const uint32_t a_hi_lo0 = (((sbase_u + kSmemAHi) >> 4) & 0x3FFFu) | kDescLoLboSw;
       const uint32_t a_lo45_lo0 = (((sbase_u + kSmemALo45) >> 4) & 0x3FFFu) | kDescLoLboSw;
+      const uint32_t ring_lo0 = (((sbase_u + kSmemRing) >> 4) & 0x3FFFu) | kDescLoLboNo;
       auto mk = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
 
       // One ring stage = NK16 K16-steps of one accumulator block: per step  A_hi*W_hi, A_hi*W_lo, A_lo*W_hi.
-      auto do_stage = [&](auto nrows_c, auto nk16_c, uint32_t d_col, int a_k16, bool fresh) {
+      // `j` (stage index inside the pass) and `a_k16` are compile-time constants after unrolling: every pass has a multiple of
+      // kStages stages, so slot = j % kStages and all descriptors fold to base + constant (the issue thread is the bottleneck
+      // for 64-cycle N=128 UMMAs; tests/ubench/ub_pattern.cu shows the pattern itself runs at the ideal rate).
+      auto do_stage = [&](auto nrows_c, auto nk16_c, int j, uint32_t d_col, int a_k16, bool fresh) {
         constexpr int NROWS = decltype(nrows_c)::value, NK16 = decltype(nk16_c)::value;
         constexpr uint32_t idesc = umma_idesc_bf16(128, NROWS);
         constexpr uint32_t kSliceU = (uint32_t)((NROWS * 32) >> 4);  // one K16 slice, in 16-byte units
-        const long long tw0 = prof_on ? clock64() : 0;
-        mbar_wait_spin(bar(kBarWFull + slot), wphase);
-        if (prof_on) w_stall += clock64() - tw0;
+        const int slot = j % kStages;
+        const uint32_t ph = wp ^ (uint32_t)((j / kStages) & 1);
+        long long tw0 = 0;
+        if (PROF) tw0 = prof_on ? clock64() : 0;
+        mbar_wait_spin(bar(kBarWFull + slot), ph);
+        if (PROF) { if (prof_on) w_stall += clock64() - tw0; }
         tc_fence_after_sync();
-        const uint32_t b_hi0 = (((sbase_u + kSmemRing + slot * kSlotBytes) >> 4) & 0x3FFFu) | kDescLoLboNo;
+        const uint32_t b_hi0 = ring_lo0 + (uint32_t)((slot * kSlotBytes) >> 4);
         const uint32_t b_lo0 = b_hi0 + NK16 * kSliceU;
         const uint32_t d = tmem_u + d_col;
 #pragma unroll
@@ -313,75 +331,92 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
             umma_ss(d, mk(a_lo45_lo0 + (uint32_t)(((kb - kALoTmemKB) * kABlockBytes + (k16 & 3) * 32) >> 4), kDescHiSw128), b_hi,
                     idesc, 1u);
         }
-        if (csize == 1) umma_commit(bar(kBarWEmpty + slot));
+        if (CSIZE == 1) umma_commit(bar(kBarWEmpty + slot));
         else umma_commit_multicast(bar(kBarWEmpty + slot), cmask);
-        if (++slot == kStages) { slot = 0; wphase ^= 1; }
       };
       auto wait_a = [&](int kb) {
-        const long long ta0 = prof_on ? clock64() : 0;
+        long long ta0 = 0;
+        if (PROF) ta0 = prof_on ? clock64() : 0;
         mbar_wait_spin(bar(kBarAReady + kb), (a_phase >> kb) & 1u);
-        if (prof_on) a_stall += clock64() - ta0;
+        if (PROF) { if (prof_on) a_stall += clock64() - ta0; }
         a_phase ^= (1u << kb);
         tc_fence_after_sync();
       };
-      // all K-slices of both accumulator blocks (blk 0: N=128, two K16 steps per stage; blk 1: N=256 / 80, one step)
-      auto run_pass = [&](auto n1_c, int k16n, bool pe_pass, bool fresh_start) {
-        for (int ks = 0; ks < k16n; ks += 4) {   // blk 0: one stage = one A K-block (4 K16 steps, 12 UMMAs of N=128)
+      // all K-slices of both accumulator blocks, fully unrolled (blk 0: N=128, one A K-block per stage; blk 1: N=256 / 80)
+      auto run_pass = [&](auto n1_c, auto k16n_c, bool pe_pass, bool fresh_start) {
+        constexpr int K16N = decltype(k16n_c)::value;
+        constexpr int NB0 = K16N / 4, NB1 = K16N / 2;
+        static_assert((NB0 + NB1) % kStages == 0, "a pass must use a whole number of ring wraps");
+#pragma unroll
+        for (int i = 0; i < NB0; ++i) {
           // blk 0 touches each A K-block first; its first UMMA overwrites columns 0..127 = K-blocks 0 and 1 of the previous
           // accumulator, so both must have been drained before it is issued.
           if (!pe_pass) {
-            if (ks == 0) { wait_a(0); wait_a(1); }
-            else if (ks >= 8) wait_a(ks >> 2);
+            if (i == 0) { wait_a(0); wait_a(1); }
+            else if (i >= 2) wait_a(i);
           }
-          do_stage(std::integral_constant<int, 128>{}, std::integral_constant<int, 4>{}, 0u, ks, fresh_start && ks == 0);
-          if (prof_on && k16n == 24 && ks >= 4) args.prof[((size_t)prof_item * 10 + prof_layer) * 16 + 10 + (ks >> 2)] = clock64();
+          do_stage(std::integral_constant<int, 128>{}, std::integral_constant<int, 4>{}, i, 0u, 4 * i, fresh_start && i == 0);
+          if (PROF) { if (prof_on && K16N == 24 && i >= 1) args.prof[((size_t)prof_item * 10 + prof_layer) * 16 + 10 + i] = clock64(); }
         }
-        if (prof_on && k16n == 24) args.prof[((size_t)prof_item * 10 + prof_layer) * 16 + 10] = clock64();  // blk 0 issued
-        for (int ks = 0; ks < k16n; ks += 2)     // blk 1: 2 K16 steps, 6 UMMAs of N=256 (80 for layer 8)
-          do_stage(n1_c, std::integral_constant<int, 2>{}, 128u, ks, fresh_start && ks == 0);
+        if (PROF) { if (prof_on && K16N == 24) args.prof[((size_t)prof_item * 10 + prof_layer) * 16 + 10] = clock64(); }  // blk 0 issued
+#pragma unroll
+        for (int i = 0; i < NB1; ++i)
+          do_stage(n1_c, std::integral_constant<int, 2>{}, NB0 + i, 128u, 2 * i, fresh_start && i == 0);
+        if (((NB0 + NB1) / kStages) & 1) wp ^= 1u;
       };
+      using I4 = std::integral_constant<int, 4>;
+      using I24 = std::integral_constant<int, 24>;
+      using N256 = std::integral_constant<int, 256>;
+      using N80 = std::integral_constant<int, 80>;
 
       for (int ci = cluster_id; ci < n_citems; ci += n_clusters) {
-        prof_item = ci / n_clusters;
-        prof_on = (args.prof != nullptr) && blockIdx.x == 0 && prof_item < 4;
+        if (PROF) {
+          prof_item = ci / n_clusters;
+          prof_on = (args.prof != nullptr) && blockIdx.x == 0 && prof_item < 4;
+        }
         // ---- layer 0: K = 64 (PE in K-block 0)
         stamp(0, 0);
         wait_a(0);
-        run_pass(std::integral_constant<int, 256>{}, 4, true, true);
+        run_pass(N256{}, I4{}, true, true);
         umma_commit(bar(kBarAccFull));
         stamp(0, 3);
         // ---- layers 1..7
+#pragma unroll 1
         for (int layer = 1; layer < 8; ++layer) {
           stamp(layer, 0);
-          run_pass(std::integral_constant<int, 256>{}, 24, false, true);
+          run_pass(N256{}, I24{}, false, true);
           if (layer == 5) {
             // skip connection: the PE columns of FeaExt_module_5 (models/mlp_nerf.py:106-107); the epilogue re-stages
             // the tile's PE into K-block 0 once every read of the hidden K-blocks has completed.
             umma_commit(bar(kBarAFree));
             wait_a(0);
-            run_pass(std::integral_constant<int, 256>{}, 4, true, false);
+            run_pass(N256{}, I4{}, true, false);
           }
           umma_commit(bar(kBarAccFull));
           stamp(layer, 3);
         }
         // ---- layer 8: [RGB_0*RGB_1 (192) | density (1) | pad] = N 128 + 80
         stamp(8, 0);
-        run_pass(std::integral_constant<int, 80>{}, 24, false, true);
+        run_pass(N80{}, I24{}, false, true);
         umma_commit(bar(kBarAccFull));
         stamp(8, 3);
       }
     }
     __syncwarp();
   } else {
-    // =============================================== epilogue warps (0..3) =======================================
-    const int row = threadIdx.x;                                   // TMEM lane == tile row == sample point
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // =============================================== epilogue warps (0..7) =======================================
+    // thread = (row, half): row = TMEM lane = sample point of the tile; half selects 32 of the 64 columns of every K-block
+    // (the drain is latency bound, two warps per scheduler hide each other's tcgen05.ld / conversion latencies)
+    const int half = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t acc_phase = 0, afree_phase = 0;
     const int N_s = args.N_s;
     const int rays_per_tile = kTile / N_s;
     // per-ray composite scratch [128][193] fp32: aliases A K-blocks 1.. (K-block 0 stays free for the next tile's PE)
     float* scratch = reinterpret_cast<float*>(smem_gen + kABlockBytes);
-    // per-CTA stash of the tile's positional encoding (packed hi/lo words) + delta, L2 resident: [65][128] u32, thread == row
+    // per-CTA stash of the tile's positional encoding, L2 resident: [64 words + delta][2 halves][128 rows]; a thread only ever
+    // reads back what it wrote itself (half 0 keeps the hi words, half 1 the lo words), so no cross-thread ordering is needed
     uint32_t* stash = args.pe_stash + (size_t)blockIdx.x * (65 * kTile) + row;
 
     auto release_kb = [&](int kb) {
@@ -390,7 +425,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(kBarAReady + kb));
     };
-    // sample point of (item, row) -> positional encoding + delta, written to the stash (read back by the same thread)
+    // one fence for two K-blocks (the fence is a MEMBAR.ALL.CTA: ~300 cycles with 8 warps storing)
+    auto release_kb_pair = [&](int kb_even) {
+      tmem_wait_st();
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(bar(kBarAReady + kb_even)); mbar_arrive(bar(kBarAReady + kb_even + 1)); }
+    };
+    // sample point of (item, row) -> positional encoding (+ delta); both halves compute it (idle window), each keeps its words
     auto stash_pe = [&](int ci) {
       int branch_, b, tile;
       decode_item(ci, branch_, b, tile);
@@ -402,31 +445,34 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
       const float delta = __fmul_rn(__fsub_rn(ze[s + 1], z), dl.w);  // (z_{k+1} - z_k) * l  (utils/model_utils.py:309-310)
       float pe[64];
       compute_pe(args.tvecs + b * 3, dl, z, pe);
-      uint32_t hi[32], lo[32];
-      split_row64(pe, hi, lo);
 #pragma unroll
       for (int q = 0; q < 32; ++q) {
-        stash[(size_t)q * kTile] = hi[q];
-        stash[(size_t)(32 + q) * kTile] = lo[q];
+        uint32_t hi, lo;
+        split2(pe[2 * q], pe[2 * q + 1], hi, lo);
+        stash[(size_t)(half * 32 + q) * kTile] = half ? lo : hi;
       }
-      stash[(size_t)64 * kTile] = __float_as_uint(delta);
-      if (args.dbg != nullptr && ci == 0 && blockIdx.x == 0)
+      if (half == 0) stash[(size_t)64 * kTile] = __float_as_uint(delta);
+      if (args.dbg != nullptr && ci == 0 && blockIdx.x == 0 && half == 0)
         for (int j = 0; j < 64; ++j) args.dbg[(size_t)row * kHidden + j] = pe[j];
+      return delta;
     };
-    // stash -> A K-block 0 (hi: smem, lo: TMEM), then release it to the MMA warp
+    // stash -> A K-block 0 (half 0: hi words -> smem row; half 1: lo words -> TMEM), then release it to the MMA warp
     auto stage_pe = [&]() {
-      uint32_t hi[32], lo[32];
+      uint32_t w[32];
 #pragma unroll
-      for (int q = 0; q < 32; ++q) {
-        hi[q] = stash[(size_t)q * kTile];
-        lo[q] = stash[(size_t)(32 + q) * kTile];
+      for (int q = 0; q < 32; ++q) w[q] = stash[(size_t)(half * 32 + q) * kTile];
+      if (half == 0) {
+        st_shared_row128(smem_base + kSmemAHi + a_row_offset(row), (uint32_t)(row & 7), w);
+      } else {
+        tmem_st32(t_lane + kALoCol, w);
+        tmem_wait_st();
       }
-      store_a_kblock(smem_base, t_lane, 0, row, hi, lo);
       release_kb(0);
     };
 
+    float delta = 0.0f, delta_next = 0.0f;
     if (cluster_id < n_citems) {
-      stash_pe(cluster_id);
+      delta = stash_pe(cluster_id);
       stage_pe();
     }
     for (int item = cluster_id; item < n_citems; item += n_clusters) {
@@ -438,10 +484,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
       const int next_item = item + n_clusters;
       const int ray = tile * rays_per_tile + row / N_s;
       const int s = row - (row / N_s) * N_s;
-      const float delta = __uint_as_float(stash[(size_t)64 * kTile]);
 
       // ---- trunk: drain layer l accumulators into A as the input of layer l+1 ----------------------------------
-      const bool eprof = (args.prof != nullptr) && blockIdx.x == 0 && (item / n_clusters) < 4 && threadIdx.x == 0;
+      const bool eprof = PROF && (args.prof != nullptr) && blockIdx.x == 0 && (item / n_clusters) < 4 && threadIdx.x == 0;
       long long* ep = eprof ? args.prof + ((size_t)(item / n_clusters) * 10) * 16 : nullptr;
       if (eprof) ep[6] = clock64();  // layer-0 row: K-block 0 (PE) of this tile released
       for (int layer = 0; layer < 8; ++layer) {
@@ -449,39 +494,33 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
         if (eprof) ep[layer * 16 + 7] = clock64();  // accumulator of `layer` complete
         acc_phase ^= 1;
         tc_fence_after_sync();
-        const float* bl = bias + bias_offset(layer);
+        const float* bl = bias + bias_offset(layer) + half * 32;
 #pragma unroll 1
         for (int kb = 0; kb < kNumKB; ++kb) {
-          uint32_t r0[32], r1[32];
-          tmem_ld32(t_lane + kb * 64, r0);
-          tmem_ld32(t_lane + kb * 64 + 32, r1);
-          tmem_wait_ld();
-          float v[64];
+          uint32_t r0[32];
+          tmem_ld32(t_lane + kb * 64 + half * 32, r0);
           const float4* b4 = reinterpret_cast<const float4*>(bl + kb * 64);
+          float4 bb[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bb[j] = __ldg(b4 + j);
+          tmem_wait_ld();
+          float v[32];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float4 bb = __ldg(b4 + j);
-            v[4 * j + 0] = fmaxf(__uint_as_float(r0[4 * j + 0]) + bb.x, 0.0f);
-            v[4 * j + 1] = fmaxf(__uint_as_float(r0[4 * j + 1]) + bb.y, 0.0f);
-            v[4 * j + 2] = fmaxf(__uint_as_float(r0[4 * j + 2]) + bb.z, 0.0f);
-            v[4 * j + 3] = fmaxf(__uint_as_float(r0[4 * j + 3]) + bb.w, 0.0f);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 bb = __ldg(b4 + 8 + j);
-            v[32 + 4 * j + 0] = fmaxf(__uint_as_float(r1[4 * j + 0]) + bb.x, 0.0f);
-            v[32 + 4 * j + 1] = fmaxf(__uint_as_float(r1[4 * j + 1]) + bb.y, 0.0f);
-            v[32 + 4 * j + 2] = fmaxf(__uint_as_float(r1[4 * j + 2]) + bb.z, 0.0f);
-            v[32 + 4 * j + 3] = fmaxf(__uint_as_float(r1[4 * j + 3]) + bb.w, 0.0f);
+            v[4 * j + 0] = fmaxf(__uint_as_float(r0[4 * j + 0]) + bb[j].x, 0.0f);
+            v[4 * j + 1] = fmaxf(__uint_as_float(r0[4 * j + 1]) + bb[j].y, 0.0f);
+            v[4 * j + 2] = fmaxf(__uint_as_float(r0[4 * j + 2]) + bb[j].z, 0.0f);
+            v[4 * j + 3] = fmaxf(__uint_as_float(r0[4 * j + 3]) + bb[j].w, 0.0f);
           }
           {
-            uint32_t hi[32], lo[32];
-            split_row64(v, hi, lo);
-            store_a_kblock(smem_base, t_lane, kb, row, hi, lo);
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) split2(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
+            store_a_half(smem_base, t_lane, kb, row, half, hi, lo);
           }
           if (dump)
-            for (int j = 0; j < 64; ++j) args.dbg[((size_t)(layer + 1) * kTile + row) * kHidden + kb * 64 + j] = v[j];
-          release_kb(kb);
+            for (int j = 0; j < 32; ++j) args.dbg[((size_t)(layer + 1) * kTile + row) * kHidden + kb * 64 + half * 32 + j] = v[j];
+          if (kb & 1) release_kb_pair(kb - 1);
           if (eprof && (kb == 1 || kb == 5)) ep[layer * 16 + (kb == 1 ? 8 : 9)] = clock64();  // K-blocks 0..1 / all released
           if (eprof && kb == 3 && layer > 0) ep[layer * 16 + 6] = clock64();
         }
@@ -494,7 +533,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
           stage_pe();
         }
         // idle window (the MMA warp is busy with layer 7): prepare the next tile's positional encoding
-        if (layer == 6 && next_item < n_citems) stash_pe(next_item);
+        if (layer == 6 && next_item < n_citems) delta_next = stash_pe(next_item);
       }
 
       // ---- last stage: density -> alpha -> transmittance scan -> weights; composite the 192-d hidden per ray ----
@@ -523,19 +562,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
         float T = __shfl_up_sync(0xffffffffu, incl, 1);
         if (lane_in_seg == 0) T = 1.0f;
         if (N_s > 32) {
-          if (lane == 31) warp_prod[warp] = incl;
+          if (lane == 31 && half == 0) warp_prod[warp & 3] = incl;
           named_bar_sync(1, kEpiThreads);
           const int warps_per_ray = N_s >> 5;
-          const int w0 = (warp / warps_per_ray) * warps_per_ray;
-          for (int w = w0; w < warp; ++w) T *= warp_prod[w];
+          const int wq = warp & 3;
+          const int w0 = (wq / warps_per_ray) * warps_per_ray;
+          for (int w = w0; w < wq; ++w) T *= warp_prod[w];
         }
         w_k = __fmul_rn(alpha, T);                                                        // :512
-        if (br.weights != nullptr) br.weights[((size_t)b * args.N_r + ray) * N_s + s] = w_k;
-        if (dump) args.dbg[((size_t)9 * kTile + row) * kHidden + kH2] = sigma;
+        if (half == 0 && br.weights != nullptr) br.weights[((size_t)b * args.N_r + ray) * N_s + s] = w_k;
+        if (dump && half == 0) args.dbg[((size_t)9 * kTile + row) * kHidden + kH2] = sigma;
       }
       // all A reads of this tile are complete (acc_full): move w * ReLU(hidden) out of TMEM into the smem scratch
 #pragma unroll 1
-      for (int c0 = 0; c0 < kH2; c0 += 32) {
+      for (int g = 0; g < 3; ++g) {
+        const int c0 = half * 96 + g * 32;
         uint32_t r[32];
         tmem_ld32(t_lane + c0, r);
         tmem_wait_ld();
@@ -546,14 +587,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
           if (dump) args.dbg[((size_t)9 * kTile + row) * kHidden + c0 + j] = h;
         }
       }
-      scratch[row * kScratchLd + kH2] = w_k;
+      if (half == 0) scratch[row * kScratchLd + kH2] = w_k;
       // the accumulators are drained: hand the next tile's layer 0 to the MMA warp BEFORE the cross-row reduction
       if (next_item < n_citems) stage_pe();
       else tc_fence_before_sync();
       named_bar_sync(1, kEpiThreads);
       {
         const int total = rays_per_tile * kScratchLd;
-        for (int idx = row; idx < total; idx += kEpiThreads) {
+        for (int idx = (int)threadIdx.x; idx < total; idx += kEpiThreads) {
           const int rl = idx / kScratchLd, c = idx - rl * kScratchLd;
           const float* col = scratch + (size_t)rl * N_s * kScratchLd + c;
           float acc = 0.0f;
@@ -563,6 +604,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
         }
       }
       named_bar_sync(1, kEpiThreads);  // scratch reads done before the next tile's layer-0 drain overwrites A K-blocks 1..
+      delta = delta_next;
       if (eprof) ep[8 * 16 + 9] = clock64();  // composite done
     }
   }
@@ -571,7 +613,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();   // no CTA may exit while a peer can still multicast into its smem or signal its barriers
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after_sync();
     tmem_dealloc_512(tmem_base);
   }
@@ -842,7 +884,10 @@ extern "C" int gnrf_mlp_tc_fwd(int n_branch, const void* const* packed, const fl
     int dev = 0;
     GNRF_CUDA(cudaGetDevice(&dev));
     GNRF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    GNRF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    GNRF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    GNRF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    GNRF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    GNRF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   }
   FwdArgs a;
   float* ws = static_cast<float*>(workspace);
@@ -876,12 +921,12 @@ extern "C" int gnrf_mlp_tc_fwd(int n_branch, const void* const* packed, const fl
     const char* e = getenv("GNRF_TC_PROF_PTR");  // test hook: device pointer (decimal) of a [4][10][16] int64 timeline buffer
     if (e != nullptr) a.prof = reinterpret_cast<long long*>(strtoull(e, nullptr, 10));
   }
-  // cluster size: CTAs of a cluster share every weight stage through TMA multicast (default 2; GNRF_TC_CLUSTER=1|2|4)
+  // cluster size: CTAs of a cluster share every weight stage through TMA multicast (default 2; GNRF_TC_CLUSTER=1|2)
   int csize = 2;
   {
     const char* e = getenv("GNRF_TC_CLUSTER");
     if (e != nullptr) csize = atoi(e);
-    if (csize != 1 && csize != 2 && csize != 4) csize = 2;
+    if (csize != 1 && csize != 2) csize = 2;
     while (csize > 1 && ((B * a.tiles_per_face) % csize != 0 || a.n_items / csize < 1)) csize >>= 1;
   }
   int grid = (a.n_items / csize) * csize < n_sm ? (a.n_items / csize) * csize : n_sm;
@@ -900,7 +945,14 @@ extern "C" int gnrf_mlp_tc_fwd(int n_branch, const void* const* packed, const fl
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    GNRF_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel, a));
+    const bool prof = a.prof != nullptr;
+    if (csize == 2) {
+      if (prof) GNRF_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<2, true>, a));
+      else GNRF_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<2, false>, a));
+    } else {
+      if (prof) GNRF_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<1, true>, a));
+      else GNRF_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<1, false>, a));
+    }
   }
   GNRF_LAUNCH_CHECK();
   {

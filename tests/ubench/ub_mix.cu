@@ -136,5 +136,11 @@ int main() {
   run<256, 1, 1, 0, 0>("N=256 fill/lastuse/TS      no TMA, no epi", d, g);
   run<256, 1, 1, 1, 0>("N=256 fill/lastuse/TS      TMA          ", d, g);
   run<256, 1, 1, 1, 1>("N=256 fill/lastuse/TS      TMA + epi    ", d, g);
+  run<192, 1, 1, 0, 0>("N=192 x3 fill/lastuse/TS   no TMA, no epi (ideal 288)", d, g);
+  run<192, 1, 1, 1, 1>("N=192 x3 fill/lastuse/TS   TMA + epi      (ideal 288)", d, g);
+  run<128, 1, 1, 1, 1>("N=128 x3 fill/lastuse/TS   TMA + epi      (ideal 192)", d, g);
+  run<256, 2, 1, 1, 1>("N=256 x6 fill/lastuse/TS   TMA + epi      (ideal 768)", d, g);
+  run<128, 4, 1, 1, 1>("N=128 x12 fill/lastuse/TS  TMA + epi      (ideal 768)", d, g);
+  run<128, 4, 1, 0, 0>("N=128 x12 fill/lastuse/TS  no TMA no epi  (ideal 768)", d, g);
   return 0;
 }
