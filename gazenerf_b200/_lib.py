@@ -18,7 +18,8 @@ CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(_ROOT, "include")
 LIB_PATH = os.path.join(_HERE, "libgnrf.so")
 
-SOURCES = ["abi.cu", "geometry.cu", "mlp_simt.cu", "mlp_tc.cu", "compose.cu", "neural_render.cu", "conv_tc.cu"]
+SOURCES = ["abi.cu", "geometry.cu", "mlp_simt.cu", "mlp_tc.cu", "compose.cu", "neural_render.cu", "conv_tc.cu", "wgrad_tc.cu",
+           "train_ops.cu", "nr_train.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -35,6 +36,11 @@ SYMBOLS = [
     "gnrf_mlp_tc_workspace_bytes", "gnrf_mlp_tc_fwd",
     "gnrf_compose_fwd", "gnrf_nr_workspace_bytes", "gnrf_neural_render_fwd",
     "gnrf_nr_tc_packed_bytes", "gnrf_nr_tc_pack", "gnrf_neural_render_tc_fwd",
+    # training path
+    "gnrf_conv_tc_packed_bytes", "gnrf_conv_tc_pack", "gnrf_conv_tc", "gnrf_wgrad_tc_workspace_bytes", "gnrf_wgrad_tc",
+    "gnrf_pe_fwd", "gnrf_pe_bwd", "gnrf_composite_cm_fwd", "gnrf_composite_cm_bwd", "gnrf_geom_bwd",
+    "gnrf_compose_bwd_blocks", "gnrf_compose_bwd",
+    "gnrf_nr_train_saved_bytes", "gnrf_nr_train_fwd", "gnrf_nr_train_bwd_workspace_bytes", "gnrf_nr_train_bwd",
 ]
 
 
@@ -113,6 +119,27 @@ def lib() -> ctypes.CDLL:
     L.gnrf_nr_tc_packed_bytes.argtypes = [i32, i32, i32]
     L.gnrf_nr_tc_pack.argtypes = [vp, i32, i32, i32, vp, vp]
     L.gnrf_neural_render_tc_fwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, sz, vp]
+    i64 = c.c_longlong
+    L.gnrf_conv_tc_packed_bytes.restype = sz
+    L.gnrf_conv_tc_packed_bytes.argtypes = [i32, i32]
+    L.gnrf_conv_tc_pack.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    L.gnrf_conv_tc.argtypes = [vp, i32, i32, vp, i64, vp, vp, i64, i32, vp, i64, i32, f32, vp, i64, i32, i32, i32, vp]
+    L.gnrf_wgrad_tc_workspace_bytes.restype = sz
+    L.gnrf_wgrad_tc_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    L.gnrf_wgrad_tc.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, vp, vp, i32, i32, vp, sz, vp]
+    L.gnrf_pe_fwd.argtypes = [vp, vp, vp, i32, i32, i32, vp, i64, vp]
+    L.gnrf_pe_bwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    L.gnrf_composite_cm_fwd.argtypes = [vp, i64, vp, i64, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
+    L.gnrf_composite_cm_bwd.argtypes = [vp, vp, vp, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32, vp, i64, vp, i64, vp, vp, vp]
+    L.gnrf_geom_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]
+    L.gnrf_compose_bwd_blocks.argtypes = [i32]
+    L.gnrf_compose_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.gnrf_nr_train_saved_bytes.restype = sz
+    L.gnrf_nr_train_saved_bytes.argtypes = [i32, i32, i32, i32, i32]
+    L.gnrf_nr_train_fwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, sz, vp]
+    L.gnrf_nr_train_bwd_workspace_bytes.restype = sz
+    L.gnrf_nr_train_bwd_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
+    L.gnrf_nr_train_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is c.c_int and name not in ("gnrf_abi_version",):

@@ -43,6 +43,11 @@ struct ConvArgs {
   int K, N, HW, Wd, n_img;
   int chunk_n, n_chunks, k16_steps, n_kb;
   int tiles_per_img, n_items, mode;
+  // generic-GEMM extensions used by the training path (all optional; zero / null = the plain neural-renderer behaviour)
+  long long x_img_stride, out_img_stride;   // elements between images of X / out (0 -> K*HW / N*HW)
+  const float* bias_img;                    // [n_img][N] per-image bias added on top of the packed one (folded code columns)
+  const float* mask; long long mask_img_stride; int mask_rows; float mask_slope;   // v *= mask>0 ? 1 : slope  (rows < mask_rows)
+  const float* add;  long long add_img_stride;  int add_rows;                      // v += add                   (rows < add_rows)
 };
 
 __device__ __forceinline__ float lrelu02(float v) { return v >= 0.0f ? v : 0.2f * v; }
@@ -93,6 +98,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const ConvArgs a
       const int H = args.HW / args.Wd;
       const int h = p / args.Wd, w = p - h * args.Wd;
       const float* bias_c = args.bias + n0;               // zero padded to n_chunks * chunk_n
+      const float* bias_i = args.bias_img ? args.bias_img + (size_t)img * args.N : nullptr;
       const size_t img_res = (size_t)img * args.Cres * args.HW + p;
       for (int c0 = 0; c0 < args.chunk_n; c0 += 32) {
         uint32_t r[32];
@@ -102,6 +108,26 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const ConvArgs a
         const int ncols = min(32, args.chunk_n - c0);
 #pragma unroll
         for (int j = 0; j < 32; ++j) bv[j] = (j < ncols) ? __ldg(bias_c + c0 + j) : 0.0f;
+        if (bias_i != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncols && n0 + c0 + j < args.N) bv[j] += __ldg(bias_i + n0 + c0 + j);
+        }
+        float av[32];
+        if (args.mode != CONV_EPI_PSU && (args.mask != nullptr || args.add != nullptr)) {
+          const float* mk = args.mask ? args.mask + (size_t)img * args.mask_img_stride + (size_t)(n0 + c0) * args.HW + p : nullptr;
+          const float* ad = args.add ? args.add + (size_t)img * args.add_img_stride + (size_t)(n0 + c0) * args.HW + p : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c0 + j;
+            const bool ok = p_ok && j < ncols && n < args.N;
+            rv[j] = (ok && mk != nullptr && n < args.mask_rows) ? (__ldg(mk + (size_t)j * args.HW) > 0.0f ? 1.0f : args.mask_slope) : 1.0f;
+            av[j] = (ok && ad != nullptr && n < args.add_rows) ? __ldg(ad + (size_t)j * args.HW) : 0.0f;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { av[j] = 0.0f; if (args.mode != CONV_EPI_PSU) rv[j] = 1.0f; }
+        }
         if (args.mode == CONV_EPI_PSU) {
           int cm = (n0 + c0) % args.Cres;   // (n % Cres), advanced incrementally
 #pragma unroll
@@ -118,13 +144,14 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const ConvArgs a
         }
         if (!p_ok) continue;
         if (args.mode != CONV_EPI_PSU) {
-          float* o = args.out + ((size_t)img * args.N + n0 + c0) * args.HW + p;
-          const bool act = args.mode == CONV_EPI_LRELU;
+          float* o = args.out + (size_t)img * args.out_img_stride + (size_t)(n0 + c0) * args.HW + p;
+          const int mode = args.mode;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (j < ncols && n0 + c0 + j < args.N) {
-              const float v = __uint_as_float(r[j]) + bv[j];
-              o[(size_t)j * args.HW] = act ? lrelu02(v) : v;
+              float v = __uint_as_float(r[j]) + bv[j];
+              v = mode == CONV_EPI_LRELU ? lrelu02(v) : (mode == CONV_EPI_RELU ? fmaxf(v, 0.0f) : v);
+              o[(size_t)j * args.HW] = fmaf(v, rv[j], av[j]);
             }
         } else {
           // + x.repeat(1,4,1,1), then pixel_shuffle(2): out[c][2h+i][2w+j] = in[4c+2i+j][h][w]  (pixel_shuffle_upsample.py:34-40)
@@ -155,7 +182,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const ConvArgs a
       decode(item, img, tile, chunk);
       const int p = tile * kCvTile + row;
       const bool p_ok = p < args.HW;
-      const float* xp = args.X + (size_t)img * args.K * args.HW + p;
+      const float* xp = args.X + (size_t)img * args.x_img_stride + p;
       for (int kb = 0; kb < args.n_kb; ++kb) {
         float v[64];
 #pragma unroll
@@ -251,8 +278,10 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const ConvArgs a
 }
 
 // Weight stream of one layer: [chunk][k16][half][ (row/8)*16 + k_half*8 + (row%8) ] 16-byte chunks; bias zero-padded.
-__global__ void conv_pack_kernel(const float* __restrict__ W, const float* __restrict__ b, int N, int K, int chunk_n, int n_chunks,
-                                 int k16_steps, unsigned char* __restrict__ stream, float* __restrict__ bias_out) {
+// W(n,k) = W[n * sn + k * sk]  (sn = K, sk = 1: dense [N][K]; sn = 1, sk = N: the transpose of a dense [K][N] matrix).
+__global__ void conv_pack_kernel(const float* __restrict__ W, long long sn, long long sk, const float* __restrict__ b, int N, int K,
+                                 int chunk_n, int n_chunks, int k16_steps, unsigned char* __restrict__ stream,
+                                 float* __restrict__ bias_out) {
   const size_t chunks_per_slice = (size_t)chunk_n * 2;
   const size_t total = (size_t)n_chunks * k16_steps * 2 * chunks_per_slice;
   for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (size_t)gridDim.x * blockDim.x) {
@@ -269,8 +298,8 @@ __global__ void conv_pack_kernel(const float* __restrict__ W, const float* __res
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int ka = k0 + 2 * q, kb = ka + 1;
-      float a = (n < N && ka < K) ? W[(size_t)n * K + ka] : 0.0f;
-      float bb = (n < N && kb < K) ? W[(size_t)n * K + kb] : 0.0f;
+      float a = (n < N && ka < K) ? W[(size_t)n * sn + (size_t)ka * sk] : 0.0f;
+      float bb = (n < N && kb < K) ? W[(size_t)n * sn + (size_t)kb * sk] : 0.0f;
       uint32_t hi, lo;
       split2(a, bb, hi, lo);
       out[q] = half ? lo : hi;
@@ -278,7 +307,7 @@ __global__ void conv_pack_kernel(const float* __restrict__ W, const float* __res
     *reinterpret_cast<uint4*>(stream + c * 16) = make_uint4(out[0], out[1], out[2], out[3]);
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_chunks * chunk_n; i += gridDim.x * blockDim.x)
-    bias_out[i] = (i < N) ? b[i] : 0.0f;
+    bias_out[i] = (i < N && b != nullptr) ? b[i] : 0.0f;
 }
 
 ConvLayerPlan conv_layer_plan(int N, int K) {
@@ -297,8 +326,13 @@ ConvLayerPlan conv_layer_plan(int N, int K) {
 }
 
 int conv_tc_pack(const ConvLayerPlan& pl, const float* W, const float* b, unsigned char* dst, cudaStream_t st) {
+  return conv_tc_pack_strided(pl, W, pl.K, 1, b, dst, st);
+}
+
+int conv_tc_pack_strided(const ConvLayerPlan& pl, const float* W, long long sn, long long sk, const float* b, unsigned char* dst,
+                         cudaStream_t st) {
   float* bias_out = reinterpret_cast<float*>(dst + pl.stream_bytes);
-  conv_pack_kernel<<<148, 256, 0, st>>>(W, b, pl.N, pl.K, pl.chunk_n, pl.n_chunks, pl.k16_steps, dst, bias_out);
+  conv_pack_kernel<<<148, 256, 0, st>>>(W, sn, sk, b, pl.N, pl.K, pl.chunk_n, pl.n_chunks, pl.k16_steps, dst, bias_out);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(GNRF_ERR_CUDA, "conv_tc_pack: %s", cudaGetErrorString(e));
   count_launches(1);
@@ -307,6 +341,12 @@ int conv_tc_pack(const ConvLayerPlan& pl, const float* W, const float* b, unsign
 
 int conv_tc_launch(const ConvLayerPlan& pl, const unsigned char* packed, const float* X, float* out, const float* res, int Cres,
                    int n_img, int HW, int Wd, int mode, cudaStream_t st) {
+  ConvExtras ex = {};
+  return conv_tc_launch_ex(pl, packed, X, out, res, Cres, n_img, HW, Wd, mode, ex, st);
+}
+
+int conv_tc_launch_ex(const ConvLayerPlan& pl, const unsigned char* packed, const float* X, float* out, const float* res, int Cres,
+                      int n_img, int HW, int Wd, int mode, const ConvExtras& ex, cudaStream_t st) {
   static int n_sm = 0;
   if (n_sm == 0) {
     int dev = 0;
@@ -326,6 +366,13 @@ int conv_tc_launch(const ConvLayerPlan& pl, const unsigned char* packed, const f
   a.tiles_per_img = (HW + kCvTile - 1) / kCvTile;
   a.n_items = n_img * a.tiles_per_img * pl.n_chunks;
   a.mode = mode;
+  a.x_img_stride = ex.x_img_stride > 0 ? ex.x_img_stride : (long long)pl.K * HW;
+  a.out_img_stride = ex.out_img_stride > 0 ? ex.out_img_stride : (long long)pl.N * HW;
+  a.bias_img = ex.bias_img;
+  a.mask = ex.mask; a.mask_img_stride = ex.mask_img_stride > 0 ? ex.mask_img_stride : (long long)pl.N * HW;
+  a.mask_rows = ex.mask_rows > 0 ? ex.mask_rows : pl.N; a.mask_slope = ex.mask_slope;
+  a.add = ex.add; a.add_img_stride = ex.add_img_stride > 0 ? ex.add_img_stride : (long long)pl.N * HW;
+  a.add_rows = ex.add_rows > 0 ? ex.add_rows : pl.N;
   int grid = a.n_items < n_sm ? a.n_items : n_sm;
   conv_tc_kernel<<<grid, kCvThreads, kCvSmemBytes, st>>>(a);
   cudaError_t e = cudaGetLastError();
@@ -336,3 +383,34 @@ int conv_tc_launch(const ConvLayerPlan& pl, const unsigned char* packed, const f
 
 }  // namespace tc
 }  // namespace gnrf
+
+using namespace gnrf;
+
+// ---- generic entry points (training path): any 1x1 conv / per-point Linear forward, and its input gradient with W^T packed ----
+extern "C" size_t gnrf_conv_tc_packed_bytes(int N, int K) {
+  if (N <= 0 || K <= 0) return 0;
+  return tc::conv_layer_plan(N, K).total_bytes;
+}
+
+extern "C" int gnrf_conv_tc_pack(const float* W, const float* bias, int N, int K, int transposed, void* packed, gnrf_stream_t stream) {
+  GNRF_CHECK_ARG(W && packed && N > 0 && K > 0);
+  GNRF_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 127) == 0);
+  // transposed: W points at a dense [K][N] matrix (a forward weight [out = K][in = N]) and the GEMM uses its transpose
+  return tc::conv_tc_pack_strided(tc::conv_layer_plan(N, K), W, transposed ? 1 : K, transposed ? N : 1, bias,
+                                  static_cast<unsigned char*>(packed), as_stream(stream));
+}
+
+extern "C" int gnrf_conv_tc(const void* packed, int N, int K, const float* X, long long x_img_stride, const float* bias_img, float* out,
+                            long long out_img_stride, int act, const float* mask, long long mask_img_stride, int mask_rows,
+                            float mask_slope, const float* add, long long add_img_stride, int add_rows, int n_img, int HW,
+                            gnrf_stream_t stream) {
+  GNRF_CHECK_ARG(packed && X && out && N > 0 && K > 0 && n_img > 0 && HW > 0);
+  GNRF_CHECK_ARG(act == GNRF_ACT_NONE || act == GNRF_ACT_RELU || act == GNRF_ACT_LRELU02);
+  tc::ConvExtras ex = {};
+  ex.x_img_stride = x_img_stride; ex.out_img_stride = out_img_stride; ex.bias_img = bias_img;
+  ex.mask = mask; ex.mask_img_stride = mask_img_stride; ex.mask_rows = mask_rows; ex.mask_slope = mask_slope;
+  ex.add = add; ex.add_img_stride = add_img_stride; ex.add_rows = add_rows;
+  const int mode = act == GNRF_ACT_NONE ? tc::CONV_EPI_LINEAR : (act == GNRF_ACT_RELU ? tc::CONV_EPI_RELU : tc::CONV_EPI_LRELU);
+  return tc::conv_tc_launch_ex(tc::conv_layer_plan(N, K), static_cast<const unsigned char*>(packed), X, out, nullptr, 1, n_img, HW, HW,
+                               mode, ex, as_stream(stream));
+}

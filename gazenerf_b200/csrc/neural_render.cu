@@ -3,6 +3,7 @@
 //            models/pixel_shuffle_upsample.py:7-42 (Blur -> kornia.filters.filter2d, PixelShuffleUpsample).
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "nr_plan.cuh"
 
 namespace gnrf {
 
@@ -292,6 +293,15 @@ extern "C" size_t gnrf_nr_workspace_bytes(int N, int C, int S, int n_blocks, int
   return nr_plan(N, C, S, n_blocks, min_feat).total;
 }
 
+// per-level buffers of one forward: aliased across levels for inference (nr_plan), distinct for training (nr_train_plan)
+struct NrBufs {
+  float* t1[8]; float* sh[8]; float* net[8];
+  float* bl; float* rgb_a; float* rgb_b;
+};
+
+static int nr_forward_bufs(const float* const* params, const unsigned char* packed, const float* featmap, int N, int C, int S, int n_blocks,
+                           int min_feat, float* img, const NrBufs& bufs, cudaStream_t st);
+
 // packed == nullptr: fp32 CUDA-core GEMMs; else: tcgen05 bf16x3 GEMMs on the packed weight streams (3 layers per block)
 static int nr_forward(const float* const* params, const unsigned char* packed, const float* featmap, int N, int C, int S, int n_blocks,
                       int min_feat, float* img, void* workspace, size_t workspace_bytes, gnrf_stream_t stream) {
@@ -301,14 +311,25 @@ static int nr_forward(const float* const* params, const unsigned char* packed, c
   NrPlan pl = nr_plan(N, C, S, n_blocks, min_feat);
   if (workspace_bytes < pl.total)
     return fail(GNRF_ERR_ARG, "gnrf_neural_render_fwd: workspace %zu < required %zu bytes", workspace_bytes, pl.total);
-  cudaStream_t st = as_stream(stream);
   char* ws = static_cast<char*>(workspace);
-  float* t1 = reinterpret_cast<float*>(ws + pl.t1);
-  float* sh = reinterpret_cast<float*>(ws + pl.sh);
-  float* bl = reinterpret_cast<float*>(ws + pl.bl);
+  NrBufs bufs;
   float* netbuf[2] = {reinterpret_cast<float*>(ws + pl.net), reinterpret_cast<float*>(ws + pl.net + (pl.rgb_a - pl.net) / 2)};
-  float* rgb_a = reinterpret_cast<float*>(ws + pl.rgb_a);
-  float* rgb_b = reinterpret_cast<float*>(ws + pl.rgb_b);
+  for (int i = 0; i < n_blocks; ++i) {
+    bufs.t1[i] = reinterpret_cast<float*>(ws + pl.t1);
+    bufs.sh[i] = reinterpret_cast<float*>(ws + pl.sh);
+    bufs.net[i] = netbuf[i & 1];
+  }
+  bufs.bl = reinterpret_cast<float*>(ws + pl.bl);
+  bufs.rgb_a = reinterpret_cast<float*>(ws + pl.rgb_a);
+  bufs.rgb_b = reinterpret_cast<float*>(ws + pl.rgb_b);
+  return nr_forward_bufs(params, packed, featmap, N, C, S, n_blocks, min_feat, img, bufs, as_stream(stream));
+}
+
+static int nr_forward_bufs(const float* const* params, const unsigned char* packed, const float* featmap, int N, int C, int S, int n_blocks,
+                           int min_feat, float* img, const NrBufs& bufs, cudaStream_t st) {
+  float* bl = bufs.bl;
+  float* rgb_a = bufs.rgb_a;
+  float* rgb_b = bufs.rgb_b;
 
   // parameter indexing (see gnrf.h): psu i: [4i..4i+3]; to_rgb j: [4nb + 2j, +1]; feat i: [4nb + 2(nb+1) + 2i, +1]
   auto psu_w = [&](int i, int l) { return params[4 * i + 2 * l]; };
@@ -343,6 +364,8 @@ static int nr_forward(const float* const* params, const unsigned char* packed, c
     int co = (C >> (i + 1)) > min_feat ? (C >> (i + 1)) : min_feat;
     int HW = s * s;
     tc::ConvLayerPlan pl1 = tc::conv_layer_plan(2 * ci, ci), pl2 = tc::conv_layer_plan(4 * ci, 2 * ci), pl3 = tc::conv_layer_plan(co, ci);
+    float* t1 = bufs.t1[i];
+    float* sh = bufs.sh[i];
     if (packed != nullptr) {
       int rc = tc::conv_tc_launch(pl1, packed + pk_off, net, t1, nullptr, 1, N, HW, s, tc::CONV_EPI_LRELU, st);
       if (rc != GNRF_OK) return rc;
@@ -361,7 +384,7 @@ static int nr_forward(const float* const* params, const unsigned char* packed, c
     }
     s *= 2;
     HW = s * s;
-    float* net_out = netbuf[i & 1];
+    float* net_out = bufs.net[i];
     bool last = (i == n_blocks - 1);
     if (packed != nullptr) {
       // feat_layers[i] un-activated on tensor cores (into `bl`), then ONE pass: net = LeakyReLU(Blur(.)), rgb += feat_2_rgb(net)
@@ -439,4 +462,55 @@ extern "C" int gnrf_neural_render_tc_fwd(const float* const* params, const void*
   GNRF_CHECK_ARG(packed);
   return nr_forward(params, static_cast<const unsigned char*>(packed), featmap, N, C, S, n_blocks, min_feat, img, workspace,
                     workspace_bytes, stream);
+}
+
+// ------------------------------------------------------------------------------------------------- training forward
+namespace gnrf {
+NrTrainPlan nr_train_plan(int N, int C, int S, int n_blocks, int min_feat) {
+  NrTrainPlan p;
+  auto al = [](size_t v) { return (v * sizeof(float) + 255) & ~(size_t)255; };
+  size_t off = 0, m_bl = 0;
+  for (int i = 0; i < n_blocks; ++i) {
+    size_t ci = (size_t)((C >> i) > min_feat ? (C >> i) : min_feat);
+    size_t co = (size_t)((C >> (i + 1)) > min_feat ? (C >> (i + 1)) : min_feat);
+    size_t s = (size_t)S << i;
+    p.t1[i] = off; off += al((size_t)N * 2 * ci * s * s);
+    p.sh[i] = off; off += al((size_t)N * ci * 4 * s * s);
+    p.net[i] = off; off += al((size_t)N * co * 4 * s * s);
+    m_bl = max(m_bl, (size_t)N * co * 4 * s * s);
+  }
+  size_t P = (size_t)S << n_blocks;
+  p.bl = off; off += al(m_bl);
+  p.rgb_a = off; off += al((size_t)N * 3 * P * P);
+  p.rgb_b = off; off += al((size_t)N * 3 * P * P);
+  p.total = off;
+  return p;
+}
+}  // namespace gnrf
+
+extern "C" size_t gnrf_nr_train_saved_bytes(int N, int C, int S, int n_blocks, int min_feat) {
+  if (N <= 0 || C <= 0 || S <= 0 || n_blocks < 1 || n_blocks > 6) return 0;
+  return nr_train_plan(N, C, S, n_blocks, min_feat).total;
+}
+
+// Same computation as gnrf_neural_render_tc_fwd, but every level keeps its own t1 / sh / net buffers inside `saved` so that
+// gnrf_nr_train_bwd can differentiate it (layout: nr_train_plan).
+extern "C" int gnrf_nr_train_fwd(const float* const* params, const void* packed, const float* featmap, int N, int C, int S, int n_blocks,
+                                 int min_feat, float* img, void* saved, size_t saved_bytes, gnrf_stream_t stream) {
+  GNRF_CHECK_ARG(params && packed && featmap && img && saved);
+  GNRF_CHECK_ARG(N > 0 && C > 0 && S >= 2 && n_blocks >= 1 && n_blocks <= 6 && S % 4 == 0);
+  NrTrainPlan pl = nr_train_plan(N, C, S, n_blocks, min_feat);
+  if (saved_bytes < pl.total) return fail(GNRF_ERR_ARG, "gnrf_nr_train_fwd: saved %zu < required %zu bytes", saved_bytes, pl.total);
+  char* ws = static_cast<char*>(saved);
+  NrBufs bufs;
+  for (int i = 0; i < n_blocks; ++i) {
+    bufs.t1[i] = reinterpret_cast<float*>(ws + pl.t1[i]);
+    bufs.sh[i] = reinterpret_cast<float*>(ws + pl.sh[i]);
+    bufs.net[i] = reinterpret_cast<float*>(ws + pl.net[i]);
+  }
+  bufs.bl = reinterpret_cast<float*>(ws + pl.bl);
+  bufs.rgb_a = reinterpret_cast<float*>(ws + pl.rgb_a);
+  bufs.rgb_b = reinterpret_cast<float*>(ws + pl.rgb_b);
+  return nr_forward_bufs(params, static_cast<const unsigned char*>(packed), featmap, N, C, S, n_blocks, min_feat, img, bufs,
+                         as_stream(stream));
 }

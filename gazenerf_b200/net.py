@@ -381,6 +381,51 @@ class GazeNeRFNet(nn.Module):
                     self.last_stages.update(coarse_stage)
         return res_dict
 
+    def _wants_grad(self, train_mode: bool, *inputs) -> bool:
+        """"train" with trainable parameters, or any mode with an input that requires grad (codes / gaze / camera)."""
+        return (train_mode and any(p.requires_grad for p in self.parameters())) or any(torch.is_tensor(t) and t.requires_grad for t in inputs)
+
+    def _forward_train(self, jitter, batch_xy, bg_code, shape_code, appea_code, gaze_dir, batch_Rmats, batch_Tvecs, batch_inv_inmats,
+                       jitter_u=None):
+        """Same outputs as ``_forward`` with gradients to parameters, codes, gaze and camera (R, T); see gazenerf_b200/train.py."""
+        from .train import forward_train
+
+        if self.hier_sampling:
+            raise NotImplementedError("the differentiable path covers the coarse render only (the reference's hier branch is dead code, "
+                                      "SURVEY §0); use torch.no_grad() for hier_sampling=True")
+        if not (self.mlp_h_channel % 2 == 0 and self.featmap_size % 4 == 0 and self.num_sample_coarse % 4 == 0):
+            raise RuntimeError("training path needs even mlp_hidden_nchannels, featmap_size % 4 == 0 and num_sample_coarse % 4 == 0")
+        L = _lib.lib()
+        batch_size, tv, n_r = batch_xy.size()
+        assert tv == 2
+        assert bg_code is None  # models/gaze_nerf.py:229
+        if n_r != self.featmap_size * self.featmap_size:
+            raise RuntimeError("batch_xy carries %d rays, expected featmap_size^2 = %d" % (n_r, self.featmap_size ** 2))
+        xy = _dev_f32(batch_xy, "batch_xy")
+        dev = xy.device
+        with torch.cuda.device(dev):
+            _lib.check(L.gnrf_device_check(), "gnrf_device_check")
+            rm = _dev_f32(batch_Rmats, "batch_Rmats").reshape(batch_size, 3, 3)
+            tvecs = _dev_f32(batch_Tvecs, "batch_Tvecs").reshape(batch_size, 3)
+            kinv = _dev_f32(batch_inv_inmats, "batch_inv_inmats").reshape(batch_size, 3, 3)
+            gaze = _dev_f32(gaze_dir, "gaze_code").reshape(batch_size, 2)
+            shape_ext = torch.cat([_dev_f32(shape_code, "shape_code"), gaze], dim=1)  # models/gaze_nerf.py:248
+            appea = _dev_f32(appea_code, "appea_code")
+            assert shape_ext.shape == (batch_size, 181) and appea.shape == (batch_size, 127)
+            n_s = self.num_sample_coarse
+            if jitter and jitter_u is None:
+                jitter_u = torch.rand((batch_size, n_r, n_s + 1), device=dev, dtype=torch.float32)  # utils/model_utils.py:306
+            ju = _dev_f32(jitter_u, "jitter_u") if jitter else None
+            z_edges = torch.empty((batch_size, n_r, n_s + 1), device=dev, dtype=torch.float32)
+            _lib.check(L.gnrf_coarse_depths(tvecs.detach().data_ptr(), self._t_vals(n_s, dev).data_ptr(), ju.data_ptr() if ju is not None else None,
+                                            batch_size, n_r, n_s, float(self.opt.world_z1), float(self.opt.world_z2), z_edges.data_ptr(),
+                                            _stream()), "gnrf_coarse_depths")
+            self.last_stages = {} if self.keep_stages else None
+            imgs = forward_train(self, xy, rm, tvecs, kinv, gaze, shape_ext, appea, z_edges, stages=self.last_stages)
+            B = batch_size
+            return {"coarse_dict": {"merge_img_face": imgs[:B], "merge_img_eyes": imgs[B:2 * B], "merge_img": imgs[2 * B:3 * B],
+                                    "bg_img": imgs[3 * B:]}}
+
     def _u_lin(self, n_f1: int, device) -> torch.Tensor:
         key = (-n_f1, str(device))
         if key not in self._tvals_cache:
@@ -390,9 +435,10 @@ class GazeNeRFNet(nn.Module):
     def forward(self, mode, batch_xy, batch_uv, bg_code, shape_code, appea_code, gaze_code, batch_Rmats, batch_Tvecs,
                 batch_inv_inmats, dist_expr=False, **kwargs):
         assert mode in ["train", "test"]
-        if mode == "train" and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "backward of the fused render is SURVEY §8(f) rank 1 ('next'); run forward('train', ...) under torch.no_grad() "
-                "for jittered inference, or see DESIGN.md")
+        inputs = (shape_code, appea_code, gaze_code, batch_Rmats, batch_Tvecs)
+        if torch.is_grad_enabled() and self._wants_grad(mode == "train", *inputs):
+            # differentiable path (train.py / trainer/gazenerf_trainer.py:479-528): layer-wise forward that keeps activations
+            return self._forward_train(mode == "train", batch_xy, bg_code, shape_code, appea_code, gaze_code, batch_Rmats, batch_Tvecs,
+                                       batch_inv_inmats, jitter_u=kwargs.get("jitter_u"))
         return self._forward(mode == "train", batch_xy, batch_uv, bg_code, shape_code, appea_code, gaze_code, batch_Rmats,
                              batch_Tvecs, batch_inv_inmats, dist_expr, jitter_u=kwargs.get("jitter_u"))

@@ -1,0 +1,277 @@
+"""Training path of the drop-in ``GazeNeRFNet``: forward that keeps activations + hand-written backward, as ONE
+``torch.autograd.Function`` over libgnrf's C ABI (include/gnrf.h, "Training path").
+
+The reference trains through torch autograd over its eager graph (trainer/gazenerf_trainer.py:479-528:
+``pred = net("train", ...)``, ``loss.backward()``, Adam).  Here the same graph -- rays -> positional encoding -> both
+radiance MLPs (models/mlp_nerf.py:95-119) -> alpha composite (utils/model_utils.py:493-534) -> compose
+(models/gaze_nerf.py:175-203) -> neural renderer (models/neural_renderer.py:98-113) -- is evaluated layer by layer on
+channel-major activations kept in HBM (B200: 180 GB; ~4 GB per face and branch at 64x64x64), every dense layer and both of
+its gradients on tcgen05 tensor cores (conv_tc.cu forward / input gradient, wgrad_tc.cu weight gradient, bf16x3 split
+precision), everything else in streaming CUDA kernels (train_ops.cu, nr_train.cu).
+
+Exact rewrites used (identities of the reference graph, as in the inference kernel):
+  * the per-face code columns of FeaExt_module_0 / FeaExt_module_5 / RGB_layer_1 are folded into per-face bias vectors.  The
+    fold itself (``bias + codes @ W_code.T``, a [B,181]x[181,384] product) is written with differentiable torch ops in
+    ``branch_tensors`` so that autograd maps the per-face bias gradients back to the weight columns, the biases and the codes;
+  * density_module is evaluated as row 384 of the RGB_layer_0 GEMM; RGB_layer_2 (linear) is applied after compositing.
+PyTorch is used for device buffers, the autograd tape around the Function and those O(B x 384) per-face vector products.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+PE = 63
+N_BRANCH_T = 21  # effective tensors per branch, see branch_tensors()
+
+
+def branch_tensors(mlp, shape_ext: torch.Tensor, appea: torch.Tensor) -> List[torch.Tensor]:
+    """Effective (folded / concatenated) fp32 tensors of one radiance MLP, built with differentiable torch ops."""
+    H = mlp.h_channel
+    W = lambda n: mlp._modules[n].weight.flatten(1)
+    b = lambda n: mlp._modules[n].bias
+    n_code = shape_ext.shape[1]
+    W0, W5, W1r = W("FeaExt_module_0"), W("FeaExt_module_5"), W("RGB_layer_1")
+    t = [W0[:, :PE].contiguous(), b("FeaExt_module_0") + shape_ext @ W0[:, PE:].t()]
+    for i in (1, 2, 3, 4):
+        t += [W("FeaExt_module_%d" % i).contiguous(), b("FeaExt_module_%d" % i)]
+    # skip layer input = cat([PE 63 | codes 181 | hidden H]) (models/mlp_nerf.py:106-107); GEMM operand = [hidden H | PE 63]
+    t += [torch.cat([W5[:, PE + n_code:], W5[:, :PE]], 1).contiguous(), b("FeaExt_module_5") + shape_ext @ W5[:, PE:PE + n_code].t()]
+    for i in (6, 7):
+        t += [W("FeaExt_module_%d" % i).contiguous(), b("FeaExt_module_%d" % i)]
+    t += [torch.cat([W("RGB_layer_0"), W("density_module")], 0).contiguous(), torch.cat([b("RGB_layer_0"), b("density_module")], 0)]
+    t += [W1r[:, :H].contiguous(), b("RGB_layer_1") + appea @ W1r[:, H:].t()]
+    t += [torch.cat([W("RGB_layer_2"), b("RGB_layer_2")[:, None]], 1).contiguous()]
+    assert len(t) == N_BRANCH_T
+    return t
+
+
+class _Ops:
+    """Thin ctypes call helpers (pointer arithmetic on device buffers; every call is enqueued on the current stream)."""
+
+    def __init__(self, device):
+        self.L = _lib.lib()
+        self.dev = device
+        self.st = torch.cuda.current_stream().cuda_stream
+        self._ws: Optional[torch.Tensor] = None
+
+    def empty(self, *shape):
+        return torch.empty(shape, device=self.dev, dtype=torch.float32)
+
+    def zeros(self, *shape):
+        return torch.zeros(shape, device=self.dev, dtype=torch.float32)
+
+    def pack(self, W: torch.Tensor, bias: Optional[torch.Tensor], N: int, K: int, transposed: bool = False) -> torch.Tensor:
+        """N, K = GEMM output / input channels.  transposed: W is the forward weight [K][N]."""
+        assert W.is_contiguous() and W.dtype == torch.float32 and W.shape == ((K, N) if transposed else (N, K)), (W.shape, N, K)
+        pk = torch.empty((self.L.gnrf_conv_tc_packed_bytes(N, K),), device=self.dev, dtype=torch.uint8)
+        _lib.check(self.L.gnrf_conv_tc_pack(W.data_ptr(), bias.data_ptr() if bias is not None else None, N, K, 1 if transposed else 0,
+                                            pk.data_ptr(), self.st), "gnrf_conv_tc_pack")
+        return pk
+
+    def conv(self, pk, N, K, x_ptr, xs, out_ptr, os_, n_img, HW, act=0, bias_img=None, mask_ptr=None, ms=0, mask_rows=0, slope=0.0,
+             add_ptr=None, as_=0, add_rows=0):
+        _lib.check(self.L.gnrf_conv_tc(pk.data_ptr(), N, K, x_ptr, xs, bias_img.data_ptr() if bias_img is not None else None, out_ptr, os_,
+                                       act, mask_ptr, ms, mask_rows, slope, add_ptr, as_, add_rows, n_img, HW, self.st), "gnrf_conv_tc")
+
+    def wgrad(self, dy_ptr, dys, x_ptr, xs, N, K, n_img, HW, db_mode: str):
+        """-> dW [N][K], db ([n_img][N] for 'img', [N] for 'sum', None for 'none')."""
+        need = self.L.gnrf_wgrad_tc_workspace_bytes(N, K, n_img, HW)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty((need,), device=self.dev, dtype=torch.uint8)
+        dW = self.empty(N, K)
+        db = self.empty(n_img, N) if db_mode == "img" else (self.empty(N) if db_mode == "sum" else None)
+        _lib.check(self.L.gnrf_wgrad_tc(dy_ptr, dys, x_ptr, xs, N, K, n_img, HW, dW.data_ptr(), db.data_ptr() if db is not None else None,
+                                        1 if db_mode == "sum" else 0, 0, self._ws.data_ptr(), self._ws.numel(), self.st), "gnrf_wgrad_tc")
+        return dW, db
+
+
+RELU, NONE = 1, 0
+
+
+def _branch_forward(o: _Ops, T: Sequence[torch.Tensor], B, n_r, n_s, H, C, ray_dl, tvecs, z_edges) -> Dict[str, torch.Tensor]:
+    """One radiance MLP + composite on channel-major activations; returns everything the backward needs."""
+    L, P = o.L, n_r * n_s
+    H2, S0 = H // 2, (H + 64) * P
+    f4 = 4
+    buf0 = o.empty(B, H + 64, P)           # rows [0,H): layer-4 output; rows [H, H+63): positional encoding (shared by layers 0 and 5)
+    pe_ptr = buf0.data_ptr() + H * P * f4
+    _lib.check(L.gnrf_pe_fwd(ray_dl.data_ptr(), tvecs.data_ptr(), z_edges.data_ptr(), B, n_r, n_s, pe_ptr, S0, o.st), "gnrf_pe_fwd")
+    h: List[Optional[torch.Tensor]] = [None] * 8
+    h[0] = o.empty(B, H, P)
+    o.conv(o.pack(T[0], None, H, PE), H, PE, pe_ptr, S0, h[0].data_ptr(), 0, B, P, act=RELU, bias_img=T[1])
+    for i in (1, 2, 3):
+        h[i] = o.empty(B, H, P)
+        o.conv(o.pack(T[2 * i], T[2 * i + 1], H, H), H, H, h[i - 1].data_ptr(), 0, h[i].data_ptr(), 0, B, P, act=RELU)
+    o.conv(o.pack(T[8], T[9], H, H), H, H, h[3].data_ptr(), 0, buf0.data_ptr(), S0, B, P, act=RELU)          # layer 4 -> buf0 rows [0,H)
+    h[5] = o.empty(B, H, P)
+    o.conv(o.pack(T[10], None, H, H + PE), H, H + PE, buf0.data_ptr(), S0, h[5].data_ptr(), 0, B, P, act=RELU, bias_img=T[11])
+    for i, k in ((6, 12), (7, 14)):
+        h[i] = o.empty(B, H, P)
+        o.conv(o.pack(T[k], T[k + 1], H, H), H, H, h[i - 1].data_ptr(), 0, h[i].data_ptr(), 0, B, P, act=RELU)
+    r0 = o.empty(B, H + 1, P)              # rows [0,H): RGB_layer_0 output; row H: raw density
+    o.conv(o.pack(T[16], T[17], H + 1, H), H + 1, H, h[7].data_ptr(), 0, r0.data_ptr(), 0, B, P, act=NONE)
+    hc = o.empty(B, H2, P)
+    o.conv(o.pack(T[18], None, H2, H), H2, H, r0.data_ptr(), (H + 1) * P, hc.data_ptr(), 0, B, P, act=RELU, bias_img=T[19])
+    Hc, bg_alpha, w = o.empty(B, H2 + 1, n_r), o.empty(B, n_r), o.empty(B, n_r, n_s)
+    sig_ptr = r0.data_ptr() + H * P * f4
+    _lib.check(L.gnrf_composite_cm_fwd(hc.data_ptr(), 0 + H2 * P, sig_ptr, (H + 1) * P, z_edges.data_ptr(), ray_dl.data_ptr(), B, n_r, n_s, H2,
+                                       Hc.data_ptr(), bg_alpha.data_ptr(), w.data_ptr(), o.st), "gnrf_composite_cm_fwd")
+    feat = o.empty(B, C, n_r)
+    o.conv(o.pack(T[20], None, C, H2 + 1), C, H2 + 1, Hc.data_ptr(), 0, feat.data_ptr(), 0, B, n_r, act=NONE)
+    return {"buf0": buf0, "h": h, "r0": r0, "hc": hc, "Hc": Hc, "bg_alpha": bg_alpha, "w": w, "feat": feat}
+
+
+def _branch_backward(o: _Ops, T: Sequence[torch.Tensor], sv: Dict[str, torch.Tensor], B, n_r, n_s, H, C, ray_dl, z_edges, g_feat, g_alpha,
+                     g_m, g_o, g_z, g_l) -> List[torch.Tensor]:
+    """Gradients of the 21 effective tensors; accumulates the per-ray geometry gradients into g_m / g_o / g_z / g_l."""
+    L, P = o.L, n_r * n_s
+    H2, S0, f4 = H // 2, (H + 64) * P, 4
+    buf0, h, r0, hc, Hc, w = sv["buf0"], sv["h"], sv["r0"], sv["hc"], sv["Hc"], sv["w"]
+    pe_ptr = buf0.data_ptr() + H * P * f4
+    g: List[Optional[torch.Tensor]] = [None] * N_BRANCH_T
+    # RGB_layer_2 (after the composite): feat = [W2 | b2] [Hc ; sum w]
+    g[20], _ = o.wgrad(g_feat.data_ptr(), 0, Hc.data_ptr(), 0, C, H2 + 1, B, n_r, "none")
+    g_Hc = o.empty(B, H2 + 1, n_r)
+    o.conv(o.pack(T[20], None, H2 + 1, C, transposed=True), H2 + 1, C, g_feat.data_ptr(), 0, g_Hc.data_ptr(), 0, B, n_r)
+    g_r0, g_hc = o.empty(B, H + 1, P), o.empty(B, H2, P)
+    _lib.check(L.gnrf_composite_cm_bwd(g_Hc.data_ptr(), g_alpha.data_ptr(), hc.data_ptr(), H2 * P, r0.data_ptr() + H * P * f4, (H + 1) * P,
+                                       w.data_ptr(), z_edges.data_ptr(), ray_dl.data_ptr(), B, n_r, n_s, H2, g_hc.data_ptr(), H2 * P,
+                                       g_r0.data_ptr() + H * P * f4, (H + 1) * P, g_z.data_ptr(), g_l.data_ptr(), o.st), "gnrf_composite_cm_bwd")
+    # RGB_layer_1 (hidden part; the appearance columns live in the per-face bias)
+    g[18], g[19] = o.wgrad(g_hc.data_ptr(), 0, r0.data_ptr(), (H + 1) * P, H2, H, B, P, "img")
+    o.conv(o.pack(T[18], None, H, H2, transposed=True), H, H2, g_hc.data_ptr(), 0, g_r0.data_ptr(), (H + 1) * P, B, P)
+    del g_hc
+    # RGB_layer_0 + density_module on h7
+    g[16], g[17] = o.wgrad(g_r0.data_ptr(), 0, h[7].data_ptr(), 0, H + 1, H, B, P, "sum")
+    ga = o.empty(B, H, P)
+    o.conv(o.pack(T[16], None, H, H + 1, transposed=True), H, H + 1, g_r0.data_ptr(), 0, ga.data_ptr(), 0, B, P, mask_ptr=h[7].data_ptr())
+    del g_r0
+    for i, k in ((7, 14), (6, 12)):
+        g[k], g[k + 1] = o.wgrad(ga.data_ptr(), 0, h[i - 1].data_ptr(), 0, H, H, B, P, "sum")
+        gb = o.empty(B, H, P)
+        o.conv(o.pack(T[k], None, H, H, transposed=True), H, H, ga.data_ptr(), 0, gb.data_ptr(), 0, B, P, mask_ptr=h[i - 1].data_ptr())
+        ga = gb
+    # skip layer 5: operand [h4 | PE] in buf0
+    g[10], g[11] = o.wgrad(ga.data_ptr(), 0, buf0.data_ptr(), S0, H, H + PE, B, P, "img")
+    g_buf0 = o.empty(B, H + 64, P)
+    o.conv(o.pack(T[10], None, H + PE, H, transposed=True), H + PE, H, ga.data_ptr(), 0, g_buf0.data_ptr(), S0, B, P,
+           mask_ptr=buf0.data_ptr(), ms=S0, mask_rows=H)
+    # layer 4 (its output gradient = rows [0,H) of g_buf0)
+    g[8], g[9] = o.wgrad(g_buf0.data_ptr(), S0, h[3].data_ptr(), 0, H, H, B, P, "sum")
+    ga = o.empty(B, H, P)
+    o.conv(o.pack(T[8], None, H, H, transposed=True), H, H, g_buf0.data_ptr(), S0, ga.data_ptr(), 0, B, P, mask_ptr=h[3].data_ptr())
+    for i in (3, 2, 1):
+        g[2 * i], g[2 * i + 1] = o.wgrad(ga.data_ptr(), 0, h[i - 1].data_ptr(), 0, H, H, B, P, "sum")
+        gb = o.empty(B, H, P)
+        o.conv(o.pack(T[2 * i], None, H, H, transposed=True), H, H, ga.data_ptr(), 0, gb.data_ptr(), 0, B, P, mask_ptr=h[i - 1].data_ptr())
+        ga = gb
+    # layer 0 on the positional encoding
+    g[0], g[1] = o.wgrad(ga.data_ptr(), 0, pe_ptr, S0, H, PE, B, P, "img")
+    g_pe = o.empty(B, PE, P)
+    o.conv(o.pack(T[0], None, PE, H, transposed=True), PE, H, ga.data_ptr(), 0, g_pe.data_ptr(), 0, B, P)
+    _lib.check(L.gnrf_pe_bwd(g_pe.data_ptr(), PE * P, g_buf0.data_ptr() + H * P * f4, S0, pe_ptr, S0, ray_dl.data_ptr(), z_edges.data_ptr(),
+                             B, n_r, n_s, g_m.data_ptr(), g_o.data_ptr(), g_z.data_ptr(), o.st), "gnrf_pe_bwd")
+    return g  # type: ignore[return-value]
+
+
+class RenderTrainFn(torch.autograd.Function):
+    """images [3B+1, 3, P, P] = (merge_img_face | merge_img_eyes | merge_img | bg_img) with gradients to every argument tensor."""
+
+    @staticmethod
+    def forward(ctx, cfg, xy, rmats, tvecs, kinv, gaze, z_edges, bg_featmap, *tensors):
+        net, H, C, S, n_s = cfg["net"], cfg["H"], cfg["C"], cfg["S"], cfg["n_s"]
+        nr = net.neural_render
+        B, n_r = xy.shape[0], xy.shape[2]
+        o = _Ops(xy.device)
+        L = o.L
+        T = [t.detach().contiguous() for t in tensors]
+        Tf, Te, Tn = T[:N_BRANCH_T], T[N_BRANCH_T:2 * N_BRANCH_T], T[2 * N_BRANCH_T:]
+        ray_dl = o.empty(B, n_r, 4)
+        _lib.check(L.gnrf_ray_setup(xy.data_ptr(), rmats.data_ptr(), kinv.data_ptr(), B, n_r, ray_dl.data_ptr(), o.st), "gnrf_ray_setup")
+        sv_f = _branch_forward(o, Tf, B, n_r, n_s, H, C, ray_dl, tvecs, z_edges)
+        sv_e = _branch_forward(o, Te, B, n_r, n_s, H, C, ray_dl, tvecs, z_edges)
+        n_img = 3 * B + 1
+        fm = o.empty(n_img, C, S, S)
+        bg = bg_featmap.detach().contiguous()
+        _lib.check(L.gnrf_compose_fwd(sv_f["feat"].data_ptr(), sv_f["bg_alpha"].data_ptr(), sv_e["feat"].data_ptr(), sv_e["bg_alpha"].data_ptr(),
+                                      bg.data_ptr(), gaze.data_ptr(), B, C, S * S, fm.data_ptr(), o.st), "gnrf_compose_fwd")
+        fm[3 * B].copy_(bg[0])
+        Pimg = S << nr.n_blocks
+        imgs = o.empty(n_img, 3, Pimg, Pimg)
+        saved_bytes = L.gnrf_nr_train_saved_bytes(n_img, C, S, nr.n_blocks, nr.min_feat)
+        saved = torch.empty((saved_bytes,), device=xy.device, dtype=torch.uint8)
+        packed = nr.packed_tc()
+        _lib.check(L.gnrf_nr_train_fwd(_lib.ptr_array([t.data_ptr() for t in Tn]), packed.data_ptr(), fm.data_ptr(), n_img, C, S, nr.n_blocks,
+                                       nr.min_feat, imgs.data_ptr(), saved.data_ptr(), saved_bytes, o.st), "gnrf_nr_train_fwd")
+        ctx.cfg = cfg
+        ctx.keep = dict(xy=xy, rmats=rmats, kinv=kinv, gaze=gaze, z_edges=z_edges, bg=bg, ray_dl=ray_dl, T=T, sv_f=sv_f, sv_e=sv_e, fm=fm,
+                        imgs=imgs, saved=saved)
+        if cfg.get("stages") is not None:
+            cfg["stages"].update({"feat_face": sv_f["feat"], "feat_eyes": sv_e["feat"], "bg_alpha_face": sv_f["bg_alpha"],
+                                  "bg_alpha_eyes": sv_e["bg_alpha"], "w_face": sv_f["w"], "w_eyes": sv_e["w"], "featmaps": fm})
+        return imgs
+
+    @staticmethod
+    def backward(ctx, g_imgs):
+        cfg, k = ctx.cfg, ctx.keep
+        net, H, C, S, n_s = cfg["net"], cfg["H"], cfg["C"], cfg["S"], cfg["n_s"]
+        nr = net.neural_render
+        xy, ray_dl, z_edges, T = k["xy"], k["ray_dl"], k["z_edges"], k["T"]
+        B, n_r = xy.shape[0], xy.shape[2]
+        o = _Ops(xy.device)
+        L = o.L
+        Tf, Te, Tn = T[:N_BRANCH_T], T[N_BRANCH_T:2 * N_BRANCH_T], T[2 * N_BRANCH_T:]
+        n_img = 3 * B + 1
+        g_imgs = g_imgs.contiguous().float()
+        # ---- neural renderer
+        g_fm = o.empty(n_img, C, S, S)
+        g_n = [torch.empty_like(t) for t in Tn]
+        ws_bytes = L.gnrf_nr_train_bwd_workspace_bytes(n_img, C, S, nr.n_blocks, nr.min_feat)
+        ws = torch.empty((ws_bytes,), device=xy.device, dtype=torch.uint8)
+        _lib.check(L.gnrf_nr_train_bwd(_lib.ptr_array([t.data_ptr() for t in Tn]), k["fm"].data_ptr(), k["saved"].data_ptr(),
+                                       k["imgs"].data_ptr(), g_imgs.data_ptr(), n_img, C, S, nr.n_blocks, nr.min_feat, g_fm.data_ptr(),
+                                       _lib.ptr_array([t.data_ptr() for t in g_n]), ws.data_ptr(), ws_bytes, o.st), "gnrf_nr_train_bwd")
+        del ws
+        # ---- compose
+        P2 = S * S
+        sv_f, sv_e = k["sv_f"], k["sv_e"]
+        g_ff, g_fe = o.empty(B, C, P2), o.empty(B, C, P2)
+        g_af, g_ae = o.empty(B, P2), o.empty(B, P2)
+        g_bg = o.empty(1, C, S, S)
+        nblk = L.gnrf_compose_bwd_blocks(P2)
+        g_gz = o.empty(B, nblk, 2)
+        _lib.check(L.gnrf_compose_bwd(g_fm.data_ptr(), sv_f["feat"].data_ptr(), sv_f["bg_alpha"].data_ptr(), sv_e["feat"].data_ptr(),
+                                      sv_e["bg_alpha"].data_ptr(), k["bg"].data_ptr(), k["gaze"].data_ptr(), B, C, P2, g_ff.data_ptr(),
+                                      g_af.data_ptr(), g_fe.data_ptr(), g_ae.data_ptr(), g_bg.data_ptr(), g_gz.data_ptr(), o.st),
+                   "gnrf_compose_bwd")
+        g_bg = g_bg + g_fm[3 * B:3 * B + 1]
+        g_gaze = g_gz.sum(1)
+        # ---- radiance MLPs + composite + positional encoding
+        g_m, g_o, g_l = o.zeros(B, n_r, 3), o.zeros(B, n_r, 3), o.zeros(B, n_r)
+        g_z = o.zeros(B, n_r, n_s + 1)
+        g_f = _branch_backward(o, Tf, sv_f, B, n_r, n_s, H, C, ray_dl, z_edges, g_ff, g_af, g_m, g_o, g_z, g_l)
+        g_e = _branch_backward(o, Te, sv_e, B, n_r, n_s, H, C, ray_dl, z_edges, g_fe, g_ae, g_m, g_o, g_z, g_l)
+        # ---- geometry
+        contrib = o.empty(B, n_r, 12)
+        _lib.check(L.gnrf_geom_bwd(xy.data_ptr(), k["rmats"].data_ptr(), k["kinv"].data_ptr(), g_m.data_ptr(), g_o.data_ptr(), g_l.data_ptr(),
+                                   g_z.data_ptr(), B, n_r, n_s, contrib.data_ptr(), o.st), "gnrf_geom_bwd")
+        cs = contrib.sum(1)
+        g_R, g_T = cs[:, :9].reshape(B, 3, 3), cs[:, 9:].reshape(B, 3)
+        ctx.keep = None
+        grads = [None, None, g_R, g_T, None, g_gaze, None, g_bg] + g_f + g_e + g_n
+        need = ctx.needs_input_grad
+        return tuple(gr if (i < len(need) and need[i]) else None for i, gr in enumerate(grads))
+
+
+def forward_train(net, xy, rmats, tvecs, kinv, gaze, shape_ext, appea, z_edges, stages=None) -> torch.Tensor:
+    """Differentiable render: returns images [3B+1,3,P,P].  ``shape_ext`` / ``appea`` / ``gaze`` / ``rmats`` / ``tvecs`` may require
+    grad (the reference optimises code offsets and camera deltas, trainer/gazenerf_trainer.py:338-405)."""
+    tf = branch_tensors(net.fg_CD_predictor_face, shape_ext, appea)
+    te = branch_tensors(net.fg_CD_predictor_eyes, shape_ext, appea)
+    tn = [p if p.dim() == 1 else p.flatten(1) for p in net.neural_render.param_list()]
+    cfg = {"net": net, "H": net.mlp_h_channel, "C": net.featmap_nc, "S": net.featmap_size, "n_s": net.num_sample_coarse, "stages": stages}
+    return RenderTrainFn.apply(cfg, xy, rmats, tvecs, kinv, gaze, z_edges, net.neural_render.bg_featmap, *tf, *te, *tn)

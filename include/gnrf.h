@@ -141,6 +141,79 @@ int gnrf_neural_render_tc_fwd(const float* const* params, const void* packed, co
                               int n_blocks, int min_feat, float* img, void* workspace, size_t workspace_bytes,
                               gnrf_stream_t stream);
 
+/* =========================================================================================================
+ * Training path (forward that keeps activations + backward).  The reference gets its gradients from torch
+ * autograd over the same graph (train.py -> trainer/gazenerf_trainer.py:479-528, loss.backward()); these entry
+ * points are the stages gazenerf_b200/train.py chains inside ONE torch.autograd.Function.  Everything is
+ * channel-major: [image][channel][pixel or sample point], points contiguous; "img stride" arguments are the
+ * element distance between consecutive images (0 = dense).
+ * ========================================================================================================= */
+enum { GNRF_ACT_NONE = 0, GNRF_ACT_RELU = 1, GNRF_ACT_LRELU02 = 2 };
+
+/* Generic 1x1 convolution / per-point Linear on tcgen05 (bf16x3 split, fp32 accumulate):
+ *   out[img][n][p] = act( sum_k W[n][k] X[img][k][p] + bias[n] + bias_img[img][n] ) * (mask > 0 ? 1 : mask_slope) + add
+ * Replaces nn.Conv2d(k=1) forward (models/mlp_nerf.py:29-93, models/pixel_shuffle_upsample.py:26-31) and, with the
+ * transposed weight packed, its input gradient.  mask / add / bias_img may be NULL; mask applies to rows < mask_rows and
+ * add to rows < add_rows (0 = all rows).  gnrf_conv_tc_pack: W dense [N][K], or with transposed != 0 a dense [K][N] matrix
+ * whose transpose is used; bias may be NULL.  packed: gnrf_conv_tc_packed_bytes(N, K), 128-byte aligned. */
+size_t gnrf_conv_tc_packed_bytes(int N, int K);
+int gnrf_conv_tc_pack(const float* W, const float* bias, int N, int K, int transposed, void* packed, gnrf_stream_t stream);
+int gnrf_conv_tc(const void* packed, int N, int K, const float* X, long long x_img_stride, const float* bias_img, float* out,
+                 long long out_img_stride, int act, const float* mask, long long mask_img_stride, int mask_rows,
+                 float mask_slope, const float* add, long long add_img_stride, int add_rows, int n_img, int HW,
+                 gnrf_stream_t stream);
+
+/* Weight gradient of the same layer on tcgen05:  dW[n][k] (=, += if accumulate) sum_img sum_p dY[img][n][p] X[img][k][p];
+ * db (nullable): db_sum == 0 -> [n_img][N] per-image sum_p dY (the per-face folded-code bias), else [N] summed over images.
+ * Deterministic split-K (partials in `workspace`, gnrf_wgrad_tc_workspace_bytes).  HW and strides multiples of 4. */
+size_t gnrf_wgrad_tc_workspace_bytes(int N, int K, int n_img, int HW);
+int gnrf_wgrad_tc(const float* dY, long long dy_img_stride, const float* X, long long x_img_stride, int N, int K, int n_img,
+                  int HW, float* dW, float* db, int db_sum, int accumulate, void* workspace, size_t workspace_bytes,
+                  gnrf_stream_t stream);
+
+/* Positional encoding of the sample points, channel-major (Embedder.forward, utils/model_utils.py:272-280, on
+ * pts = o + d*l*z, :315):  pe [B][63][N_r*N_s].  gnrf_pe_bwd: gradients arriving at the encoding from layer 0 (g_pe_a) and
+ * from the skip layer (g_pe_b, nullable) -> per-ray  g_m [B][N_r][3] (d*l), g_o [B][N_r][3], g_z [B][N_r][N_s+1]  (all +=). */
+int gnrf_pe_fwd(const float* ray_dl, const float* tvecs, const float* z_edges, int B, int N_r, int N_s, float* pe,
+                long long pe_img_stride, gnrf_stream_t stream);
+int gnrf_pe_bwd(const float* g_pe_a, long long ga_stride, const float* g_pe_b, long long gb_stride, const float* pe,
+                long long pe_stride, const float* ray_dl, const float* z_edges, int B, int N_r, int N_s, float* g_m, float* g_o,
+                float* g_z, gnrf_stream_t stream);
+
+/* Alpha compositing on channel-major activations (CalcRayColor.forward, utils/model_utils.py:493-534; sigma = ReLU(raw)):
+ *   h [B][C][N_r*N_s], sigma_raw [B][N_r*N_s]  ->  Hc [B][C+1][N_r] (row C = sum_k w_k), bg_alpha [B][N_r], weights [B][N_r][N_s].
+ * Backward: g_Hc [B][C+1][N_r], g_bg_alpha (nullable) -> g_h [B][C][P] (already multiplied by h > 0: h is a post-ReLU
+ * activation), g_sigma [B][P] (w.r.t. the raw density), g_z [B][N_r][N_s+1] (+=), g_l [B][N_r] (+=). */
+int gnrf_composite_cm_fwd(const float* h, long long h_stride, const float* sigma_raw, long long s_stride, const float* z_edges,
+                          const float* ray_dl, int B, int N_r, int N_s, int C, float* Hc, float* bg_alpha, float* weights,
+                          gnrf_stream_t stream);
+int gnrf_composite_cm_bwd(const float* g_Hc, const float* g_bg_alpha, const float* h, long long h_stride, const float* sigma_raw,
+                          long long s_stride, const float* weights, const float* z_edges, const float* ray_dl, int B, int N_r,
+                          int N_s, int C, float* g_h, long long gh_stride, float* g_sigma, long long gs_stride, float* g_z,
+                          float* g_l, gnrf_stream_t stream);
+
+/* Ray geometry backward (GenSamplePoints, utils/model_utils.py:364-372): per-ray gradients -> contrib [B][N_r][12] =
+ * (dL/dR 3x3 row-major, dL/dT 3); the caller sums over rays. */
+int gnrf_geom_bwd(const float* xy, const float* rmats, const float* inv_inmats, const float* g_m, const float* g_o,
+                  const float* g_l, const float* g_z, int B, int N_r, int N_s, float* contrib, gnrf_stream_t stream);
+
+/* Backward of gnrf_compose_fwd.  g_out [3][B][C][P] -> g_feat_* [B][C][P], g_a_* [B][P], g_bg [C][P],
+ * g_gaze_part [B][gnrf_compose_bwd_blocks(P)][2] (the caller sums over blocks). */
+int gnrf_compose_bwd_blocks(int P);
+int gnrf_compose_bwd(const float* g_out, const float* feat_face, const float* a_face, const float* feat_eyes, const float* a_eyes,
+                     const float* bg, const float* gaze, int B, int C, int P, float* g_feat_face, float* g_a_face,
+                     float* g_feat_eyes, float* g_a_eyes, float* g_bg, float* g_gaze_part, gnrf_stream_t stream);
+
+/* Neural renderer, training: forward that keeps per-level activations in `saved` (gnrf_nr_train_saved_bytes), and its
+ * backward -> g_featmap [N][C][S][S] and g_params (HOST array of device pointers, same order / shapes as params). */
+size_t gnrf_nr_train_saved_bytes(int N, int C, int S, int n_blocks, int min_feat);
+int gnrf_nr_train_fwd(const float* const* params, const void* packed, const float* featmap, int N, int C, int S, int n_blocks,
+                      int min_feat, float* img, void* saved, size_t saved_bytes, gnrf_stream_t stream);
+size_t gnrf_nr_train_bwd_workspace_bytes(int N, int C, int S, int n_blocks, int min_feat);
+int gnrf_nr_train_bwd(const float* const* params, const float* featmap, const void* saved, const float* img, const float* g_img,
+                      int N, int C, int S, int n_blocks, int min_feat, float* g_featmap, float* const* g_params, void* workspace,
+                      size_t workspace_bytes, gnrf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,402 @@
+"""Training path: gradients of the drop-in forward against (a) gradient goldens produced by the UNMODIFIED reference's own autograd
+(oracle/gen_golden_grad.py) and (b) autograd of the CPU oracle, plus unit parity of every training-path C-ABI stage.
+
+Tolerances: gradients are compared as relative L2 per tensor, <= 5e-3.  The GEMMs themselves are good to ~1e-5 (bf16x3 split, unit
+tests below hold them to 3e-5); what dominates is that ReLU / LeakyReLU / max masks are decided on forward values that differ from
+the CPU reference by ~1e-5, so a fraction ~1e-5 of the mask decisions flip and each flip changes one gradient element by O(1):
+relative L2 ~ sqrt(1e-5) = 3e-3 on tensors that few elements feed (the reference's own CPU-vs-CUDA runs differ the same way).
+Forward images <= 2e-4.
+CPU tests (not gpu) pin the ORACLE's autograd to the reference gradient goldens, so the oracle is a valid gradient checker.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_state_dict, load_golden, rel_l2
+from oracle import gazenerf_oracle as O
+
+IMG_KEYS = ("merge_img_face", "merge_img_eyes", "merge_img", "bg_img")
+TOL_GRAD = 5e-3
+TOL_GRAD_SMALL = 1e-2   # camera / gaze gradients: sums of many cancelling terms
+
+
+def loss_weights(shapes, seed=99):  # same recipe as oracle/gen_golden_grad.py
+    g = torch.Generator().manual_seed(seed)
+    return {k: torch.randn(shapes[k], generator=g) for k in IMG_KEYS}
+
+
+def proj_vec(shape, idx):
+    g = torch.Generator().manual_seed(1000 + idx)
+    return torch.randn(shape, generator=g)
+
+
+def oracle_grads(sd, oo, mode, g, jitter_u=None):
+    """loss + gradients through the CPU oracle's autograd."""
+    sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and not k.endswith(".f")) for k, v in sd.items()}
+    t = lambda k: torch.from_numpy(g[k])
+    leaves = {"shape": t("in_shape").requires_grad_(True), "appea": t("in_appea").requires_grad_(True), "gaze": t("in_gaze").requires_grad_(True),
+              "R": t("in_R").requires_grad_(True), "T": t("in_T").requires_grad_(True)}
+    out = O.forward(sd, oo, mode, t("in_xy"), leaves["shape"], leaves["appea"], leaves["gaze"], leaves["R"], leaves["T"], t("in_Kinv"),
+                    jitter_u=jitter_u)["coarse_dict"]
+    wt = loss_weights({k: out[k].shape for k in IMG_KEYS})
+    loss = sum((out[k] * wt[k]).sum() for k in IMG_KEYS)
+    loss.backward()
+    gp = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in sd.items() if v.requires_grad}
+    return float(loss.detach()), {k: v.grad for k, v in leaves.items()}, gp
+
+
+def _oo(g):
+    m = g["meta"]
+    return O.OracleOptions(featmap_size=int(m[0]), featmap_nc=int(m[1]), pred_img_size=int(m[2]), num_sample_coarse=int(m[3]),
+                           mlp_hidden_nchannels=int(m[4]))
+
+
+# ------------------------------------------------------------------------------------------------ CPU: oracle autograd == reference autograd
+def test_oracle_autograd_matches_reference_tiny():
+    g, gg = load_golden("tiny"), load_golden("tiny_grad")
+    loss, gin, gp = oracle_grads(golden_state_dict(g), _oo(g), "test", g)
+    assert abs(loss - float(gg["loss"][0])) < 1e-4 * abs(float(gg["loss"][0]))
+    for k, v in gin.items():
+        assert rel_l2(v, gg["gin/" + k]) < 2e-4, k
+    n = 0
+    for k, v in gp.items():
+        ref = torch.from_numpy(gg["gp/" + k])
+        if float(ref.abs().max()) == 0.0:
+            assert float(v.abs().max()) == 0.0, k
+            continue
+        assert rel_l2(v, ref) < 2e-4, k
+        n += 1
+    assert n > 60
+
+
+def _std_train_sd(g):
+    import gazenerf_b200 as G
+    opt = G.BaseOptions({"featmap_size": 8, "featmap_nc": 258, "pred_img_size": 64})
+    opt.num_sample_coarse = 8
+    torch.manual_seed(45)
+    net = G.GazeNeRFNet(opt, include_vd=False, hier_sampling=False)
+    sd = O.densify({k: v.clone() for k, v in net.state_dict().items()}, *g["dense_bias"])
+    return opt, net, sd
+
+
+def test_oracle_autograd_matches_reference_std_train():
+    g, gg = load_golden("std_dense_train"), load_golden("std_dense_train_grad")
+    opt, net, sd = _std_train_sd(g)
+    loss, gin, gp = oracle_grads(sd, _oo(g), "train", g, jitter_u=torch.from_numpy(g["jitter_u"]))
+    assert abs(loss - float(gg["loss"][0])) < 1e-4 * abs(float(gg["loss"][0]))
+    for k, v in gin.items():
+        assert rel_l2(v, gg["gin/" + k]) < 5e-4, k
+    names = [k for k, _ in net.named_parameters()]
+    for i, k in enumerate(names):
+        s = gg["gs/" + k]
+        v = gp[k].double()
+        got = np.array([float(v.sum()), float(v.abs().sum()), float(v.norm()), float((v * proj_vec(v.shape, i).double()).sum())])
+        scale = max(s[2], 1e-12)  # l2 norm of the reference gradient
+        assert abs(got[2] - s[2]) < 5e-4 * scale, k
+        assert abs(got[3] - s[3]) < 2e-3 * scale * np.sqrt(v.numel()) ** 0 + 2e-3 * abs(s[3]) + 1e-3 * scale, k
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+gpu = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import gazenerf_b200._lib as _lib
+    assert torch.cuda.is_available()
+    _lib.check(_lib.lib().gnrf_device_check(), "gnrf_device_check")
+    return torch.device("cuda:0")
+
+
+def S():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@gpu
+@pytest.mark.parametrize("N,K,HW,n_img", [(384, 384, 512, 2), (385, 384, 640, 1), (63, 384, 200, 2), (447, 384, 384, 2), (3, 64, 4096, 3), (258, 193, 64, 2)])
+def test_conv_tc_generic(dev, N, K, HW, n_img):
+    """gnrf_conv_tc with per-image bias, strides, mask, add vs float64 einsum."""
+    from gazenerf_b200 import _lib
+    from gazenerf_b200.train import _Ops
+    o = _Ops(dev)
+    g = torch.Generator().manual_seed(N * 7 + K)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    bi = torch.randn(n_img, N, generator=g)
+    rows_x = K + 5
+    X = torch.randn(n_img, rows_x, HW, generator=g)       # strided input: only the first K rows are used
+    mask = torch.randn(n_img, N, HW, generator=g)
+    add = torch.randn(n_img, N, HW, generator=g)
+    for act, use_mask, use_add, tr in ((1, False, False, False), (0, True, True, True), (2, True, False, False)):
+        Wd = (W.t().contiguous() if tr else W).to(dev)
+        pk = o.pack(Wd, b.to(dev), N, K, transposed=tr)
+        out = torch.full((n_img, N + 2, HW), -7.0, device=dev)
+        Xd, md, ad, bid = X.to(dev), mask.to(dev), add.to(dev), bi.to(dev)
+        mrows = N // 2
+        o.conv(pk, N, K, Xd.data_ptr(), rows_x * HW, out.data_ptr(), (N + 2) * HW, n_img, HW, act=act, bias_img=bid,
+               mask_ptr=md.data_ptr() if use_mask else None, mask_rows=mrows, slope=0.2, add_ptr=ad.data_ptr() if use_add else None)
+        torch.cuda.synchronize()
+        ref = torch.einsum("nk,ikp->inp", W.double(), X[:, :K].double()) + b.double()[None, :, None] + bi.double()[:, :, None]
+        if act == 1:
+            ref = ref.clamp_min(0)
+        elif act == 2:
+            ref = torch.where(ref >= 0, ref, 0.2 * ref)
+        if use_mask:
+            m = torch.where(mask.double() > 0, 1.0, 0.2)
+            m[:, mrows:] = 1.0
+            ref = ref * m
+        if use_add:
+            ref = ref + add.double()
+        got = out.cpu()
+        assert rel_l2(got[:, :N], ref) < 3e-5, (act, use_mask, use_add, tr)
+        assert float((got[:, N:] + 7.0).abs().max()) == 0.0   # rows beyond N untouched
+
+
+@gpu
+@pytest.mark.parametrize("N,K,HW,n_img", [(384, 384, 2048, 2), (385, 384, 512, 2), (384, 447, 576, 1), (3, 64, 4096, 3), (258, 193, 64, 2),
+                                           (1032, 516, 256, 2), (192, 384, 100, 2)])
+def test_wgrad_tc(dev, N, K, HW, n_img):
+    from gazenerf_b200.train import _Ops
+    o = _Ops(dev)
+    g = torch.Generator().manual_seed(N + K)
+    dY = torch.randn(n_img, N + 3, HW, generator=g)
+    X = torch.randn(n_img, K + 1, HW, generator=g)
+    dYd, Xd = dY.to(dev), X.to(dev)
+    ref_w = torch.einsum("inp,ikp->nk", dY[:, :N].double(), X[:, :K].double())
+    ref_b = dY[:, :N].double().sum(2)
+    for mode in ("img", "sum", "none"):
+        dW, db = o.wgrad(dYd.data_ptr(), (N + 3) * HW, Xd.data_ptr(), (K + 1) * HW, N, K, n_img, HW, mode)
+        torch.cuda.synchronize()
+        assert rel_l2(dW.cpu(), ref_w) < 3e-5, mode
+        if mode == "img":
+            assert rel_l2(db.cpu(), ref_b) < 1e-5
+        elif mode == "sum":
+            assert rel_l2(db.cpu(), ref_b.sum(0)) < 1e-5
+
+
+@gpu
+def test_pe_and_composite_cm(dev):
+    """channel-major PE + composite forward/backward vs the oracle's autograd."""
+    from gazenerf_b200 import _lib
+    L = _lib.lib()
+    g = load_golden("std_dense_train")
+    B, n_r, n_s, C = 2, 64, 8, 24
+    P = n_r * n_s
+    t = lambda k: torch.from_numpy(g[k])
+    o_, d_, l_ = O.gen_rays(t("in_xy"), t("in_R"), t("in_T"), t("in_Kinv"))
+    z = O.jitter_depths(O.coarse_depths(o_, n_s, 2.5, -3.5), t("jitter_u")).requires_grad_(True)
+    o_, d_, l_ = o_.clone().requires_grad_(True), d_, l_.clone().requires_grad_(True)
+    m_ = (d_ * l_).detach().requires_grad_(True)          # d*l as an independent leaf
+    o4, m4 = o_.unsqueeze(-1), m_.unsqueeze(-1)
+    pts = o4 + m4 * z[..., :-1].unsqueeze(1)
+    pe = O.posenc(pts)
+    gen = torch.Generator().manual_seed(5)
+    gw = torch.randn(pe.shape, generator=gen)
+    h = torch.randn(B, C, n_r, n_s, generator=gen).requires_grad_(True)
+    sraw = (torch.randn(B, 1, n_r, n_s, generator=gen) * 2).requires_grad_(True)
+    z_dists = (z[..., 1:] - z[..., :-1]).unsqueeze(1) * l_.unsqueeze(-1)
+    fr, ba, _, w = O.composite(torch.relu(h), torch.relu(sraw), z_dists, z[..., :-1].unsqueeze(1))
+    gfr, gba = torch.randn(fr.shape, generator=gen), torch.randn(ba.shape, generator=gen)
+    ((pe * gw).sum() + (fr * gfr).sum() + (ba * gba).sum()).backward()
+
+    ray_dl = torch.cat([d_.permute(0, 2, 1), l_.permute(0, 2, 1)], -1).detach().contiguous().to(dev)
+    tv = t("in_T").reshape(B, 3).contiguous().to(dev)
+    zd = z.detach().contiguous().to(dev)
+    pe_d = torch.empty(B, 63, P, device=dev)
+    _lib.check(L.gnrf_pe_fwd(ray_dl.data_ptr(), tv.data_ptr(), zd.data_ptr(), B, n_r, n_s, pe_d.data_ptr(), 0, S()))
+    assert rel_l2(pe_d.cpu().reshape(B, 63, n_r, n_s), pe.detach()) < 2e-5
+    g_m, g_o, g_l = (torch.zeros(B, n_r, 3, device=dev), torch.zeros(B, n_r, 3, device=dev), torch.zeros(B, n_r, device=dev))
+    g_z = torch.zeros(B, n_r, n_s + 1, device=dev)
+    gw_d = gw.reshape(B, 63, P).contiguous().to(dev)
+    half = (0.5 * gw_d).contiguous()
+    _lib.check(L.gnrf_pe_bwd(half.data_ptr(), 63 * P, half.data_ptr(), 63 * P, pe_d.data_ptr(), 63 * P, ray_dl.data_ptr(), zd.data_ptr(),
+                             B, n_r, n_s, g_m.data_ptr(), g_o.data_ptr(), g_z.data_ptr(), S()))
+    # composite (h is post-ReLU in the kernel's contract)
+    hr = torch.relu(h).detach().reshape(B, C, P).contiguous().to(dev)
+    sr = sraw.detach().reshape(B, P).contiguous().to(dev)
+    Hc, bga, wd = torch.empty(B, C + 1, n_r, device=dev), torch.empty(B, n_r, device=dev), torch.empty(B, n_r, n_s, device=dev)
+    _lib.check(L.gnrf_composite_cm_fwd(hr.data_ptr(), C * P, sr.data_ptr(), P, zd.data_ptr(), ray_dl.data_ptr(), B, n_r, n_s, C, Hc.data_ptr(),
+                                       bga.data_ptr(), wd.data_ptr(), S()))
+    assert rel_l2(Hc[:, :C].cpu(), fr.detach()) < 1e-5 and rel_l2(bga.cpu(), ba.detach()[:, 0]) < 1e-5
+    assert rel_l2(wd.cpu(), w.detach()[:, 0]) < 1e-5 and rel_l2(Hc[:, C].cpu(), 1 - ba.detach()[:, 0]) < 1e-5
+    g_Hc = torch.cat([gfr, torch.zeros(B, 1, n_r)], 1).contiguous().to(dev)
+    g_h, g_s = torch.empty(B, C, P, device=dev), torch.empty(B, P, device=dev)
+    _lib.check(L.gnrf_composite_cm_bwd(g_Hc.data_ptr(), gba[:, 0].contiguous().to(dev).data_ptr(), hr.data_ptr(), C * P, sr.data_ptr(), P,
+                                       wd.data_ptr(), zd.data_ptr(), ray_dl.data_ptr(), B, n_r, n_s, C, g_h.data_ptr(), C * P, g_s.data_ptr(), P,
+                                       g_z.data_ptr(), g_l.data_ptr(), S()))
+    torch.cuda.synchronize()
+    assert rel_l2(g_h.cpu().reshape(h.shape), h.grad) < 1e-4
+    assert rel_l2(g_s.cpu().reshape(sraw.shape), sraw.grad) < 1e-4
+    assert rel_l2(g_z.cpu(), z.grad) < 1e-4
+    assert rel_l2(g_l.cpu(), l_.grad[:, 0]) < 1e-4
+    assert rel_l2(g_m.cpu(), m_.grad.permute(0, 2, 1)) < 1e-4
+    assert rel_l2(g_o.cpu(), o_.grad.permute(0, 2, 1)) < 1e-4
+
+
+@gpu
+def test_compose_bwd(dev):
+    from gazenerf_b200 import _lib
+    L = _lib.lib()
+    B, C, s = 2, 48, 8
+    P = s * s
+    gen = torch.Generator().manual_seed(3)
+    ff, fe = (torch.randn(B, C, s, s, generator=gen).requires_grad_(True) for _ in range(2))
+    af, ae = (torch.rand(B, 1, s, s, generator=gen).requires_grad_(True) for _ in range(2))
+    bg = torch.randn(1, C, s, s, generator=gen).requires_grad_(True)
+    gaze = (torch.rand(B, 2, generator=gen) - 0.5).requires_grad_(True)
+    outs = O.compose_featmaps(ff, af, fe, ae, bg, gaze)
+    gs = [torch.randn(o.shape, generator=gen) for o in outs]
+    sum((o * g).sum() for o, g in zip(outs, gs)).backward()
+    d = lambda x: x.detach().contiguous().to(dev)
+    g_out = d(torch.stack(gs, 0))
+    g_ff, g_fe, g_af, g_ae = torch.empty(B, C, P, device=dev), torch.empty(B, C, P, device=dev), torch.empty(B, P, device=dev), torch.empty(B, P, device=dev)
+    g_bg = torch.empty(C, P, device=dev)
+    nblk = L.gnrf_compose_bwd_blocks(P)
+    part = torch.empty(B, nblk, 2, device=dev)
+    ins = [d(ff), d(af), d(fe), d(ae), d(bg), d(gaze)]
+    _lib.check(L.gnrf_compose_bwd(g_out.data_ptr(), *[x.data_ptr() for x in ins], B, C, P, g_ff.data_ptr(), g_af.data_ptr(), g_fe.data_ptr(),
+                                  g_ae.data_ptr(), g_bg.data_ptr(), part.data_ptr(), S()))
+    torch.cuda.synchronize()
+    assert rel_l2(g_ff.cpu().reshape(ff.shape), ff.grad) < 1e-5 and rel_l2(g_fe.cpu().reshape(fe.shape), fe.grad) < 1e-5
+    assert rel_l2(g_af.cpu().reshape(af.shape), af.grad) < 1e-5 and rel_l2(g_ae.cpu().reshape(ae.shape), ae.grad) < 1e-5
+    assert rel_l2(g_bg.cpu().reshape(bg.shape), bg.grad) < 1e-5
+    assert rel_l2(part.sum(1).cpu(), gaze.grad) < 1e-4
+
+
+@gpu
+@pytest.mark.parametrize("C,Ssz,nb,N", [(48, 8, 2, 3), (258, 8, 3, 2)])
+def test_neural_render_train_fwd_bwd(dev, C, Ssz, nb, N):
+    import gazenerf_b200 as G
+    from gazenerf_b200 import _lib
+    L = _lib.lib()
+    torch.manual_seed(11)
+    nr = G.NeuralRendererParams(feat_nc=C, featmap_size=Ssz, img_size=Ssz << nb)
+    sd = {"neural_render." + k: v.clone().requires_grad_(v.dtype.is_floating_point and not k.endswith(".f")) for k, v in nr.state_dict().items()}
+    x = torch.randn(N, C, Ssz, Ssz).requires_grad_(True)
+    ref = O.neural_render(sd, x, nb)
+    gi = torch.randn(ref.shape)
+    (ref * gi).sum().backward()
+    nr = nr.to(dev)
+    params = [p.detach() if p.dim() == 1 else p.detach().flatten(1) for p in nr.param_list()]
+    pa = _lib.ptr_array([p.data_ptr() for p in params])
+    P = Ssz << nb
+    xd, img = x.detach().to(dev), torch.empty(N, 3, P, P, device=dev)
+    sb = L.gnrf_nr_train_saved_bytes(N, C, Ssz, nb, 32)
+    saved = torch.empty(sb, dtype=torch.uint8, device=dev)
+    _lib.check(L.gnrf_nr_train_fwd(pa, nr.packed_tc().data_ptr(), xd.data_ptr(), N, C, Ssz, nb, 32, img.data_ptr(), saved.data_ptr(), sb, S()))
+    assert float((img.cpu() - ref.detach()).abs().max()) < 2e-5
+    wb = L.gnrf_nr_train_bwd_workspace_bytes(N, C, Ssz, nb, 32)
+    ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+    g_x = torch.empty_like(xd)
+    g_p = [torch.empty_like(p) for p in params]
+    gid = gi.to(dev)
+    _lib.check(L.gnrf_nr_train_bwd(pa, xd.data_ptr(), saved.data_ptr(), img.data_ptr(), gid.data_ptr(), N, C, Ssz, nb, 32, g_x.data_ptr(),
+                                   _lib.ptr_array([p.data_ptr() for p in g_p]), ws.data_ptr(), wb, S()))
+    torch.cuda.synchronize()
+    assert rel_l2(g_x.cpu(), x.grad) < 2e-4
+    names = [n for n, _ in nr.named_parameters() if n != "bg_featmap"]
+    by_ptr = {p.data_ptr(): n for n, p in nr.named_parameters()}
+    for p, gp_ in zip(nr.param_list(), g_p):
+        n = by_ptr[p.data_ptr()]
+        refg = sd["neural_render." + n].grad
+        assert rel_l2(gp_.cpu().reshape(refg.shape), refg) < 3e-4, n
+    assert len(names) == len(g_p)
+
+
+def _check_full_grads(dev, gname, ggname, mode):
+    import gazenerf_b200 as G
+    from test_gpu_parity import _net_from_golden
+    g, gg = load_golden(gname), load_golden(ggname)
+    opt, net = _net_from_golden(g, dev, "tc")
+    net.train()
+    t = lambda k: torch.from_numpy(g[k]).to(dev)
+    leaves = {"shape": t("in_shape").requires_grad_(True), "appea": t("in_appea").requires_grad_(True), "gaze": t("in_gaze").requires_grad_(True),
+              "R": t("in_R").requires_grad_(True), "T": t("in_T").requires_grad_(True)}
+    extra = {"jitter_u": t("jitter_u")} if mode == "train" else {}
+    if mode == "test":
+        for p in net.parameters():
+            assert p.requires_grad
+    out = net(mode, t("in_xy"), None, None, leaves["shape"], leaves["appea"], leaves["gaze"], leaves["R"], leaves["T"], t("in_Kinv"), **extra)
+    imgs = out["coarse_dict"]
+    for k in IMG_KEYS:
+        assert float((imgs[k].detach().cpu() - torch.from_numpy(g["img_" + k])).abs().max()) < 2e-4, k
+    wt = loss_weights({k: imgs[k].shape for k in IMG_KEYS})
+    loss = sum((imgs[k] * wt[k].to(dev)).sum() for k in IMG_KEYS)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(gg["loss"][0])) < 2e-4 * abs(float(gg["loss"][0]))
+    return net, leaves, gg
+
+
+@gpu
+def test_full_gradients_tiny_vs_reference(dev):
+    """hidden=32, featmap_nc=48: EVERY gradient tensor against the reference's own autograd."""
+    net, leaves, gg = _check_full_grads(dev, "tiny", "tiny_grad", "test")
+    for k in ("shape", "appea"):
+        assert rel_l2(leaves[k].grad.cpu(), gg["gin/" + k]) < TOL_GRAD, k
+    for k in ("gaze", "R", "T"):
+        assert rel_l2(leaves[k].grad.cpu(), gg["gin/" + k]) < TOL_GRAD_SMALL, k
+    errs = {}
+    for k, p in net.named_parameters():
+        ref = torch.from_numpy(gg["gp/" + k])
+        if float(ref.abs().max()) == 0.0:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        errs[k] = rel_l2(p.grad.cpu(), ref)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    print("worst parameter-gradient rel-L2:", worst)
+    assert worst[0][1] < TOL_GRAD, worst
+
+
+@gpu
+def test_full_gradients_std_train_vs_reference_and_oracle(dev):
+    """Real layer widths, train mode (jitter): input gradients vs the reference golden; every parameter gradient vs the reference's
+    summaries and, element-wise, vs autograd of the CPU oracle (itself pinned to the reference by the CPU tests above)."""
+    net, leaves, gg = _check_full_grads(dev, "std_dense_train", "std_dense_train_grad", "train")
+    for k in ("shape", "appea"):
+        assert rel_l2(leaves[k].grad.cpu(), gg["gin/" + k]) < TOL_GRAD, k
+    for k in ("gaze", "R", "T"):
+        assert rel_l2(leaves[k].grad.cpu(), gg["gin/" + k]) < TOL_GRAD_SMALL, k
+    g = load_golden("std_dense_train")
+    _, _, sd = _std_train_sd(g)
+    _, _, gp = oracle_grads(sd, _oo(g), "train", g, jitter_u=torch.from_numpy(g["jitter_u"]))
+    errs, nerr = {}, {}
+    for i, (k, p) in enumerate(net.named_parameters()):
+        ref = gp[k]
+        if float(ref.abs().max()) == 0.0:
+            continue
+        errs[k] = rel_l2(p.grad.cpu(), ref)
+        s = gg["gs/" + k]
+        nerr[k] = abs(float(p.grad.double().norm()) - s[2]) / s[2]
+    # single-scalar gradients (density_module.bias) are sums of ~1e3 signed terms that cancel to a few percent of their absolute
+    # sum, so their relative error is amplified accordingly: held to 2e-2, every multi-element tensor to TOL_GRAD
+    numel = {k: p.numel() for k, p in net.named_parameters()}
+    tol = lambda k: 2e-2 if numel[k] == 1 else TOL_GRAD
+    print("norm errors vs reference summaries:", sorted(nerr.items(), key=lambda kv: -kv[1])[:5])
+    assert all(v < tol(k) for k, v in nerr.items()), sorted(nerr.items(), key=lambda kv: -kv[1])[:5]
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    print("worst parameter-gradient rel-L2 vs oracle autograd:", worst)
+    assert all(v < tol(k) for k, v in errs.items()), worst
+
+
+@gpu
+def test_adam_step_refreshes_packed_weights(dev):
+    """One optimizer step through the drop-in module (trainer/gazenerf_trainer.py:520-528): loss decreases, caches refresh."""
+    import gazenerf_b200 as G
+    from test_gpu_parity import _net_from_golden
+    g = load_golden("std_dense_train")
+    opt, net = _net_from_golden(g, dev, "tc")
+    net.train()
+    t = lambda k: torch.from_numpy(g[k]).to(dev)
+    optim = torch.optim.Adam(net.parameters(), lr=1e-3)
+    target = torch.rand(2, 3, 64, 64, device=dev)
+    losses = []
+    for _ in range(3):
+        out = net("train", t("in_xy"), None, None, t("in_shape"), t("in_appea"), t("in_gaze"), t("in_R"), t("in_T"), t("in_Kinv"),
+                  jitter_u=t("jitter_u"))
+        loss = sum(((out["coarse_dict"][k] - target) ** 2).mean() for k in ("merge_img_face", "merge_img_eyes", "merge_img"))
+        optim.zero_grad()
+        loss.backward()
+        optim.step()
+        losses.append(float(loss))
+    assert losses[2] < losses[0], losses
