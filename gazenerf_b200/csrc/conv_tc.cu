@@ -5,15 +5,20 @@
 //
 // UMMA view: M = 128 pixels (TMEM lane = pixel), N = a chunk of <= 256 output channels, K = input channels.
 // Same bf16x3 split-precision scheme as the radiance MLP (x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, fp32 accumulate).
-// Warp-specialised, persistent (1 CTA / SM, 320 threads):
+// Warp-specialised, persistent (1 CTA / SM, 352 threads):
 //   warps 0-3  epilogue  : tcgen05.ld accumulators -> +bias, LeakyReLU (+ PSU residual, pixel-shuffle scatter) -> fp32 NCHW stores
 //                          (thread = pixel, so every store instruction writes 32 consecutive pixels of one channel: coalesced)
-//   warps 4-7  converters: read a [64 channels x 128 pixels] fp32 block of X (coalesced along pixels), split to bf16 hi/lo and
-//                          write the UMMA-canonical SWIZZLE_128B K-major A tile into a 3-stage smem ring
+//   warp 10    X loader  : ONE TMA tensor load (cp.async.bulk.tensor.3d over a [n_img][K][HW] tensor map, zero fill outside) per
+//                          [64 channels x 128 pixels] fp32 block of X into a 3-stage staging ring -- 96 KB in flight per SM, no
+//                          registers, no per-thread load latency
+//   warps 4-7  converters: read their pixel's 64 channel values from the staging block (conflict-free ld.shared), split to bf16
+//                          hi/lo and write the UMMA-canonical SWIZZLE_128B K-major A tile into a 2-stage smem ring
 //   warp  8    TMA       : streams the pre-arranged weight K-slices (W_hi then W_lo, no-swizzle core-matrix layout) with
-//                          cp.async.bulk + mbarrier complete_tx through a 6-stage ring
+//                          cp.async.bulk + mbarrier complete_tx through a 4-stage ring
 //   warp  9    MMA       : issues 3 UMMAs per K16 step into one of TWO 256-column TMEM accumulator buffers, so the epilogue of
 //                          work item i overlaps the MMAs of item i+1
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
+
 #include "common.cuh"
 #include "conv_tc.cuh"
 #include "tc_common.cuh"
@@ -22,14 +27,17 @@ namespace gnrf {
 namespace tc {
 
 constexpr int kCvTile = 128;
-constexpr int kCvAStages = 3, kCvAStageBytes = 32768;   // [hi 16 KB | lo 16 KB] of one K-block
-constexpr int kCvBStages = 6, kCvBStageBytes = 16384;   // [W_hi slice | W_lo slice], chunk_n x 32 B each
-constexpr int kCvThreads = 320;
+constexpr int kCvAStages = 2, kCvAStageBytes = 32768;   // [hi 16 KB | lo 16 KB] of one K-block
+constexpr int kCvBStages = 4, kCvBStageBytes = 16384;   // [W_hi slice | W_lo slice], chunk_n x 32 B each
+constexpr int kCvSStages = 3, kCvSStageBytes = 32768;   // fp32 staging: [64 channels][128 px]
+constexpr int kCvThreads = 352;
 constexpr int kCvSmemA = 0;
 constexpr int kCvSmemB = kCvAStages * kCvAStageBytes;
-constexpr int kCvSmemBars = kCvSmemB + kCvBStages * kCvBStageBytes;
+constexpr int kCvSmemS = kCvSmemB + kCvBStages * kCvBStageBytes;
+constexpr int kCvSmemBars = kCvSmemS + kCvSStages * kCvSStageBytes;
 constexpr int kCvBarAFull = 0, kCvBarAEmpty = kCvAStages, kCvBarBFull = 2 * kCvAStages, kCvBarBEmpty = kCvBarBFull + kCvBStages,
-              kCvBarAccFull = kCvBarBEmpty + kCvBStages, kCvBarAccEmpty = kCvBarAccFull + 2, kCvNumBars = kCvBarAccEmpty + 2;
+              kCvBarAccFull = kCvBarBEmpty + kCvBStages, kCvBarAccEmpty = kCvBarAccFull + 2, kCvBarSFull = kCvBarAccEmpty + 2,
+              kCvBarSEmpty = kCvBarSFull + kCvSStages, kCvNumBars = kCvBarSEmpty + kCvSStages;
 constexpr int kCvSmemMisc = kCvSmemBars + kCvNumBars * 8;
 constexpr int kCvSmemBytes = kCvSmemMisc + 64 + 1024;
 
@@ -43,6 +51,7 @@ struct ConvArgs {
   int K, N, HW, Wd, n_img;
   int chunk_n, n_chunks, k16_steps, n_kb;
   int tiles_per_img, n_items, mode;
+  int s_pitch, s_bytes;                     // staging row pitch (= TMA box width * 4) and box bytes
   // generic-GEMM extensions used by the training path (all optional; zero / null = the plain neural-renderer behaviour)
   long long x_img_stride, out_img_stride;   // elements between images of X / out (0 -> K*HW / N*HW)
   const float* bias_img;                    // [n_img][N] per-image bias added on top of the packed one (folded code columns)
@@ -52,7 +61,7 @@ struct ConvArgs {
 
 __device__ __forceinline__ float lrelu02(float v) { return v >= 0.0f ? v : 0.2f * v; }
 
-__global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const ConvArgs args) {
+__global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const ConvArgs args, const __grid_constant__ CUtensorMap x_map) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -65,6 +74,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const ConvArgs a
     for (int i = 0; i < kCvAStages; ++i) { mbar_init(bar(kCvBarAFull + i), 4); mbar_init(bar(kCvBarAEmpty + i), 1); }
     for (int i = 0; i < kCvBStages; ++i) { mbar_init(bar(kCvBarBFull + i), 1); mbar_init(bar(kCvBarBEmpty + i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar(kCvBarAccFull + i), 1); mbar_init(bar(kCvBarAccEmpty + i), 4); }
+    for (int i = 0; i < kCvSStages; ++i) { mbar_init(bar(kCvBarSFull + i), 1); mbar_init(bar(kCvBarSEmpty + i), 4); }
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc_512(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)));
@@ -100,39 +110,43 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const ConvArgs a
       const float* bias_c = args.bias + n0;               // zero padded to n_chunks * chunk_n
       const float* bias_i = args.bias_img ? args.bias_img + (size_t)img * args.N : nullptr;
       const size_t img_res = (size_t)img * args.Cres * args.HW + p;
+      // act(v) = max(v, v * act_slope): 0.2 = LeakyReLU, 0 = ReLU, 1 = linear (branch-free)
+      const float act_slope = (args.mode == CONV_EPI_LRELU || args.mode == CONV_EPI_PSU) ? 0.2f : (args.mode == CONV_EPI_RELU ? 0.0f : 1.0f);
+      const bool extras = args.mask != nullptr || args.add != nullptr;
       for (int c0 = 0; c0 < args.chunk_n; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(t_addr + c0, r);
         // batch every global load of this 32-column group before any store, so their latencies overlap
-        float bv[32], rv[32];
+        float bv[32], rv[32], av[32];
         const int ncols = min(32, args.chunk_n - c0);
+        const int nvalid = min(ncols, args.N - n0 - c0);   // columns of this group that exist in the output (may be <= 0)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) bv[j] = (j < ncols) ? __ldg(bias_c + c0 + j) : 0.0f;
+        for (int q = 0; q < 8; ++q) {   // the packed bias is zero padded 32 floats past the last chunk: unpredicated vector loads
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_c + c0) + q);
+          bv[4 * q] = b4.x; bv[4 * q + 1] = b4.y; bv[4 * q + 2] = b4.z; bv[4 * q + 3] = b4.w;
+        }
         if (bias_i != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (j < ncols && n0 + c0 + j < args.N) bv[j] += __ldg(bias_i + n0 + c0 + j);
+            if (j < nvalid) bv[j] += __ldg(bias_i + n0 + c0 + j);
         }
-        float av[32];
-        if (args.mode != CONV_EPI_PSU && (args.mask != nullptr || args.add != nullptr)) {
-          const float* mk = args.mask ? args.mask + (size_t)img * args.mask_img_stride + (size_t)(n0 + c0) * args.HW + p : nullptr;
-          const float* ad = args.add ? args.add + (size_t)img * args.add_img_stride + (size_t)(n0 + c0) * args.HW + p : nullptr;
+        if (args.mode != CONV_EPI_PSU) {
+          if (extras) {
+            // raw mask / add values are only LOADED here (independent loads issue back to back); they are consumed after the wait
+            const float* mk = args.mask ? args.mask + (size_t)img * args.mask_img_stride + (size_t)(n0 + c0) * args.HW + p : nullptr;
+            const float* ad = args.add ? args.add + (size_t)img * args.add_img_stride + (size_t)(n0 + c0) * args.HW + p : nullptr;
+            const int m_lim = (mk != nullptr && p_ok) ? min(nvalid, args.mask_rows - n0 - c0) : 0;
+            const int a_lim = (ad != nullptr && p_ok) ? min(nvalid, args.add_rows - n0 - c0) : 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c0 + j;
-            const bool ok = p_ok && j < ncols && n < args.N;
-            rv[j] = (ok && mk != nullptr && n < args.mask_rows) ? (__ldg(mk + (size_t)j * args.HW) > 0.0f ? 1.0f : args.mask_slope) : 1.0f;
-            av[j] = (ok && ad != nullptr && n < args.add_rows) ? __ldg(ad + (size_t)j * args.HW) : 0.0f;
+            for (int j = 0; j < 32; ++j) rv[j] = j < m_lim ? __ldg(mk + (size_t)j * args.HW) : 1.0f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) av[j] = j < a_lim ? __ldg(ad + (size_t)j * args.HW) : 0.0f;
           }
         } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { av[j] = 0.0f; if (args.mode != CONV_EPI_PSU) rv[j] = 1.0f; }
-        }
-        if (args.mode == CONV_EPI_PSU) {
           int cm = (n0 + c0) % args.Cres;   // (n % Cres), advanced incrementally
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            rv[j] = (p_ok && j < ncols && n0 + c0 + j < args.N) ? __ldg(args.res + img_res + (size_t)cm * args.HW) : 0.0f;
+            rv[j] = (p_ok && j < nvalid) ? __ldg(args.res + img_res + (size_t)cm * args.HW) : 0.0f;
             if (++cm == args.Cres) cm = 0;
           }
         }
@@ -142,17 +156,40 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const ConvArgs a
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(kCvBarAccEmpty + buf));
         }
-        if (!p_ok) continue;
+        if (!p_ok || nvalid <= 0) continue;
         if (args.mode != CONV_EPI_PSU) {
           float* o = args.out + (size_t)img * args.out_img_stride + (size_t)(n0 + c0) * args.HW + p;
-          const int mode = args.mode;
+          const size_t hw = (size_t)args.HW;
+          if (!extras) {
+            if (nvalid == 32) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncols && n0 + c0 + j < args.N) {
-              float v = __uint_as_float(r[j]) + bv[j];
-              v = mode == CONV_EPI_LRELU ? lrelu02(v) : (mode == CONV_EPI_RELU ? fmaxf(v, 0.0f) : v);
-              o[(size_t)j * args.HW] = fmaf(v, rv[j], av[j]);
+              for (int j = 0; j < 32; ++j) {
+                const float v = __uint_as_float(r[j]) + bv[j];
+                *o = fmaxf(v, v * act_slope);
+                o += hw;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (j < nvalid) {
+                  const float v = __uint_as_float(r[j]) + bv[j];
+                  *o = fmaxf(v, v * act_slope);
+                }
+                o += hw;
+              }
             }
+          } else {
+            const float ms = args.mask_slope;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < nvalid) {
+                float v = __uint_as_float(r[j]) + bv[j];
+                v = fmaxf(v, v * act_slope);
+                *o = fmaf(v, rv[j] > 0.0f ? 1.0f : ms, av[j]);
+              }
+              o += hw;
+            }
+          }
         } else {
           // + x.repeat(1,4,1,1), then pixel_shuffle(2): out[c][2h+i][2w+j] = in[4c+2i+j][h][w]  (pixel_shuffle_upsample.py:34-40)
           // n0 + c0 is a multiple of 16, so the 32 columns are 8 complete groups of 4 = (si, sj) in {0,1}^2 of channel c.
@@ -160,36 +197,42 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const ConvArgs a
           float* o = args.out + ((size_t)img * (args.N >> 2) + ((n0 + c0) >> 2)) * plane + (size_t)(2 * h) * (2 * args.Wd) + 2 * w;
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            if (4 * g < ncols && n0 + c0 + 4 * g < args.N) {
+            if (4 * g < nvalid) {
               float v0 = lrelu02(__uint_as_float(r[4 * g + 0]) + bv[4 * g + 0]) + rv[4 * g + 0];
               float v1 = lrelu02(__uint_as_float(r[4 * g + 1]) + bv[4 * g + 1]) + rv[4 * g + 1];
               float v2 = lrelu02(__uint_as_float(r[4 * g + 2]) + bv[4 * g + 2]) + rv[4 * g + 2];
               float v3 = lrelu02(__uint_as_float(r[4 * g + 3]) + bv[4 * g + 3]) + rv[4 * g + 3];
-              float* og = o + (size_t)g * plane;
-              *reinterpret_cast<float2*>(og) = make_float2(v0, v1);                       // row 2h,   cols 2w, 2w+1
-              *reinterpret_cast<float2*>(og + 2 * args.Wd) = make_float2(v2, v3);         // row 2h+1
+              *reinterpret_cast<float2*>(o) = make_float2(v0, v1);                       // row 2h,   cols 2w, 2w+1
+              *reinterpret_cast<float2*>(o + 2 * args.Wd) = make_float2(v2, v3);         // row 2h+1
             }
+            o += plane;
           }
         }
       }
     }
   } else if (warp < 8) {
-    // ======================================= converters: fp32 NCHW -> bf16 hi/lo SW128 A tiles =======================================
+    // ======================================= converters: staged fp32 [channel][pixel] -> bf16 hi/lo SW128 A tiles =================
     const int row = (warp - 4) * 32 + lane;
-    uint32_t slot = 0, phase = 0;
+    uint32_t slot = 0, phase = 0, ss = 0, sphase = 0;
     for (int item = blockIdx.x; item < args.n_items; item += gridDim.x) {
       int img, tile, chunk;
       decode(item, img, tile, chunk);
       const int p = tile * kCvTile + row;
       const bool p_ok = p < args.HW;
-      const float* xp = args.X + (size_t)img * args.x_img_stride + p;
       for (int kb = 0; kb < args.n_kb; ++kb) {
+        mbar_wait(bar(kCvBarSFull + ss), sphase);
+        const uint32_t s_addr = smem_base + kCvSmemS + ss * kCvSStageBytes + (uint32_t)row * 4u;
+        const int nch = min(64, args.K - kb * 64);
         float v[64];
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
-          const int c = kb * 64 + j;
-          v[j] = (p_ok && c < args.K) ? __ldg(xp + (size_t)c * args.HW) : 0.0f;
+          float t;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(s_addr + (uint32_t)(j * args.s_pitch)));
+          v[j] = (p_ok && j < nch) ? t : 0.0f;   // rows beyond the TMA box hold stale data (inside the box TMA zero-fills)
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(kCvBarSEmpty + ss));
+        if (++ss == kCvSStages) { ss = 0; sphase ^= 1; }
         uint32_t hi[32], lo[32];
         split_row64(v, hi, lo);
         mbar_wait(bar(kCvBarAEmpty + slot), phase ^ 1);
@@ -202,6 +245,28 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const ConvArgs a
         if (++slot == kCvAStages) { slot = 0; phase ^= 1; }
       }
     }
+  } else if (warp == 10) {
+    // ======================================= X loader: one TMA tensor load per K-block ===========================================
+    if (lane == 0) {
+      uint32_t ss = 0, sphase = 0;
+      const uint64_t map_ptr = reinterpret_cast<uint64_t>(&x_map);
+      for (int item = blockIdx.x; item < args.n_items; item += gridDim.x) {
+        int img, tile, chunk;
+        decode(item, img, tile, chunk);
+        const int p0 = tile * kCvTile;
+        for (int kb = 0; kb < args.n_kb; ++kb) {
+          mbar_wait(bar(kCvBarSEmpty + ss), sphase ^ 1);
+          mbar_arrive_expect_tx(bar(kCvBarSFull + ss), (uint32_t)args.s_bytes);
+          asm volatile(
+              "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                  smem_base + kCvSmemS + ss * kCvSStageBytes),
+              "l"(map_ptr), "r"(p0), "r"(kb * 64), "r"(img), "r"(bar(kCvBarSFull + ss))
+              : "memory");
+          if (++ss == kCvSStages) { ss = 0; sphase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
   } else if (warp == 8) {
     // ======================================= TMA producer (weights) =======================================
     if (lane == 0) {
@@ -220,7 +285,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const ConvArgs a
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp == 9) {
     // ======================================= MMA issuer (converged warp, one elected lane issues) =======================================
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -306,7 +371,7 @@ __global__ void conv_pack_kernel(const float* __restrict__ W, long long sn, long
     }
     *reinterpret_cast<uint4*>(stream + c * 16) = make_uint4(out[0], out[1], out[2], out[3]);
   }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_chunks * chunk_n; i += gridDim.x * blockDim.x)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_chunks * chunk_n + 32; i += gridDim.x * blockDim.x)
     bias_out[i] = (i < N && b != nullptr) ? b[i] : 0.0f;
 }
 
@@ -320,7 +385,7 @@ ConvLayerPlan conv_layer_plan(int N, int K) {
   pl.k16_steps = (K + 15) / 16;
   pl.n_kb = (K + 63) / 64;
   pl.stream_bytes = (size_t)pl.n_chunks * pl.k16_steps * 2 * pl.chunk_n * 32;
-  pl.bias_floats = (size_t)pl.n_chunks * pl.chunk_n;
+  pl.bias_floats = (size_t)pl.n_chunks * pl.chunk_n + 32;   // + 32: the epilogue reads whole 32-float groups
   pl.total_bytes = ((pl.stream_bytes + pl.bias_floats * sizeof(float)) + 255) & ~(size_t)255;
   return pl;
 }
@@ -337,6 +402,21 @@ int conv_tc_pack_strided(const ConvLayerPlan& pl, const float* W, long long sn, 
   if (e != cudaSuccess) return fail(GNRF_ERR_CUDA, "conv_tc_pack: %s", cudaGetErrorString(e));
   count_launches(1);
   return GNRF_OK;
+}
+
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TensorMapEncodeFn>(p);
+  }
+  return fn;
 }
 
 int conv_tc_launch(const ConvLayerPlan& pl, const unsigned char* packed, const float* X, float* out, const float* res, int Cres,
@@ -366,6 +446,8 @@ int conv_tc_launch_ex(const ConvLayerPlan& pl, const unsigned char* packed, cons
   a.tiles_per_img = (HW + kCvTile - 1) / kCvTile;
   a.n_items = n_img * a.tiles_per_img * pl.n_chunks;
   a.mode = mode;
+  if (HW % 4 != 0 || (ex.x_img_stride % 4) != 0 || (reinterpret_cast<uintptr_t>(X) & 15) != 0)
+    return fail(GNRF_ERR_ARG, "conv_tc_launch: X must be 16-byte aligned with HW and the image stride multiples of 4 floats (TMA rows)");
   a.x_img_stride = ex.x_img_stride > 0 ? ex.x_img_stride : (long long)pl.K * HW;
   a.out_img_stride = ex.out_img_stride > 0 ? ex.out_img_stride : (long long)pl.N * HW;
   a.bias_img = ex.bias_img;
@@ -373,8 +455,21 @@ int conv_tc_launch_ex(const ConvLayerPlan& pl, const unsigned char* packed, cons
   a.mask_rows = ex.mask_rows > 0 ? ex.mask_rows : pl.N; a.mask_slope = ex.mask_slope;
   a.add = ex.add; a.add_img_stride = ex.add_img_stride > 0 ? ex.add_img_stride : (long long)pl.N * HW;
   a.add_rows = ex.add_rows > 0 ? ex.add_rows : pl.N;
+  // fp32 tensor [n_img][K][HW] (strides in bytes), box = [1][<=64 channels][<=128 px]; out-of-range elements are zero-filled
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  if (enc == nullptr) return fail(GNRF_ERR_CUDA, "conv_tc_launch: cuTensorMapEncodeTiled is not available from the driver");
+  CUtensorMap x_map;
+  const cuuint64_t gdim[3] = {(cuuint64_t)HW, (cuuint64_t)pl.K, (cuuint64_t)n_img};
+  const cuuint64_t gstr[2] = {(cuuint64_t)HW * 4, (cuuint64_t)a.x_img_stride * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)(HW < kCvTile ? HW : kCvTile), (cuuint32_t)(pl.K < 64 ? pl.K : 64), 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult cr = enc(&x_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(X), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(GNRF_ERR_CUDA, "conv_tc_launch: cuTensorMapEncodeTiled failed (%d) for HW=%d K=%d n_img=%d", (int)cr, HW, pl.K, n_img);
+  a.s_pitch = (int)box[0] * 4;
+  a.s_bytes = (int)(box[0] * box[1]) * 4;
   int grid = a.n_items < n_sm ? a.n_items : n_sm;
-  conv_tc_kernel<<<grid, kCvThreads, kCvSmemBytes, st>>>(a);
+  conv_tc_kernel<<<grid, kCvThreads, kCvSmemBytes, st>>>(a, x_map);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(GNRF_ERR_CUDA, "conv_tc_launch: %s", cudaGetErrorString(e));
   count_launches(1);
