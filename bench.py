@@ -2,6 +2,7 @@
 """bench.py -- faces/s of the GazeNeRF render hot path (BASELINE.json metric) on N B200s of one node.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mlp-impl tc|simt] [--faces-per-gpu F]
+    python bench.py --workload train [--faces-per-gpu 2]      # BASELINE config[4]: full train step (not the default line)
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 A "step" is one full drop-in forward("test") -- rays -> both radiance MLPs (fused tcgen05 kernel) -> composite ->
@@ -142,6 +143,138 @@ def cpu_baseline(torch, G, steps, warmup, ray_step=16):
             "s_per_face": t_face}
 
 
+# ------------------------------------------------------------------------------------------------ train step (BASELINE config[4])
+def synthetic_targets(torch, faces, size, seed, device="cpu"):
+    """gt ~ U(0,1); head rectangle + two eye rectangles as masks."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    gt = torch.rand(faces, 3, size, size, generator=g)
+    head = torch.zeros(faces, 1, size, size)
+    head[:, :, size // 8: size - size // 8, size // 6: size - size // 6] = 1.0
+    le, re = torch.zeros_like(head), torch.zeros_like(head)
+    le[:, :, size * 3 // 8: size * 7 // 16, size * 5 // 16: size * 7 // 16] = 1.0
+    re[:, :, size * 3 // 8: size * 7 // 16, size * 9 // 16: size * 11 // 16] = 1.0
+    return {"gt": gt, "head": head, "left_eye": le, "right_eye": re}
+
+
+def data_loss(torch, pred, tg, bg_value=1.0):
+    """GazeNeRFLoss.calc_total_loss data terms (losses/gazenerf_loss.py:294-352, 420-434; use_l1_loss=True, use_vgg_loss=False):
+    l1_loss(a[mask], b[mask]) == sum(mask |a - b|) / sum(mask), written with mask weights so nothing syncs with the host."""
+    eyes_any = ((tg["left_eye"] >= 0.5) | (tg["right_eye"] >= 0.5)).float()
+    head_in = (tg["head"] >= 0.5).float()
+    head_m = head_in * (1.0 - eyes_any)          # full_eye_mask == union of the two eye masks in the synthetic setup
+    face_m = head_m
+    nonhead_m = 1.0 - head_in
+
+    def l1(a, m):
+        return ((a - tg["gt"]).abs() * m).sum() / (3.0 * m.sum()).clamp_min(1.0)
+
+    bg = ((pred["bg_img"] - bg_value) ** 2).mean()
+    nonhead = (((pred["merge_img"] - bg_value) ** 2) * nonhead_m).sum() / (3.0 * nonhead_m.sum()).clamp_min(1.0)
+    return bg + l1(pred["merge_img"], head_m) + l1(pred["merge_img_eyes"], eyes_any) + l1(pred["merge_img_face"], face_m) + nonhead
+
+
+def run_train(args, torch, G, rank, local_rank, world, dev, dist):
+    L = G.lib()
+    F = args.faces_per_gpu
+    opt = G.BaseOptions()
+    torch.manual_seed(45)
+    net = G.GazeNeRFNet(opt, include_vd=False, hier_sampling=False).to(dev).train()
+    optim = torch.optim.Adam(net.parameters(), lr=1e-4)   # README.md:30 of the reference
+    params = [p for p in net.parameters()]
+    host_kw = synthetic_inputs(torch, G, opt, F, seed=rank)
+    host_tg = synthetic_targets(torch, F, opt.pred_img_size, seed=rank)
+    pin = lambda d: {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in d.items()}
+    todev = lambda d: {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in d.items()}
+    pinned_kw, pinned_tg = pin(host_kw), pin(host_tg)
+    dev_kw, dev_tg = todev(host_kw), todev(host_tg)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step(kw, tg):
+        pred = net("train", **kw)["coarse_dict"]
+        loss = data_loss(torch, pred, tg)
+        optim.zero_grad(set_to_none=True)
+        loss.backward()
+        if world > 1:   # data-parallel: one flat all-reduce of the 20 MB of gradients
+            flat = torch._utils._flatten_dense_tensors([p.grad for p in params])
+            dist.all_reduce(flat)
+            flat /= world
+            for p, gsync in zip(params, torch._utils._unflatten_dense_tensors(flat, [p.grad for p in params])):
+                p.grad.copy_(gsync)
+        optim.step()
+        return loss.detach()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(dev_kw, dev_tg)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = L.gnrf_launch_count()
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        step(dev_kw, dev_tg)
+        ev[i][1].record()
+    barrier()
+    launches = (L.gnrf_launch_count() - launches0) // max(args.steps, 1)
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+
+    h2d = sum(v.numel() * v.element_size() for d in (pinned_kw, pinned_tg) for v in d.values() if torch.is_tensor(v))
+
+    def e2e_step():
+        loss = step(todev(pinned_kw), todev(pinned_tg))
+        loss_host.copy_(loss, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+    if rank == 0:
+        peaks = measured_peaks()
+        faces_total = world * F * args.steps
+        step_s = total_ms * 1e-3 / args.steps
+        # forward + input-gradient + weight-gradient GEMMs of both MLPs = 3 x the forward's algorithmic FLOPs (SURVEY §8d)
+        algo_flop = 3 * 2 * F * N_RAYS * N_SAMPLES * MLP_FLOP_PER_POINT_PER_BRANCH
+        achieved = algo_flop / step_s / 1e12
+        peak = peaks["bf16_sustained"]
+        line = {
+            "metric": "train faces/s (512x512, 64 samp/ray; forward + loss + backward + Adam)", "value": faces_total / (total_ms * 1e-3),
+            "unit": "faces/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 split (fp32 accumulate) on tensor cores for every GEMM (forward, dX, dW); f32 elsewhere", "data": "synthetic",
+            "config": {"workload": "config[4]: full train step, two-branch render + neural renderer + GazeNeRFLoss data terms + backward + Adam",
+                       "faces_per_gpu_per_step": F, "rays": N_RAYS, "samples_per_ray": N_SAMPLES, "l2": "256 MiB memset between timed steps (untimed)",
+                       "multi_gpu": "data parallel, one flat gradient all-reduce per step" if world > 1 else "single GPU",
+                       "precision_note": "config[4] allows bf16; this path keeps the bf16x3 split so gradients match fp32 autograd to 5e-3"},
+            "roofline": {"bound": "tensor", "kernel": "whole step (conv_tc_kernel forward/dX + wgrad_tc_kernel dW dominate)", "achieved": achieved,
+                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": "%s bf16 dense, sustained" % peaks["src"],
+                         "traffic": None, "algorithmic_flop_per_step": algo_flop,
+                         "note": "MLP GEMM FLOPs as written in the reference, x3 for forward + both gradients; step time, not kernel time"},
+            "e2e": {"value": faces_total / e2e_s, "unit": "faces/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -152,7 +285,10 @@ def main():
     ap.add_argument("--mlp-impl", default="tc", choices=["tc", "simt"])
     ap.add_argument("--faces-per-gpu", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="render", choices=["render", "train"])
     args = ap.parse_args()
+    if args.workload == "train" and args.faces_per_gpu == 1:
+        args.faces_per_gpu = 2   # config[4]: batch = 2
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     import torch
@@ -184,6 +320,12 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     from gazenerf_b200.dist import all_gather_images
+
+    if args.workload == "train":
+        run_train(args, torch, G, rank, local_rank, world, dev, dist if world > 1 else None)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     L = G.lib()
     F = args.faces_per_gpu

@@ -28,6 +28,7 @@ constexpr int kWgBBytes = 65536;                 // [hi 32 KB | lo 32 KB], <= 25
 constexpr int kWgStageBytes = kWgABytes + kWgBBytes;
 constexpr int kWgThreads = 288;
 constexpr int kWgConvWarps = 8;
+constexpr int kWgMaxIter = (128 + 256) / 2 / kWgConvWarps;   // row pairs per converter warp and K-block
 constexpr int kWgBarFull = 0, kWgBarEmpty = kWgStages, kWgBarAccFull = 2 * kWgStages, kWgBarAccEmpty = kWgBarAccFull + 1,
               kWgNumBars = kWgBarAccEmpty + 1;
 constexpr int kWgSmemBars = kWgStages * kWgStageBytes;
@@ -88,40 +89,40 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradArgs
       const float* dy_img = args.dY + (size_t)img * args.dy_img_stride;
       const float* x_img = args.X + (size_t)img * args.x_img_stride;
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(bar(kWgBarEmpty + slot), phase ^ 1);
         const int p = kb * 64 + l16 * 4;
         const bool p_ok = p < args.HW;
-        const uint32_t stage = smem_base + slot * kWgStageBytes;
-        for (int i0 = 0; i0 < n_iter; i0 += 8) {
-          float4 v[8];
+        // issue EVERY load of this K-block (<= 24 x 16 B per lane, ~96 KB per CTA in flight) before touching shared memory: the
+        // loads do not depend on the ring, only the stores below wait for the stage to be released by the MMA warp
+        float4 v[kWgMaxIter];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int row = ((i0 + u) * kWgConvWarps + warp) * 2 + half;
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i0 + u < n_iter && p_ok) {
-              if (row < 128) {
-                if (m0 + row < args.N_dy) v[u] = __ldg(reinterpret_cast<const float4*>(dy_img + (size_t)(m0 + row) * args.HW + p));
-              } else {
-                const int n = n0 + row - 128;
-                if (n < args.K_x) v[u] = __ldg(reinterpret_cast<const float4*>(x_img + (size_t)n * args.HW + p));
-                else if (n < args.rows_x) v[u] = make_float4(1.f, 1.f, 1.f, 1.f);   // the ones row -> bias gradient column
-              }
+        for (int u = 0; u < kWgMaxIter; ++u) {
+          const int row = (u * kWgConvWarps + warp) * 2 + half;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (u < n_iter && p_ok) {
+            if (row < 128) {
+              if (m0 + row < args.N_dy) v[u] = __ldg(reinterpret_cast<const float4*>(dy_img + (size_t)(m0 + row) * args.HW + p));
+            } else {
+              const int n = n0 + row - 128;
+              if (n < args.K_x) v[u] = __ldg(reinterpret_cast<const float4*>(x_img + (size_t)n * args.HW + p));
+              else if (n < args.rows_x) v[u] = make_float4(1.f, 1.f, 1.f, 1.f);   // the ones row -> bias gradient column
             }
           }
+        }
+        mbar_wait(bar(kWgBarEmpty + slot), phase ^ 1);
+        const uint32_t stage = smem_base + slot * kWgStageBytes;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int row = ((i0 + u) * kWgConvWarps + warp) * 2 + half;
-            if (i0 + u < n_iter && row < 128 + args.chunk_n) {
-              uint32_t h0, l0, h1, l1;
-              split2(v[u].x, v[u].y, h0, l0);
-              split2(v[u].z, v[u].w, h1, l1);
-              const int r = row < 128 ? row : row - 128;
-              const uint32_t base = stage + (row < 128 ? 0u : (uint32_t)kWgABytes) + a_row_offset(r) +
-                                    ((((uint32_t)l16 >> 1) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)l16 & 1u) * 8u;
-              const uint32_t lo_off = row < 128 ? 16384u : 32768u;
-              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(base), "r"(h0), "r"(h1) : "memory");
-              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(base + lo_off), "r"(l0), "r"(l1) : "memory");
-            }
+        for (int u = 0; u < kWgMaxIter; ++u) {
+          const int row = (u * kWgConvWarps + warp) * 2 + half;
+          if (u < n_iter && row < 128 + args.chunk_n) {
+            uint32_t h0, l0, h1, l1;
+            split2(v[u].x, v[u].y, h0, l0);
+            split2(v[u].z, v[u].w, h1, l1);
+            const int r = row < 128 ? row : row - 128;
+            const uint32_t base = stage + (row < 128 ? 0u : (uint32_t)kWgABytes) + a_row_offset(r) +
+                                  ((((uint32_t)l16 >> 1) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)l16 & 1u) * 8u;
+            const uint32_t lo_off = row < 128 ? 16384u : 32768u;
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(base), "r"(h0), "r"(h1) : "memory");
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(base + lo_off), "r"(l0), "r"(l1) : "memory");
           }
         }
         fence_proxy_async_smem();

@@ -19,6 +19,26 @@ KEYS = [
 ]
 
 
+def launches_between(path, marker="ray_setup", which=-2):
+    """Launch list of one step of a multi-step run: the launches between two consecutive `marker` kernels."""
+    lines = [l for l in open(path) if not l.startswith("==")]
+    rows = [r for r in csv.DictReader(lines) if r.get("Metric Name") == "gpu__time_duration.sum"]
+    names = [(r["Kernel Name"], float(r["Metric Value"].replace(",", ""))) for r in rows]
+    starts = [i for i, (n, _) in enumerate(names) if marker in n]
+    step = names[starts[which]:starts[which + 1]] if len(starts) >= 2 and which + 1 != 0 else names[starts[-1]:]
+    tot = sum(t for _, t in step)
+    agg = collections.OrderedDict()
+    for n, t in step:
+        k = n.split("(")[0]
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += t
+    print("| kernel | launches | time (us) | share |\n|---|---:|---:|---:|")
+    for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print("| `%s` | %d | %.1f | %.1f %% |" % (k[:90], c, t / 1e3, 100 * t / tot))
+    print("| **total** | %d | %.1f | 100 %% |" % (len(step), tot / 1e3))
+
+
 def launches(path):
     lines = [l for l in open(path) if not l.startswith("==")]
     rows = [r for r in csv.DictReader(lines) if r.get("Metric Name") == "gpu__time_duration.sum"]
@@ -55,6 +75,10 @@ def kernel(rep, label):
                 print("| %s | %s | %s |" % (k, d[k], u[k]))
         print()
 
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "train_launches":
+    launches_between(sys.argv[2])
+    sys.exit(0)
 
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
