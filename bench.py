@@ -153,24 +153,7 @@ def synthetic_targets(torch, faces, size, seed, device="cpu"):
     le, re = torch.zeros_like(head), torch.zeros_like(head)
     le[:, :, size * 3 // 8: size * 7 // 16, size * 5 // 16: size * 7 // 16] = 1.0
     re[:, :, size * 3 // 8: size * 7 // 16, size * 9 // 16: size * 11 // 16] = 1.0
-    return {"gt": gt, "head": head, "left_eye": le, "right_eye": re}
-
-
-def data_loss(torch, pred, tg, bg_value=1.0):
-    """GazeNeRFLoss.calc_total_loss data terms (losses/gazenerf_loss.py:294-352, 420-434; use_l1_loss=True, use_vgg_loss=False):
-    l1_loss(a[mask], b[mask]) == sum(mask |a - b|) / sum(mask), written with mask weights so nothing syncs with the host."""
-    eyes_any = ((tg["left_eye"] >= 0.5) | (tg["right_eye"] >= 0.5)).float()
-    head_in = (tg["head"] >= 0.5).float()
-    head_m = head_in * (1.0 - eyes_any)          # full_eye_mask == union of the two eye masks in the synthetic setup
-    face_m = head_m
-    nonhead_m = 1.0 - head_in
-
-    def l1(a, m):
-        return ((a - tg["gt"]).abs() * m).sum() / (3.0 * m.sum()).clamp_min(1.0)
-
-    bg = ((pred["bg_img"] - bg_value) ** 2).mean()
-    nonhead = (((pred["merge_img"] - bg_value) ** 2) * nonhead_m).sum() / (3.0 * nonhead_m.sum()).clamp_min(1.0)
-    return bg + l1(pred["merge_img"], head_m) + l1(pred["merge_img_eyes"], eyes_any) + l1(pred["merge_img_face"], face_m) + nonhead
+    return {"gt": gt, "head": head, "left_eye": le, "right_eye": re, "full_eye": ((le + re) > 0).float()}
 
 
 def run_train(args, torch, G, rank, local_rank, world, dev, dist):
@@ -178,9 +161,19 @@ def run_train(args, torch, G, rank, local_rank, world, dev, dist):
     F = args.faces_per_gpu
     opt = G.BaseOptions()
     torch.manual_seed(45)
+    from gazenerf_b200.trainer_utils import build_code_and_cam
+
     net = G.GazeNeRFNet(opt, include_vd=False, hier_sampling=False).to(dev).train()
-    optim = torch.optim.Adam(net.parameters(), lr=1e-4)   # README.md:30 of the reference
-    params = [p for p in net.parameters()]
+    # the reference's fitting step (trainer/gazenerf_trainer.py:338-528): learnable code offsets + camera deltas next to the network
+    off = {"iden": torch.zeros(F, 100, device=dev, requires_grad=True), "expr": torch.zeros(F, 79, device=dev, requires_grad=True),
+           "appea": torch.zeros(F, 127, device=dev, requires_grad=True)}
+    d_eul = torch.zeros(F, 3, device=dev, requires_grad=True)
+    d_tv = torch.zeros(F, 3, 1, device=dev, requires_grad=True)
+    lr = 1e-4   # README.md:30 of the reference
+    optim = torch.optim.Adam([{"params": list(net.parameters()), "lr": lr}, {"params": list(off.values()), "lr": lr * 1.5},
+                              {"params": [d_eul, d_tv], "lr": lr * 0.1}])
+    params = [p for p in net.parameters()] + list(off.values()) + [d_eul, d_tv]
+    loss_fn = G.GazeNeRFLoss(eye_loss_importance=1.0, vgg_importance=1.0, use_vgg_loss=False, use_l1_loss=True)
     host_kw = synthetic_inputs(torch, G, opt, F, seed=rank)
     host_tg = synthetic_targets(torch, F, opt.pred_img_size, seed=rank)
     pin = lambda d: {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in d.items()}
@@ -191,8 +184,13 @@ def run_train(args, torch, G, rank, local_rank, world, dev, dist):
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
     def step(kw, tg):
-        pred = net("train", **kw)["coarse_dict"]
-        loss = data_loss(torch, pred, tg)
+        base = {"iden": kw["shape_code"][:, :100], "expr": kw["shape_code"][:, 100:], "text": kw["appea_code"][:, :100],
+                "illu": kw["appea_code"][:, 100:], "gaze": kw["gaze_code"]}
+        cam = {k: kw[k] for k in ("batch_Rmats", "batch_Tvecs", "batch_inv_inmats")}
+        code_info, opt_code, cam_info, delta_cam = build_code_and_cam(base, off, cam, 0, F, d_eul, d_tv)
+        pred = net("train", kw["batch_xy"], None, **code_info, **cam_info)
+        loss = loss_fn.calc_total_loss(delta_cam, opt_code, pred, tg["gt"], tg["head"], tg["full_eye"], tg["left_eye"], tg["right_eye"],
+                                       None, None, 0, 0)["total_loss"]
         optim.zero_grad(set_to_none=True)
         loss.backward()
         if world > 1:   # data-parallel: one flat all-reduce of the 20 MB of gradients
@@ -261,7 +259,7 @@ def run_train(args, torch, G, rank, local_rank, world, dev, dist):
             "unit": "faces/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3 split (fp32 accumulate) on tensor cores for every GEMM (forward, dX, dW); f32 elsewhere", "data": "synthetic",
-            "config": {"workload": "config[4]: full train step, two-branch render + neural renderer + GazeNeRFLoss data terms + backward + Adam",
+            "config": {"workload": "config[4]: full train step (trainer perform_fitting): build_code_and_cam -> two-branch render + neural renderer -> GazeNeRFLoss (l1, no VGG) -> backward to weights, code offsets, camera deltas -> Adam",
                        "faces_per_gpu_per_step": F, "rays": N_RAYS, "samples_per_ray": N_SAMPLES, "l2": "256 MiB memset between timed steps (untimed)",
                        "multi_gpu": "data parallel, one flat gradient all-reduce per step" if world > 1 else "single GPU",
                        "precision_note": "config[4] allows bf16; this path keeps the bf16x3 split so gradients match fp32 autograd to 5e-3"},

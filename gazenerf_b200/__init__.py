@@ -6,6 +6,7 @@ and the host-side mirror of the reference's module / option / render-util interf
 from .options import BaseOptions  # noqa: F401
 from .net import GazeNeRFNet, NeuralRendererParams, RadianceMLP  # noqa: F401
 from .render_utils import RenderUtils  # noqa: F401
+from .losses import GazeNeRFLoss  # noqa: F401
 from ._lib import build, lib  # noqa: F401
 
-__all__ = ["BaseOptions", "GazeNeRFNet", "NeuralRendererParams", "RadianceMLP", "RenderUtils", "build", "lib"]
+__all__ = ["BaseOptions", "GazeNeRFNet", "NeuralRendererParams", "RadianceMLP", "RenderUtils", "GazeNeRFLoss", "build", "lib"]

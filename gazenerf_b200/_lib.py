@@ -19,7 +19,7 @@ INCLUDE = os.path.join(_ROOT, "include")
 LIB_PATH = os.path.join(_HERE, "libgnrf.so")
 
 SOURCES = ["abi.cu", "geometry.cu", "mlp_simt.cu", "mlp_tc.cu", "compose.cu", "neural_render.cu", "conv_tc.cu", "wgrad_tc.cu",
-           "train_ops.cu", "nr_train.cu"]
+           "train_ops.cu", "nr_train.cu", "loss.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -41,6 +41,7 @@ SYMBOLS = [
     "gnrf_pe_fwd", "gnrf_pe_bwd", "gnrf_composite_cm_fwd", "gnrf_composite_cm_bwd", "gnrf_geom_bwd",
     "gnrf_compose_bwd_blocks", "gnrf_compose_bwd",
     "gnrf_nr_train_saved_bytes", "gnrf_nr_train_fwd", "gnrf_nr_train_bwd_workspace_bytes", "gnrf_nr_train_bwd",
+    "gnrf_data_loss_workspace_floats", "gnrf_data_loss_fwd", "gnrf_data_loss_bwd",
 ]
 
 
@@ -140,6 +141,9 @@ def lib() -> ctypes.CDLL:
     L.gnrf_nr_train_bwd_workspace_bytes.restype = sz
     L.gnrf_nr_train_bwd_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
     L.gnrf_nr_train_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp]
+    L.gnrf_data_loss_workspace_floats.restype = sz
+    L.gnrf_data_loss_fwd.argtypes = [vp] * 9 + [i32, i32, i32, f32, vp, vp, vp, vp]
+    L.gnrf_data_loss_bwd.argtypes = [vp] * 9 + [i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is c.c_int and name not in ("gnrf_abi_version",):

@@ -280,8 +280,9 @@ class GazeNeRFNet(nn.Module):
             raise ValueError("mlp_impl must be 'tc' or 'simt', got %r" % (impl,))
         return feat, alpha, wts
 
-    def _images(self, feat, alpha, gaze, B: int) -> Dict[str, torch.Tensor]:
-        """compose (bg blend, rotate, max-merge) + ONE batched neural-render call over [face|eyes|merge|bg]."""
+    def _images(self, feat, alpha, gaze, B: int, only_merge: bool = False) -> Dict[str, torch.Tensor]:
+        """compose (bg blend, rotate, max-merge) + ONE batched neural-render call over [face|eyes|merge|bg]
+        (``only_merge``: just [merge|bg] -- what the view-sweep callers consume, utils/render_utils.py:214-219)."""
         L = _lib.lib()
         C, S = self.featmap_nc, self.featmap_size
         P = S * S
@@ -295,19 +296,26 @@ class GazeNeRFNet(nn.Module):
                                       gaze.data_ptr(), B, C, P, fm.data_ptr(), _stream()), "gnrf_compose_fwd")
         if bg_img is None:
             fm[3 * B].copy_(bg[0])
+        if self.keep_stages:
+            self.last_stages.update({"merge_face": fm[:B], "eyes_planes": fm[B:2 * B], "merge": fm[2 * B:3 * B]})
+        if only_merge:
+            imgs = neural_render(self.neural_render, fm[2 * B:])
+            if bg_img is None:
+                bg_img = imgs[B:]
+                if self.cache_bg_img:
+                    self._bg_cache = (key, bg_img.clone())
+            return {"merge_img": imgs[:B], "bg_img": bg_img}
         imgs = neural_render(self.neural_render, fm)  # ONE batched call over [face | eyes | merge (| bg)]
         if bg_img is None:
             bg_img = imgs[3 * B:]
             if self.cache_bg_img:
                 self._bg_cache = (key, bg_img.clone())
-        if self.keep_stages:
-            self.last_stages.update({"merge_face": fm[:B], "eyes_planes": fm[B:2 * B], "merge": fm[2 * B:3 * B]})
         return {"merge_img_face": imgs[:B], "merge_img_eyes": imgs[B:2 * B], "merge_img": imgs[2 * B:3 * B], "bg_img": bg_img}
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def _forward(self, for_train, batch_xy, batch_uv, bg_code, shape_code, appea_code, gaze_dir, batch_Rmats, batch_Tvecs,
-                 batch_inv_inmats, dist_expr, jitter_u=None):
+                 batch_inv_inmats, dist_expr, jitter_u=None, only_merge=False):
         L = _lib.lib()
         batch_size, tv, n_r = batch_xy.size()
         assert tv == 2
@@ -353,7 +361,7 @@ class GazeNeRFNet(nn.Module):
             if self.keep_stages:
                 self.last_stages.update({"ray_dl": ray_dl, "z_edges": z_edges, "feat_face": feat[0], "feat_eyes": feat[1],
                                          "bg_alpha_face": alpha[0], "bg_alpha_eyes": alpha[1], "w_face": wts[0], "w_eyes": wts[1]})
-            res_dict = {"coarse_dict": self._images(feat, alpha, gaze, batch_size)}
+            res_dict = {"coarse_dict": self._images(feat, alpha, gaze, batch_size, only_merge=only_merge and not self.hier_sampling)}
 
             if self.hier_sampling:
                 # BASELINE config 3.  The reference's own hier branch is dead code; this composes its working
@@ -441,4 +449,5 @@ class GazeNeRFNet(nn.Module):
             return self._forward_train(mode == "train", batch_xy, bg_code, shape_code, appea_code, gaze_code, batch_Rmats, batch_Tvecs,
                                        batch_inv_inmats, jitter_u=kwargs.get("jitter_u"))
         return self._forward(mode == "train", batch_xy, batch_uv, bg_code, shape_code, appea_code, gaze_code, batch_Rmats,
-                             batch_Tvecs, batch_inv_inmats, dist_expr, jitter_u=kwargs.get("jitter_u"))
+                             batch_Tvecs, batch_inv_inmats, dist_expr, jitter_u=kwargs.get("jitter_u"),
+                             only_merge=bool(kwargs.get("only_merge", False)))

@@ -214,6 +214,19 @@ int gnrf_nr_train_bwd(const float* const* params, const float* featmap, const vo
                       int N, int C, int S, int n_blocks, int min_feat, float* g_featmap, float* const* g_params, void* workspace,
                       size_t workspace_bytes, gnrf_stream_t stream);
 
+/* Fused data terms of GazeNeRFLoss (losses/gazenerf_loss.py:294-352; mask algebra of calc_total_loss :420-424).
+ * images [B,3,HW] (bg_img [1,3,HW]), masks [B,1,HW] float.  terms[5] = (head, eyes, face, nonhead, bg), each the mean the reference
+ * takes over its boolean gather (an empty mask yields NaN, as there); sums[9] keeps the numerators / pixel counts for the backward.
+ * workspace: gnrf_data_loss_workspace_floats() floats.  Backward: g_terms[5] -> gradients of the four images. */
+size_t gnrf_data_loss_workspace_floats(void);
+int gnrf_data_loss_fwd(const float* img_face, const float* img_eyes, const float* img, const float* bg_img, const float* gt,
+                       const float* face_mask, const float* full_eye, const float* left_eye, const float* right_eye, int B, int HW,
+                       int use_l1, float bg_value, float* terms, float* sums, float* workspace, gnrf_stream_t stream);
+int gnrf_data_loss_bwd(const float* img_face, const float* img_eyes, const float* img, const float* bg_img, const float* gt,
+                       const float* face_mask, const float* full_eye, const float* left_eye, const float* right_eye, int B, int HW,
+                       int use_l1, float bg_value, const float* sums, const float* g_terms, float* g_img_face, float* g_img_eyes,
+                       float* g_img, float* g_bg_img, gnrf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -519,3 +519,41 @@ def calibrate_dense_bias(sd, opt: OracleOptions, batch_xy, shape_code, appea_cod
         raw = pos - neg
         out.append(-scale * float(raw.median()))
     return out[0], out[1]
+
+
+# --------------------------------------------------------------------------------------
+# GazeNeRFLoss data terms (losses/gazenerf_loss.py:294-352 + mask algebra :420-424), use_vgg_loss=False
+# --------------------------------------------------------------------------------------
+def data_loss_terms(pred: Dict[str, Tensor], gt: Tensor, face_mask: Tensor, full_eye: Tensor, left_eye: Tensor, right_eye: Tensor,
+                    use_l1: bool = True, bg_value: float = 1.0) -> Dict[str, Tensor]:
+    """Boolean-gather formulation exactly as the reference writes it."""
+    head_m = torch.logical_and(face_mask >= 0.5, full_eye < 0.5).expand(-1, 3, -1, -1)
+    face_m = torch.logical_and(face_mask >= 0.5, torch.logical_and(left_eye < 0.5, right_eye < 0.5)).expand(-1, 3, -1, -1)
+    eyes_m = torch.logical_or(left_eye >= 0.5, right_eye >= 0.5).expand(-1, 3, -1, -1)
+    nonhead_m = (face_mask < 0.5).expand(-1, 3, -1, -1)
+    fn = torch.nn.functional.l1_loss if use_l1 else torch.nn.functional.mse_loss
+    bg = pred["bg_img"]
+    tv = pred["merge_img"][nonhead_m] - bg_value
+    return {
+        "bg_loss": torch.mean((bg - bg_value) * (bg - bg_value)),
+        "eyes_loss": fn(pred["merge_img_eyes"][eyes_m], gt[eyes_m]),
+        "face_loss": fn(pred["merge_img_face"][face_m], gt[face_m]),
+        "nonhead_loss": torch.mean(tv * tv),
+        "head_loss": fn(pred["merge_img"][head_m], gt[head_m]),
+    }
+
+
+def synthetic_loss_inputs(batch: int, size: int, seed: int = 0):
+    """Random images / gt and blob-like masks (head ellipse, two eye boxes, full-eye box) for loss parity."""
+    g = torch.Generator().manual_seed(seed)
+    pred = {k: torch.rand(batch, 3, size, size, generator=g) for k in ("merge_img_face", "merge_img_eyes", "merge_img")}
+    pred["bg_img"] = torch.rand(1, 3, size, size, generator=g)
+    gt = torch.rand(batch, 3, size, size, generator=g)
+    yy, xx = torch.meshgrid(torch.arange(size).float(), torch.arange(size).float(), indexing="ij")
+    c = (size - 1) / 2.0
+    face = ((((yy - c) / (0.42 * size)) ** 2 + ((xx - c) / (0.34 * size)) ** 2) < 1.0).float()
+    face = (face * (0.6 + 0.4 * torch.rand(batch, 1, size, size, generator=g)))          # soft values around the 0.5 threshold
+    box = lambda y0, y1, x0, x1: ((yy >= y0 * size) & (yy < y1 * size) & (xx >= x0 * size) & (xx < x1 * size)).float().expand(batch, 1, -1, -1).clone()
+    left, right = box(0.38, 0.46, 0.30, 0.44), box(0.38, 0.46, 0.56, 0.70)
+    full_eye = box(0.36, 0.48, 0.28, 0.72)
+    return pred, gt, face, full_eye, left, right

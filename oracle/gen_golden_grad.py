@@ -103,5 +103,38 @@ def main():
     print("std_dense_train_grad.npz loss", loss, sum(v.nbytes for v in out.values()) // 1024, "KiB raw")
 
 
+
+
+def loss_goldens():
+    """GazeNeRFLoss data terms + image gradients from the reference's own loss module (use_vgg_loss=False)."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import gazenerf_oracle as O
+    from losses.gazenerf_loss import GazeNeRFLoss  # reference
+
+    out = {}
+    for use_l1 in (True, False):
+        pred, gt, face, full_eye, left, right = O.synthetic_loss_inputs(2, 64, seed=5)
+        pred = {k: v.clone().requires_grad_(True) for k, v in pred.items()}
+        lf = GazeNeRFLoss(eye_loss_importance=1.0, vgg_importance=1.0, use_vgg_loss=False, use_l1_loss=use_l1)
+        opt_code = {"iden": torch.zeros(2, 100), "expr": torch.zeros(2, 79), "appea": torch.zeros(2, 127), "bg": None}
+        ld = lf.calc_total_loss(None, opt_code, {"coarse_dict": pred}, gt, face, full_eye, left, right, None, None, 0, 0)
+        w = {"bg_loss": 1.0, "eyes_loss": 2.0, "face_loss": 3.0, "nonhead_loss": 4.0, "head_loss": 5.0}
+        sum(w[k] * ld[k] for k in w).backward()
+        tag = "l1" if use_l1 else "mse"
+        for k in w:
+            out["%s/%s" % (tag, k)] = np.array([float(ld[k])])
+        out["%s/total_loss" % tag] = np.array([float(ld["total_loss"])])
+        for k, v in pred.items():
+            out["%s/g_%s" % (tag, k)] = GG.np32(v.grad)
+    np.savez_compressed(os.path.join(GG.OUT, "loss.npz"), **out)
+    print("loss.npz", sum(v.nbytes for v in out.values()) // 1024, "KiB raw")
+
+
 if __name__ == "__main__":
-    main()
+    if os.environ.get("GNRF_LOSS_ONLY"):   # only tests/golden/loss.npz
+        GG.install_kornia_shim()
+        sys.path.insert(0, GG.REF)
+        os.chdir(GG.REF)
+    else:
+        main()
+    loss_goldens()
