@@ -134,7 +134,7 @@ constexpr int kSmemALo45 = kABytes;                                         // A
 constexpr int kSmemRing = kABytes + (kNumKB - kALoTmemKB) * kABlockBytes;   // 131072
 constexpr int kSmemBars = kSmemRing + kStages * kSlotBytes;                 // 229376
 constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarAReady = 2 * kStages, kBarAccFull = kBarAReady + kNumKB,
-              kBarAFree = kBarAccFull + 1, kNumBars = kBarAFree + 1;
+              kBarAFree = kBarAccFull + 1, kBarA01Free = kBarAFree + 1, kNumBars = kBarA01Free + 1;
 constexpr int kSmemMisc = kSmemBars + kNumBars * 8;          // tmem ptr, scan scratch
 constexpr int kSmemBytes = kSmemMisc + 64 + 1024;            // + alignment slack
 
@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
     for (int i = 0; i < kNumKB; ++i) mbar_init(bar(kBarAReady + i), 8);  // one arrive per epilogue warp
     mbar_init(bar(kBarAccFull), 1);
     mbar_init(bar(kBarAFree), 1);
+    mbar_init(bar(kBarA01Free), 1);
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc_512(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)));
@@ -343,7 +344,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
         tc_fence_after_sync();
       };
       // all K-slices of both accumulator blocks, fully unrolled (blk 0: N=128, one A K-block per stage; blk 1: N=256 / 80)
-      auto run_pass = [&](auto n1_c, auto k16n_c, bool pe_pass, bool fresh_start) {
+      // `early`: accumulator columns 0..127 (blk 0) are final once blk 0 has been issued, and A K-blocks 0,1 are dead once blk 1 has
+      // consumed its first four stages -> commit kBarA01Free there, so the epilogue drains K-blocks 0,1 of this layer's output (the
+      // first operands AND the first accumulator columns of the next layer's blk 0) while blk 1 is still running.
+      auto run_pass = [&](auto n1_c, auto k16n_c, bool pe_pass, bool fresh_start, bool early) {
         constexpr int K16N = decltype(k16n_c)::value;
         constexpr int NB0 = K16N / 4, NB1 = K16N / 2;
         static_assert((NB0 + NB1) % kStages == 0, "a pass must use a whole number of ring wraps");
@@ -360,8 +364,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
         }
         if (PROF) { if (prof_on && K16N == 24) args.prof[((size_t)prof_item * 10 + prof_layer) * 16 + 10] = clock64(); }  // blk 0 issued
 #pragma unroll
-        for (int i = 0; i < NB1; ++i)
+        for (int i = 0; i < NB1; ++i) {
           do_stage(n1_c, std::integral_constant<int, 2>{}, NB0 + i, 128u, 2 * i, fresh_start && i == 0);
+          if (NB1 > 4 && i == 3 && early) umma_commit(bar(kBarA01Free));
+        }
         if (((NB0 + NB1) / kStages) & 1) wp ^= 1u;
       };
       using I4 = std::integral_constant<int, 4>;
@@ -377,27 +383,29 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
         // ---- layer 0: K = 64 (PE in K-block 0)
         stamp(0, 0);
         wait_a(0);
-        run_pass(N256{}, I4{}, true, true);
+        run_pass(N256{}, I4{}, true, true, false);
+        umma_commit(bar(kBarA01Free));
         umma_commit(bar(kBarAccFull));
         stamp(0, 3);
         // ---- layers 1..7
 #pragma unroll 1
         for (int layer = 1; layer < 8; ++layer) {
           stamp(layer, 0);
-          run_pass(N256{}, I24{}, false, true);
+          run_pass(N256{}, I24{}, false, true, layer != 5);
           if (layer == 5) {
             // skip connection: the PE columns of FeaExt_module_5 (models/mlp_nerf.py:106-107); the epilogue re-stages
             // the tile's PE into K-block 0 once every read of the hidden K-blocks has completed.
             umma_commit(bar(kBarAFree));
             wait_a(0);
-            run_pass(N256{}, I4{}, true, false);
+            run_pass(N256{}, I4{}, true, false, false);
+            umma_commit(bar(kBarA01Free));
           }
           umma_commit(bar(kBarAccFull));
           stamp(layer, 3);
         }
         // ---- layer 8: [RGB_0*RGB_1 (192) | density (1) | pad] = N 128 + 80
         stamp(8, 0);
-        run_pass(N80{}, I24{}, false, true);
+        run_pass(N80{}, I24{}, false, true, false);
         umma_commit(bar(kBarAccFull));
         stamp(8, 3);
       }
@@ -410,7 +418,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
     const int half = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    uint32_t acc_phase = 0, afree_phase = 0;
+    uint32_t acc_phase = 0, afree_phase = 0, a01_phase = 0;
     const int N_s = args.N_s;
     const int rays_per_tile = kTile / N_s;
     // per-ray composite scratch [128][193] fp32: aliases A K-blocks 1.. (K-block 0 stays free for the next tile's PE)
@@ -490,13 +498,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
       long long* ep = eprof ? args.prof + ((size_t)(item / n_clusters) * 10) * 16 : nullptr;
       if (eprof) ep[6] = clock64();  // layer-0 row: K-block 0 (PE) of this tile released
       for (int layer = 0; layer < 8; ++layer) {
-        mbar_wait(bar(kBarAccFull), acc_phase);
-        if (eprof) ep[layer * 16 + 7] = clock64();  // accumulator of `layer` complete
-        acc_phase ^= 1;
-        tc_fence_after_sync();
         const float* bl = bias + bias_offset(layer) + half * 32;
-#pragma unroll 1
-        for (int kb = 0; kb < kNumKB; ++kb) {
+        // drain one K-block (64 accumulator columns; this thread: 32 of them) into the next layer's A operand
+        auto drain_kb = [&](int kb) {
           uint32_t r0[32];
           tmem_ld32(t_lane + kb * 64 + half * 32, r0);
           const float4* b4 = reinterpret_cast<const float4*>(bl + kb * 64);
@@ -520,8 +524,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
           }
           if (dump)
             for (int j = 0; j < 32; ++j) args.dbg[((size_t)(layer + 1) * kTile + row) * kHidden + kb * 64 + half * 32 + j] = v[j];
+        };
+        // K-blocks 0,1: accumulator columns 0..127 are final and A K-blocks 0,1 are no longer read (kBarA01Free) while the rest of
+        // the layer (blk 1) may still be running; the next layer's blk 0 can then start the moment this layer completes.
+        mbar_wait(bar(kBarA01Free), a01_phase);
+        a01_phase ^= 1;
+        tc_fence_after_sync();
+        drain_kb(0);
+        drain_kb(1);
+        release_kb_pair(0);
+        if (eprof) ep[layer * 16 + 8] = clock64();  // K-blocks 0..1 released
+        mbar_wait(bar(kBarAccFull), acc_phase);
+        if (eprof) ep[layer * 16 + 7] = clock64();  // accumulator of `layer` complete
+        acc_phase ^= 1;
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (int kb = 2; kb < kNumKB; ++kb) {
+          drain_kb(kb);
           if (kb & 1) release_kb_pair(kb - 1);
-          if (eprof && (kb == 1 || kb == 5)) ep[layer * 16 + (kb == 1 ? 8 : 9)] = clock64();  // K-blocks 0..1 / all released
+          if (eprof && kb == 5) ep[layer * 16 + 9] = clock64();  // all released
           if (eprof && kb == 3 && layer > 0) ep[layer * 16 + 6] = clock64();
         }
         if (layer == 4) {
