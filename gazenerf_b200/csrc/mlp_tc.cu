@@ -347,7 +347,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
       // `early`: accumulator columns 0..127 (blk 0) are final once blk 0 has been issued, and A K-blocks 0,1 are dead once blk 1 has
       // consumed its first four stages -> commit kBarA01Free there, so the epilogue drains K-blocks 0,1 of this layer's output (the
       // first operands AND the first accumulator columns of the next layer's blk 0) while blk 1 is still running.
-      auto run_pass = [&](auto n1_c, auto k16n_c, bool pe_pass, bool fresh_start, bool early) {
+      // `afree`: (layer 5) A K-block 0 is dead once blk 1 has consumed its first two stages; kBarAFree is committed there, so the
+      // epilogue re-stages the positional encoding into K-block 0 while the rest of the hidden pass is still running.
+      auto run_pass = [&](auto n1_c, auto k16n_c, bool pe_pass, bool fresh_start, bool early, bool afree = false) {
         constexpr int K16N = decltype(k16n_c)::value;
         constexpr int NB0 = K16N / 4, NB1 = K16N / 2;
         static_assert((NB0 + NB1) % kStages == 0, "a pass must use a whole number of ring wraps");
@@ -367,6 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
         for (int i = 0; i < NB1; ++i) {
           do_stage(n1_c, std::integral_constant<int, 2>{}, NB0 + i, 128u, 2 * i, fresh_start && i == 0);
           if (NB1 > 4 && i == 3 && early) umma_commit(bar(kBarA01Free));
+          if (NB1 > 4 && i == 1 && afree) umma_commit(bar(kBarAFree));
         }
         if (((NB0 + NB1) / kStages) & 1) wp ^= 1u;
       };
@@ -391,11 +394,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
 #pragma unroll 1
         for (int layer = 1; layer < 8; ++layer) {
           stamp(layer, 0);
-          run_pass(N256{}, I24{}, false, true, layer != 5);
+          run_pass(N256{}, I24{}, false, true, layer != 5, layer == 5);
           if (layer == 5) {
-            // skip connection: the PE columns of FeaExt_module_5 (models/mlp_nerf.py:106-107); the epilogue re-stages
-            // the tile's PE into K-block 0 once every read of the hidden K-blocks has completed.
-            umma_commit(bar(kBarAFree));
+            // skip connection: the PE columns of FeaExt_module_5 (models/mlp_nerf.py:106-107); the epilogue re-staged the tile's
+            // PE into K-block 0 as soon as the hidden pass had finished reading that K-block (kBarAFree, committed inside the pass).
             wait_a(0);
             run_pass(N256{}, I4{}, true, false, false);
             umma_commit(bar(kBarA01Free));
