@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256) blur_lrelu_rgb_kernel(const float* __rest
     float o[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) o[i] = lrelu((col[i] + 2.0f * col[i + 1] + col[i + 2]) * 0.0625f);
-    *reinterpret_cast<float4*>(po + (size_t)c * HW + (size_t)y * Wd + x0) = make_float4(o[0], o[1], o[2], o[3]);
+    if (net != nullptr) *reinterpret_cast<float4*>(po + (size_t)c * HW + (size_t)y * Wd + x0) = make_float4(o[0], o[1], o[2], o[3]);
     const float w0 = s_w[c], w1 = s_w[C + c], w2 = s_w[2 * C + c];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -297,6 +297,7 @@ extern "C" size_t gnrf_nr_workspace_bytes(int N, int C, int S, int n_blocks, int
 struct NrBufs {
   float* t1[8]; float* sh[8]; float* net[8];
   float* bl; float* rgb_a; float* rgb_b;
+  bool keep_last;   // write the last level's activation (needed by the backward only)
 };
 
 static int nr_forward_bufs(const float* const* params, const unsigned char* packed, const float* featmap, int N, int C, int S, int n_blocks,
@@ -322,6 +323,7 @@ static int nr_forward(const float* const* params, const unsigned char* packed, c
   bufs.bl = reinterpret_cast<float*>(ws + pl.bl);
   bufs.rgb_a = reinterpret_cast<float*>(ws + pl.rgb_a);
   bufs.rgb_b = reinterpret_cast<float*>(ws + pl.rgb_b);
+  bufs.keep_last = false;
   return nr_forward_bufs(params, packed, featmap, N, C, S, n_blocks, min_feat, img, bufs, as_stream(stream));
 }
 
@@ -392,8 +394,9 @@ static int nr_forward_bufs(const float* const* params, const unsigned char* pack
                                   tc::CONV_EPI_LINEAR, st);
       if (rc != GNRF_OK) return rc;
       dim3 grid(ceil_div(HW / 4, 256), N);
+      // the last level's activation is consumed only by the fused to-RGB head: not written unless the caller keeps it (training)
       blur_lrelu_rgb_kernel<<<grid, 256, 3 * co * sizeof(float), st>>>(bl, co, s, s, rgb_w(i + 1), rgb_bi(i + 1), rgb_up, last ? 1 : 0,
-                                                                      net_out, last ? img : rgb_cur);
+                                                                      (last && !bufs.keep_last) ? nullptr : net_out, last ? img : rgb_cur);
       count_launches(1);
     } else {
       {
@@ -511,6 +514,7 @@ extern "C" int gnrf_nr_train_fwd(const float* const* params, const void* packed,
   bufs.bl = reinterpret_cast<float*>(ws + pl.bl);
   bufs.rgb_a = reinterpret_cast<float*>(ws + pl.rgb_a);
   bufs.rgb_b = reinterpret_cast<float*>(ws + pl.rgb_b);
+  bufs.keep_last = true;
   return nr_forward_bufs(params, static_cast<const unsigned char*>(packed), featmap, N, C, S, n_blocks, min_feat, img, bufs,
                          as_stream(stream));
 }
