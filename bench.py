@@ -421,7 +421,7 @@ def main():
                          "peak_source": "%s bf16 dense, sustained (kernel timed inside a long step)" % peaks["src"],
                          # dram__bytes_read.sum + dram__bytes_write.sum of one mlp_tc_kernel launch at F=1, ncu --set full
                          # (profiles/r1_mlp_tc_kernel.md): the packed weights of both branches, once; everything else stays on chip / in L2
-                         "traffic": 10.6e6 if (args.mlp_impl == "tc" and F == 1) else None, "traffic_unit": "bytes/launch",
+                         "traffic": 11.0e6 if (args.mlp_impl == "tc" and F == 1) else None, "traffic_unit": "bytes/launch",
                          "kernel_ms": mlp_avg, "algorithmic_flop_per_launch": algo_flop,
                          "executed_mma_tflops": exec_tflops, "executed_frac": exec_tflops / peak,
                          "note": "achieved = reference-as-written FLOPs (3 030 144/point/branch) / time; executed = bf16x3 UMMA FLOPs after exact folds"},

@@ -404,3 +404,46 @@ def test_adam_step_refreshes_packed_weights(dev):
         optim.step()
         losses.append(float(loss))
     assert losses[2] < losses[0], losses
+
+
+@gpu
+@pytest.mark.parametrize("B,S,n_s,mode", [(1, 16, 16, "test"), (3, 8, 32, "train")])
+def test_full_gradients_other_shapes_vs_oracle(dev, B, S, n_s, mode):
+    """Batch sizes 1 and 3, 256 / 64 rays, 16 / 32 samples (tiles that straddle rays differently), orbit cameras: the drop-in
+    forward+backward vs autograd of the CPU oracle (pinned to the reference by the CPU tests of this file)."""
+    import gazenerf_b200 as G
+    opt = G.BaseOptions({"featmap_size": S, "featmap_nc": 258, "pred_img_size": 4 * S})
+    opt.num_sample_coarse = n_s
+    torch.manual_seed(45)
+    net = G.GazeNeRFNet(opt, include_vd=False, hier_sampling=False)
+    ru = G.RenderUtils(45, "cpu", opt)
+    shape, appea, gaze = O.synthetic_codes(B, seed=3)
+    cams = [ru.cam_info_list[(7 * i + 2) % 45] for i in range(B)]
+    g = {"in_xy": ru.ray_xy.expand(B, -1, -1).contiguous().numpy(), "in_shape": shape.numpy(), "in_appea": appea.numpy(), "in_gaze": gaze.numpy(),
+         "in_R": torch.cat([c["batch_Rmats"] for c in cams]).numpy(), "in_T": torch.cat([c["batch_Tvecs"] for c in cams]).numpy(),
+         "in_Kinv": torch.cat([c["batch_inv_inmats"] for c in cams]).numpy()}
+    oo = O.OracleOptions(featmap_size=S, featmap_nc=258, pred_img_size=4 * S, num_sample_coarse=n_s)
+    t = lambda k: torch.from_numpy(g[k])
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    bias = O.calibrate_dense_bias(sd0, oo, t("in_xy"), shape, appea, gaze, t("in_R"), t("in_T"), t("in_Kinv"))
+    sd = O.densify(sd0, *bias)
+    net.load_state_dict(sd)
+    ju = torch.rand(B, S * S, n_s + 1, generator=torch.Generator().manual_seed(9)) if mode == "train" else None
+    loss_ref, gin, gp = oracle_grads(sd, oo, mode, g, jitter_u=ju)
+    net = net.to(dev).train()
+    leaves = {k: t(n).to(dev).requires_grad_(True) for k, n in (("shape", "in_shape"), ("appea", "in_appea"), ("gaze", "in_gaze"), ("R", "in_R"), ("T", "in_T"))}
+    extra = {"jitter_u": ju.to(dev)} if ju is not None else {}
+    out = net(mode, t("in_xy").to(dev), None, None, leaves["shape"], leaves["appea"], leaves["gaze"], leaves["R"], leaves["T"], t("in_Kinv").to(dev), **extra)
+    imgs = out["coarse_dict"]
+    wt = loss_weights({k: imgs[k].shape for k in IMG_KEYS})
+    loss = sum((imgs[k] * wt[k].to(dev)).sum() for k in IMG_KEYS)
+    loss.backward()
+    assert abs(float(loss.detach()) - loss_ref) < 2e-4 * abs(loss_ref)
+    for k in ("shape", "appea"):
+        assert rel_l2(leaves[k].grad.cpu(), gin[k]) < TOL_GRAD, k
+    for k in ("gaze", "R", "T"):
+        assert rel_l2(leaves[k].grad.cpu(), gin[k]) < TOL_GRAD_SMALL, k
+    errs = {k: rel_l2(p.grad.cpu(), gp[k]) for k, p in net.named_parameters() if float(gp[k].abs().max()) > 0}
+    tol = lambda k: 2e-2 if (gp[k].numel() == 1 or "feat_upsample_list" in k) else TOL_GRAD
+    bad = {k: v for k, v in errs.items() if v >= tol(k)}
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:5]
