@@ -3,6 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mlp-impl tc|simt] [--faces-per-gpu F]
     python bench.py --workload train [--faces-per-gpu 2]      # BASELINE config[4]: full train step (not the default line)
+    python bench.py --workload hier                            # BASELINE config[2]: coarse 64 + FineSample 64 -> 128 samples/ray
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 A "step" is one full drop-in forward("test") -- rays -> both radiance MLPs (fused tcgen05 kernel) -> composite ->
@@ -283,7 +284,7 @@ def main():
     ap.add_argument("--mlp-impl", default="tc", choices=["tc", "simt"])
     ap.add_argument("--faces-per-gpu", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="render", choices=["render", "train"])
+    ap.add_argument("--workload", default="render", choices=["render", "train", "hier"])
     args = ap.parse_args()
     if args.workload == "train" and args.faces_per_gpu == 1:
         args.faces_per_gpu = 2   # config[4]: batch = 2
@@ -328,15 +329,19 @@ def main():
     L = G.lib()
     F = args.faces_per_gpu
     opt = G.BaseOptions()
+    hier = args.workload == "hier"
+    if hier:
+        opt.num_sample_fine = 64   # 64 coarse + 64(+1) fine -> 128 sorted samples per ray
     torch.manual_seed(45)  # the reference's seed (train.py:53); identical weights on every rank
-    net = G.GazeNeRFNet(opt, include_vd=False, hier_sampling=False, mlp_impl=args.mlp_impl).to(dev).eval()
+    net = G.GazeNeRFNet(opt, include_vd=False, hier_sampling=hier, mlp_impl=args.mlp_impl).to(dev).eval()
     host_kw = synthetic_inputs(torch, G, opt, F, seed=rank)
     pinned = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host_kw.items()}
     dev_kw = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host_kw.items()}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step(kw):
-        out = net("test", **kw)["coarse_dict"]
+        out = net("test", **kw)
+        out = out["fine_dict"] if hier else out["coarse_dict"]
         if world > 1:
             out = all_gather_images(out, world * F)
         return out
@@ -405,24 +410,31 @@ def main():
         faces_total = world * F * args.steps
         value = faces_total / (total_ms * 1e-3)
         algo_flop = 2 * F * N_RAYS * N_SAMPLES * MLP_FLOP_PER_POINT_PER_BRANCH   # per fused-MLP launch (both branches)
-        achieved = algo_flop / (mlp_avg * 1e-3) / 1e12
-        exec_tflops = 2 * F * N_RAYS * N_SAMPLES * 2 * EXEC_MAC_PER_POINT_PER_BRANCH / (mlp_avg * 1e-3) / 1e12
+        mlp_ms = mlp_avg
+        if hier:
+            # the coarse pass (64 samples) is the timed launch; the fine pass (128 samples) is a second launch of the same kernel with
+            # twice the points: report the step-level rate over all three passes' worth of work (4.766e12 FLOP/face)
+            algo_flop *= 3
+            mlp_ms = total_ms / args.steps
+        achieved = algo_flop / (mlp_ms * 1e-3) / 1e12
+        exec_tflops = (3 if hier else 1) * 2 * F * N_RAYS * N_SAMPLES * 2 * EXEC_MAC_PER_POINT_PER_BRANCH / (mlp_ms * 1e-3) / 1e12
         peak = peaks["bf16_sustained"]
         line = {
-            "metric": METRIC, "value": value, "unit": "faces/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC if not hier else "faces/s (512x512, hierarchical 64 coarse + 64 fine samp/ray)", "value": value, "unit": "faces/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3 split (fp32 accumulate) on tensor cores; f32 elsewhere" if args.mlp_impl == "tc" else "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "faces_per_gpu_per_step": F, "rays": N_RAYS, "samples_per_ray": N_SAMPLES, "mlp_impl": args.mlp_impl,
+            "config": {"workload": WORKLOAD if not hier else "config[2]: hierarchical coarse(64)+fine(64) sampling at 512x512 (FineSample path), face+eye branches",
+                       "faces_per_gpu_per_step": F, "rays": N_RAYS, "samples_per_ray": N_SAMPLES, "mlp_impl": args.mlp_impl,
                        "weights": "reference init, torch.manual_seed(45)", "l2": "256 MiB memset between timed steps (untimed)",
                        "multi_gpu": "batch-sharded, one all-gather of the rendered images per step" if world > 1 else "single GPU"},
-            "roofline": {"bound": "tensor", "kernel": "mlp_tc_kernel (+fold, rgb_head)" if args.mlp_impl == "tc" else "mlp_simt_kernel+composite",
+            "roofline": {"bound": "tensor", "kernel": ("whole step: coarse + fine mlp_tc_kernel launches, fine_depths, 2x neural renderer" if hier else "mlp_tc_kernel (+fold, rgb_head)") if args.mlp_impl == "tc" else "mlp_simt_kernel+composite",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": "%s bf16 dense, sustained (kernel timed inside a long step)" % peaks["src"],
                          # dram__bytes_read.sum + dram__bytes_write.sum of one mlp_tc_kernel launch at F=1, ncu --set full
                          # (profiles/r1_mlp_tc_kernel.md): the packed weights of both branches, once; everything else stays on chip / in L2
-                         "traffic": 11.0e6 if (args.mlp_impl == "tc" and F == 1) else None, "traffic_unit": "bytes/launch",
-                         "kernel_ms": mlp_avg, "algorithmic_flop_per_launch": algo_flop,
+                         "traffic": 11.0e6 if (args.mlp_impl == "tc" and F == 1 and not hier) else None, "traffic_unit": "bytes/launch",
+                         "kernel_ms": mlp_ms, "algorithmic_flop_per_launch": algo_flop,
                          "executed_mma_tflops": exec_tflops, "executed_frac": exec_tflops / peak,
                          "note": "achieved = reference-as-written FLOPs (3 030 144/point/branch) / time; executed = bf16x3 UMMA FLOPs after exact folds"},
             "e2e": {"value": faces_total / e2e_s, "unit": "faces/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -22,7 +22,7 @@ TOL_GRAD_SMALL = 1e-2   # camera / gaze gradients: sums of many cancelling terms
 
 def loss_weights(shapes, seed=99):  # same recipe as oracle/gen_golden_grad.py
     g = torch.Generator().manual_seed(seed)
-    return {k: torch.randn(shapes[k], generator=g) for k in IMG_KEYS}
+    return {k: torch.randn(shapes[k], generator=g, dtype=torch.float32) for k in IMG_KEYS}
 
 
 def proj_vec(shape, idx):
@@ -30,8 +30,18 @@ def proj_vec(shape, idx):
     return torch.randn(shape, generator=g)
 
 
-def oracle_grads(sd, oo, mode, g, jitter_u=None):
-    """loss + gradients through the CPU oracle's autograd."""
+def oracle_grads(sd, oo, mode, g, jitter_u=None, dtype=torch.float32):
+    """loss + gradients through the CPU oracle's autograd (dtype=float64: the same graph in double precision, used to measure how
+    sensitive a configuration's gradients are to rounding, i.e. to ReLU / max decisions flipping)."""
+    if dtype == torch.float64:
+        prev = torch.get_default_dtype()
+        torch.set_default_dtype(torch.float64)
+        try:
+            sd64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in sd.items()}
+            g64 = {k: (v.astype(np.float64) if v.dtype == np.float32 else v) for k, v in g.items()}
+            return oracle_grads(sd64, oo, mode, g64, jitter_u=None if jitter_u is None else jitter_u.double(), dtype=None)
+        finally:
+            torch.set_default_dtype(prev)
     sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and not k.endswith(".f")) for k, v in sd.items()}
     t = lambda k: torch.from_numpy(g[k])
     leaves = {"shape": t("in_shape").requires_grad_(True), "appea": t("in_appea").requires_grad_(True), "gaze": t("in_gaze").requires_grad_(True),
@@ -39,7 +49,7 @@ def oracle_grads(sd, oo, mode, g, jitter_u=None):
     out = O.forward(sd, oo, mode, t("in_xy"), leaves["shape"], leaves["appea"], leaves["gaze"], leaves["R"], leaves["T"], t("in_Kinv"),
                     jitter_u=jitter_u)["coarse_dict"]
     wt = loss_weights({k: out[k].shape for k in IMG_KEYS})
-    loss = sum((out[k] * wt[k]).sum() for k in IMG_KEYS)
+    loss = sum((out[k] * wt[k].to(out[k].dtype)).sum() for k in IMG_KEYS)
     loss.backward()
     gp = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in sd.items() if v.requires_grad}
     return float(loss.detach()), {k: v.grad for k, v in leaves.items()}, gp
@@ -407,18 +417,22 @@ def test_adam_step_refreshes_packed_weights(dev):
 
 
 @gpu
-@pytest.mark.parametrize("B,S,n_s,mode", [(1, 16, 16, "test"), (3, 8, 32, "train")])
-def test_full_gradients_other_shapes_vs_oracle(dev, B, S, n_s, mode):
+@pytest.mark.parametrize("B,S,n_s,mode,seed", [(1, 16, 16, "test", 3), (1, 16, 16, "test", 4), (1, 16, 16, "test", 5), (3, 8, 32, "train", 3)])
+def test_full_gradients_other_shapes_vs_oracle(dev, B, S, n_s, mode, seed):
     """Batch sizes 1 and 3, 256 / 64 rays, 16 / 32 samples (tiles that straddle rays differently), orbit cameras: the drop-in
-    forward+backward vs autograd of the CPU oracle (pinned to the reference by the CPU tests of this file)."""
+    forward+backward vs autograd of the CPU oracle (pinned to the reference by the CPU tests of this file).
+    The oracle is run in fp32 AND fp64: their difference measures how much of a gradient hangs on ReLU / max decisions that flip
+    under rounding in this configuration (7e-3 .. 1.2e-2 in these dense, density-centred-on-zero setups; WHICH tensors are hit depends
+    on which decision flips, so the bound is the configuration's worst tensor), and the GPU path is held to max(TOL, 3 x that) against
+    the fp64 run -- i.e. it must be about as close to exact arithmetic as the fp32 reference itself is."""
     import gazenerf_b200 as G
     opt = G.BaseOptions({"featmap_size": S, "featmap_nc": 258, "pred_img_size": 4 * S})
     opt.num_sample_coarse = n_s
     torch.manual_seed(45)
     net = G.GazeNeRFNet(opt, include_vd=False, hier_sampling=False)
     ru = G.RenderUtils(45, "cpu", opt)
-    shape, appea, gaze = O.synthetic_codes(B, seed=3)
-    cams = [ru.cam_info_list[(7 * i + 2) % 45] for i in range(B)]
+    shape, appea, gaze = O.synthetic_codes(B, seed=seed)
+    cams = [ru.cam_info_list[(7 * i + 2 + seed) % 45] for i in range(B)]
     g = {"in_xy": ru.ray_xy.expand(B, -1, -1).contiguous().numpy(), "in_shape": shape.numpy(), "in_appea": appea.numpy(), "in_gaze": gaze.numpy(),
          "in_R": torch.cat([c["batch_Rmats"] for c in cams]).numpy(), "in_T": torch.cat([c["batch_Tvecs"] for c in cams]).numpy(),
          "in_Kinv": torch.cat([c["batch_inv_inmats"] for c in cams]).numpy()}
@@ -429,7 +443,10 @@ def test_full_gradients_other_shapes_vs_oracle(dev, B, S, n_s, mode):
     sd = O.densify(sd0, *bias)
     net.load_state_dict(sd)
     ju = torch.rand(B, S * S, n_s + 1, generator=torch.Generator().manual_seed(9)) if mode == "train" else None
-    loss_ref, gin, gp = oracle_grads(sd, oo, mode, g, jitter_u=ju)
+    loss_ref, gin32, gp32 = oracle_grads(sd, oo, mode, g, jitter_u=ju)
+    _, gin, gp = oracle_grads(sd, oo, mode, g, jitter_u=ju, dtype=torch.float64)
+    sens_in = {k: rel_l2(gin32[k], gin[k]) for k in gin}
+    sens = {k: rel_l2(gp32[k], gp[k]) for k in gp if float(gp[k].abs().max()) > 0}
     net = net.to(dev).train()
     leaves = {k: t(n).to(dev).requires_grad_(True) for k, n in (("shape", "in_shape"), ("appea", "in_appea"), ("gaze", "in_gaze"), ("R", "in_R"), ("T", "in_T"))}
     extra = {"jitter_u": ju.to(dev)} if ju is not None else {}
@@ -439,11 +456,14 @@ def test_full_gradients_other_shapes_vs_oracle(dev, B, S, n_s, mode):
     loss = sum((imgs[k] * wt[k].to(dev)).sum() for k in IMG_KEYS)
     loss.backward()
     assert abs(float(loss.detach()) - loss_ref) < 2e-4 * abs(loss_ref)
-    for k in ("shape", "appea"):
-        assert rel_l2(leaves[k].grad.cpu(), gin[k]) < TOL_GRAD, k
-    for k in ("gaze", "R", "T"):
-        assert rel_l2(leaves[k].grad.cpu(), gin[k]) < TOL_GRAD_SMALL, k
     errs = {k: rel_l2(p.grad.cpu(), gp[k]) for k, p in net.named_parameters() if float(gp[k].abs().max()) > 0}
-    tol = lambda k: 2e-2 if (gp[k].numel() == 1 or "feat_upsample_list" in k) else TOL_GRAD
+    print("input-gradient errors:", {k: rel_l2(leaves[k].grad.cpu(), gin[k]) for k in leaves}, "fp32-vs-fp64 oracle:", sens_in)
+    print("worst parameter-gradient errors:", sorted(errs.items(), key=lambda kv: -kv[1])[:8], "fp32-vs-fp64 oracle worst:", max(sens.values()))
+    s_in, s_p = max(sens_in.values()), max(sens.values())
+    for k in ("shape", "appea"):
+        assert rel_l2(leaves[k].grad.cpu(), gin[k]) < max(TOL_GRAD, 3 * s_in), k
+    for k in ("gaze", "R", "T"):
+        assert rel_l2(leaves[k].grad.cpu(), gin[k]) < max(TOL_GRAD_SMALL, 3 * s_in), k
+    tol = lambda k: max(2e-2 if (gp[k].numel() == 1 or "feat_upsample_list" in k) else TOL_GRAD, 3 * s_p)
     bad = {k: v for k, v in errs.items() if v >= tol(k)}
     assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:5]
