@@ -19,16 +19,18 @@
 // On-chip layout per CTA (1 CTA / SM, 320 threads = 8 epilogue warps + 1 TMA warp + 1 MMA warp):
 //   smem  A_hi       : 6 K-blocks x [128 rows x 64 bf16], SWIZZLE_128B K-major (UMMA canonical)          96 KB
 //         A_lo[4..5] : K-blocks 4,5 of the low halves, same layout                                        32 KB
-//         W ring     : 3 x 32 KB stages; a stage = one K-slice of one accumulator block, W_hi then W_lo (no-swizzle
+//         W ring     : 4 x 24 KB stages; a stage = one K-slice of one accumulator block, W_hi then W_lo (no-swizzle
 //                      K-major core-matrix layout), streamed from the pre-arranged packed image in L2 by cp.async.bulk
 //                      (TMA bulk copy) + mbarrier complete_tx                                              96 KB
-//   TMEM  columns 0..383   : fp32 accumulators (block 0 = cols 0..127, block 1 = cols 128..383)
+//   TMEM  columns 0..383   : fp32 accumulators (block 0 = cols 0..191, block 1 = cols 192..383)
 //         columns 384..511 : A_lo K-blocks 0..3 as packed bf16 pairs (32 columns per K-block) -> TS-mode UMMA reads the A
 //                      operand straight from tensor memory; this is what frees 64 KB of smem for a ring deep enough to
 //                      cover the L2 -> smem latency (profiles/: the 32 KB ring version was latency/issue bound at 39 %).
 // Layer pipeline: the epilogue warps drain an N=384 accumulator K-block by K-block (64 columns: +bias, ReLU, hi/lo split,
-// swizzled st.shared / tcgen05.st) and release each K-block to the MMA warp through its own mbarrier, so the next layer's
-// first accumulator block (N=128) runs while the drain is still in progress; the N=256 block then runs at full rate.
+// swizzled st.shared / tcgen05.st) and release each K-block to the MMA warp through its own mbarrier.  Both accumulator blocks
+// are N=192 (96 tensor cycles per UMMA >= the single-thread issue cost, so both run at the tensor rate); block 0's columns
+// (K-blocks 0..2 of the layer's output) are drained EARLY, while block 1 of the same layer is still running, so the next
+// layer's block 0 starts the moment the layer completes and the late drain of K-blocks 3..5 stays ahead of it.
 // The positional encoding needed again by layer 5 (skip connection) is recomputed by the epilogue warps while they would
 // otherwise wait for layer 5's first pass.
 #include <cstdlib>
@@ -50,8 +52,8 @@ constexpr int kTile = 128;               // points per tile == UMMA M
 constexpr int kKB = 64;                  // K-block (bf16 elements) == 128-byte swizzle span
 constexpr int kNumKB = kHidden / kKB;    // 6
 constexpr int kL8N = 208;                // 192 + 1 density + 15 zero rows
-constexpr int kSlotBytes = 32768;        // W ring slot (W_hi slices + W_lo slices of one stage)
-constexpr int kStages = 3;
+constexpr int kSlotBytes = 24576;        // W ring slot (W_hi slices + W_lo slices of one stage)
+constexpr int kStages = 4;
 constexpr int kALoTmemKB = 4;            // A_lo K-blocks 0..3 live in TMEM, 4..5 in smem
 constexpr int kALoCol = 384;             // first TMEM column of A_lo
 constexpr int kABlockBytes = kTile * 128;            // 16384: one K-block of A (hi or lo)
@@ -62,15 +64,15 @@ constexpr int kMaxGrid = 160;            // persistent grid upper bound (>= SM c
 constexpr int kScratchLd = 193;          // composite scratch row stride (floats): conflict-free for both phases
 
 // ---- weight stage schedule -------------------------------------------------------------------------------------------
-// Every layer's N is split into two accumulator blocks: blk 0 = outputs [0,128) (TMEM cols 0..127, UMMA N=128) and
-// blk 1 = outputs [128,384) (cols 128..383, N=256; layer 8: [128,208), N=80).  blk 0 goes first: it only needs its own
-// 128 columns drained, so it overlaps the epilogue's drain of the previous layer; each UMMA then covers 64..128 tensor
-// cycles, which hides the ~100-cycle scalar cost of issuing one tcgen05.mma from a single thread (measured, profiles/).
+// Every layer's N = 384 is split into two accumulator blocks of N = 192: blk 0 = outputs [0,192) (TMEM cols 0..191) and
+// blk 1 = outputs [192,384) (cols 192..383); the last stage (192 RGB rows + density + pad) is ONE N = 208 block.  blk 0 goes first:
+// it only needs its own 192 columns (K-blocks 0..2) drained, which the epilogue does early (see the kernel).  History (profiles/,
+// tests/ubench): with 128 + 256 blocks the N=128 UMMAs (64 tensor cycles) were bound by the ~88-cycle single-thread issue cost
+// (blk 0 took 6.7 K cycles instead of 4.6 K per layer); at N = 192 every UMMA covers 96 tensor cycles.
 // A ring stage is a K-slice of one block: [nrows x 16] bf16 per K16 step in the no-swizzle K-major core-matrix layout
 // (8 rows x 16 B contiguous, K-halves 128 B apart, 8-row groups 256 B apart), the W_hi slice followed by the W_lo slice;
-// a stage is 4 K16 steps of blk 0 or 2 of blk 1 = 32 KB = 768 tensor cycles (layer 8's N=80 block: 10 KB): the UMMA queue is
-// shallow, so the ~150-300 cycles of scalar work between bursts (try_wait, fence, descriptors) are only hidden when bursts are
-// long (measured, tests/ubench/ub_mix.cu: 6-UMMA bursts of N=128 ran at 525-680 cycles instead of 384).  Stream == consumption order:
+// a stage is 2 K16 steps of an N=192 block = 24 KB = 6 UMMAs = 576 tensor cycles (last stage: 1 K16 step of N=208, 13 KB).
+// Stream == consumption order:
 //   for layer: for phase (layer 5 only: hidden columns, then PE columns): for blk: for K-slice: one stage
 struct StageInfo {
   int layer, phase2, blk, ks, nk16, n0, nrows;
@@ -82,10 +84,11 @@ __host__ __device__ inline void for_each_stage(F&& f) {
     const int n_phase = (layer == 5) ? 2 : 1;
     for (int ph = 0; ph < n_phase; ++ph) {
       const int k16n = (layer == 0 || ph == 1) ? 4 : 24;
-      for (int blk = 0; blk < 2; ++blk) {
-        const int n0 = blk ? 128 : 0;
-        const int nrows = blk ? (layer == 8 ? 80 : 256) : 128;
-        const int step = blk ? 2 : 4;   // K16 steps per stage
+      const int n_blk = layer == 8 ? 1 : 2;
+      for (int blk = 0; blk < n_blk; ++blk) {
+        const int n0 = blk ? 192 : 0;
+        const int nrows = layer == 8 ? kL8N : 192;
+        const int step = layer == 8 ? 1 : 2;   // K16 steps per stage
         for (int ks = 0; ks < k16n; ks += step) {
           StageInfo st{layer, ph, blk, ks, step, n0, nrows, (uint32_t)(2 * nrows * 32 * step)};
           f(st);
@@ -99,7 +102,7 @@ constexpr int stage_count() {
   for (int layer = 0; layer < 9; ++layer)
     for (int ph = 0; ph < ((layer == 5) ? 2 : 1); ++ph) {
       const int k16n = (layer == 0 || ph == 1) ? 4 : 24;
-      n += (k16n / 4) + (k16n / 2);
+      n += layer == 8 ? k16n : 2 * (k16n / 2);
     }
   return n;
 }
@@ -108,11 +111,11 @@ constexpr size_t stream_bytes() {
   for (int layer = 0; layer < 9; ++layer)
     for (int ph = 0; ph < ((layer == 5) ? 2 : 1); ++ph) {
       const int k16n = (layer == 0 || ph == 1) ? 4 : 24;
-      n += (size_t)k16n * 2 * 32 * (128 + (layer == 8 ? 80 : 256));
+      n += (size_t)k16n * 2 * 32 * (layer == 8 ? kL8N : 384);
     }
   return n;
 }
-constexpr int kNumStagesPerTile = stage_count();   // 150
+constexpr int kNumStagesPerTile = stage_count();   // 200
 constexpr size_t kStreamBytes = stream_bytes();
 // fp32 auxiliary block (float offsets from aux base)
 constexpr int kBiasFloats = 8 * kHidden + kL8N;                       // 3280 per face
@@ -134,7 +137,7 @@ constexpr int kSmemALo45 = kABytes;                                         // A
 constexpr int kSmemRing = kABytes + (kNumKB - kALoTmemKB) * kABlockBytes;   // 131072
 constexpr int kSmemBars = kSmemRing + kStages * kSlotBytes;                 // 229376
 constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarAReady = 2 * kStages, kBarAccFull = kBarAReady + kNumKB,
-              kBarAFree = kBarAccFull + 1, kBarA01Free = kBarAFree + 1, kNumBars = kBarA01Free + 1;
+              kBarAFree = kBarAccFull + 1, kBarAEarly = kBarAFree + 1, kNumBars = kBarAEarly + 1;
 constexpr int kSmemMisc = kSmemBars + kNumBars * 8;          // tmem ptr, scan scratch
 constexpr int kSmemBytes = kSmemMisc + 64 + 1024;            // + alignment slack
 
@@ -237,7 +240,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
     for (int i = 0; i < kNumKB; ++i) mbar_init(bar(kBarAReady + i), 8);  // one arrive per epilogue warp
     mbar_init(bar(kBarAccFull), 1);
     mbar_init(bar(kBarAFree), 1);
-    mbar_init(bar(kBarA01Free), 1);
+    mbar_init(bar(kBarAEarly), 1);
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc_512(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)));
@@ -343,40 +346,55 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
         a_phase ^= (1u << kb);
         tc_fence_after_sync();
       };
-      // all K-slices of both accumulator blocks, fully unrolled (blk 0: N=128, one A K-block per stage; blk 1: N=256 / 80)
-      // `early`: accumulator columns 0..127 (blk 0) are final once blk 0 has been issued, and A K-blocks 0,1 are dead once blk 1 has
-      // consumed its first four stages -> commit kBarA01Free there, so the epilogue drains K-blocks 0,1 of this layer's output (the
-      // first operands AND the first accumulator columns of the next layer's blk 0) while blk 1 is still running.
+      // all K-slices of both accumulator blocks (N = 192 each: 96 tensor cycles per UMMA, above the ~88-cycle single-thread issue
+      // cost, so both blocks run at the tensor rate), fully unrolled; a stage = 2 K16 steps = 6 UMMAs.
+      // `early`: accumulator columns 0..191 (blk 0) are final once blk 0 has been issued, and A K-blocks 0..2 are dead once blk 1 has
+      // consumed its first six stages -> commit kBarAEarly there, so the epilogue drains K-blocks 0..2 of this layer's output (the
+      // first operands AND the accumulator columns of the next layer's blk 0) while blk 1 is still running.
       // `afree`: (layer 5) A K-block 0 is dead once blk 1 has consumed its first two stages; kBarAFree is committed there, so the
       // epilogue re-stages the positional encoding into K-block 0 while the rest of the hidden pass is still running.
-      auto run_pass = [&](auto n1_c, auto k16n_c, bool pe_pass, bool fresh_start, bool early, bool afree = false) {
+      auto run_pass = [&](auto k16n_c, bool pe_pass, bool fresh_start, bool early, bool afree = false) {
         constexpr int K16N = decltype(k16n_c)::value;
-        constexpr int NB0 = K16N / 4, NB1 = K16N / 2;
-        static_assert((NB0 + NB1) % kStages == 0, "a pass must use a whole number of ring wraps");
+        constexpr int NBH = K16N / 2;   // stages per block
+        static_assert((2 * NBH) % kStages == 0, "a pass must use a whole number of ring wraps");
+        using N192 = std::integral_constant<int, 192>;
+        using S2 = std::integral_constant<int, 2>;
 #pragma unroll
-        for (int i = 0; i < NB0; ++i) {
-          // blk 0 touches each A K-block first; its first UMMA overwrites columns 0..127 = K-blocks 0 and 1 of the previous
-          // accumulator, so both must have been drained before it is issued.
+        for (int i = 0; i < NBH; ++i) {
+          // blk 0's first UMMA overwrites columns 0..191 = K-blocks 0..2 of the previous accumulator: all three must have been
+          // drained before it is issued; K-blocks 3..5 are awaited when blk 0 first reads them (two stages per K-block).
           if (!pe_pass) {
-            if (i == 0) { wait_a(0); wait_a(1); }
-            else if (i >= 2) wait_a(i);
+            if (i == 0) { wait_a(0); wait_a(1); wait_a(2); }
+            else if (i >= 6 && (i & 1) == 0) wait_a(i >> 1);
           }
-          do_stage(std::integral_constant<int, 128>{}, std::integral_constant<int, 4>{}, i, 0u, 4 * i, fresh_start && i == 0);
-          if (PROF) { if (prof_on && K16N == 24 && i >= 1) args.prof[((size_t)prof_item * 10 + prof_layer) * 16 + 10 + i] = clock64(); }
+          do_stage(N192{}, S2{}, i, 0u, 2 * i, fresh_start && i == 0);
+          if (PROF) { if (prof_on && K16N == 24 && i >= 2 && (i & 1) == 1) args.prof[((size_t)prof_item * 10 + prof_layer) * 16 + 10 + (i >> 1)] = clock64(); }
         }
         if (PROF) { if (prof_on && K16N == 24) args.prof[((size_t)prof_item * 10 + prof_layer) * 16 + 10] = clock64(); }  // blk 0 issued
 #pragma unroll
-        for (int i = 0; i < NB1; ++i) {
-          do_stage(n1_c, std::integral_constant<int, 2>{}, NB0 + i, 128u, 2 * i, fresh_start && i == 0);
-          if (NB1 > 4 && i == 3 && early) umma_commit(bar(kBarA01Free));
-          if (NB1 > 4 && i == 1 && afree) umma_commit(bar(kBarAFree));
+        for (int i = 0; i < NBH; ++i) {
+          do_stage(N192{}, S2{}, NBH + i, 192u, 2 * i, fresh_start && i == 0);
+          if (K16N == 24 && i == 5 && early) umma_commit(bar(kBarAEarly));
+          if (K16N == 24 && i == 1 && afree) umma_commit(bar(kBarAFree));
         }
-        if (((NB0 + NB1) / kStages) & 1) wp ^= 1u;
+        if (((2 * NBH) / kStages) & 1) wp ^= 1u;
+      };
+      // last stage: one N = 208 block (192 RGB rows + density + pad), one K16 step per ring stage
+      auto run_last = [&]() {
+        using N208 = std::integral_constant<int, kL8N>;
+        using S1 = std::integral_constant<int, 1>;
+        static_assert(24 % kStages == 0, "a pass must use a whole number of ring wraps");
+#pragma unroll
+        for (int i = 0; i < 24; ++i) {
+          if (i == 0) { wait_a(0); wait_a(1); wait_a(2); wait_a(3); }   // columns 0..207 drained, K-blocks 0..3 staged
+          else if (i == 16) wait_a(4);
+          else if (i == 20) wait_a(5);
+          do_stage(N208{}, S1{}, i, 0u, i, i == 0);
+        }
+        if ((24 / kStages) & 1) wp ^= 1u;
       };
       using I4 = std::integral_constant<int, 4>;
       using I24 = std::integral_constant<int, 24>;
-      using N256 = std::integral_constant<int, 256>;
-      using N80 = std::integral_constant<int, 80>;
 
       for (int ci = cluster_id; ci < n_citems; ci += n_clusters) {
         if (PROF) {
@@ -386,28 +404,28 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
         // ---- layer 0: K = 64 (PE in K-block 0)
         stamp(0, 0);
         wait_a(0);
-        run_pass(N256{}, I4{}, true, true, false);
-        umma_commit(bar(kBarA01Free));
+        run_pass(I4{}, true, true, false);
+        umma_commit(bar(kBarAEarly));
         umma_commit(bar(kBarAccFull));
         stamp(0, 3);
         // ---- layers 1..7
 #pragma unroll 1
         for (int layer = 1; layer < 8; ++layer) {
           stamp(layer, 0);
-          run_pass(N256{}, I24{}, false, true, layer != 5, layer == 5);
+          run_pass(I24{}, false, true, layer != 5, layer == 5);
           if (layer == 5) {
             // skip connection: the PE columns of FeaExt_module_5 (models/mlp_nerf.py:106-107); the epilogue re-staged the tile's
             // PE into K-block 0 as soon as the hidden pass had finished reading that K-block (kBarAFree, committed inside the pass).
             wait_a(0);
-            run_pass(N256{}, I4{}, true, false, false);
-            umma_commit(bar(kBarA01Free));
+            run_pass(I4{}, true, false, false);
+            umma_commit(bar(kBarAEarly));
           }
           umma_commit(bar(kBarAccFull));
           stamp(layer, 3);
         }
         // ---- layer 8: [RGB_0*RGB_1 (192) | density (1) | pad] = N 128 + 80
         stamp(8, 0);
-        run_pass(N80{}, I24{}, false, true, false);
+        run_last();
         umma_commit(bar(kBarAccFull));
         stamp(8, 3);
       }
@@ -436,6 +454,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
       if (lane == 0) mbar_arrive(bar(kBarAReady + kb));
     };
     // one fence for two K-blocks (the fence is a MEMBAR.ALL.CTA: ~300 cycles with 8 warps storing)
+    auto release_kb_one = [&](int kb) {
+      tmem_wait_st();
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kBarAReady + kb));
+    };
     auto release_kb_pair = [&](int kb_even) {
       tmem_wait_st();
       fence_proxy_async_smem();
@@ -527,26 +552,28 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
           if (dump)
             for (int j = 0; j < 32; ++j) args.dbg[((size_t)(layer + 1) * kTile + row) * kHidden + kb * 64 + half * 32 + j] = v[j];
         };
-        // K-blocks 0,1: accumulator columns 0..127 are final and A K-blocks 0,1 are no longer read (kBarA01Free) while the rest of
+        // K-blocks 0..2: accumulator columns 0..191 are final and A K-blocks 0..2 are no longer read (kBarAEarly) while the rest of
         // the layer (blk 1) may still be running; the next layer's blk 0 can then start the moment this layer completes.
-        mbar_wait(bar(kBarA01Free), a01_phase);
+        mbar_wait(bar(kBarAEarly), a01_phase);
         a01_phase ^= 1;
         tc_fence_after_sync();
         drain_kb(0);
         drain_kb(1);
         release_kb_pair(0);
-        if (eprof) ep[layer * 16 + 8] = clock64();  // K-blocks 0..1 released
+        drain_kb(2);
+        release_kb_one(2);
+        if (eprof) ep[layer * 16 + 8] = clock64();  // K-blocks 0..2 released
         mbar_wait(bar(kBarAccFull), acc_phase);
         if (eprof) ep[layer * 16 + 7] = clock64();  // accumulator of `layer` complete
         acc_phase ^= 1;
         tc_fence_after_sync();
-#pragma unroll 1
-        for (int kb = 2; kb < kNumKB; ++kb) {
-          drain_kb(kb);
-          if (kb & 1) release_kb_pair(kb - 1);
-          if (eprof && kb == 5) ep[layer * 16 + 9] = clock64();  // all released
-          if (eprof && kb == 3 && layer > 0) ep[layer * 16 + 6] = clock64();
-        }
+        drain_kb(3);
+        release_kb_one(3);   // blk 0 of the next layer reads K-block 3 first
+        if (eprof && layer > 0) ep[layer * 16 + 6] = clock64();
+        drain_kb(4);
+        drain_kb(5);
+        release_kb_pair(4);
+        if (eprof) ep[layer * 16 + 9] = clock64();  // all released
         if (layer == 4) {
           // layer 5 = [hidden | PE] (skip connection, models/mlp_nerf.py:106-107): once the MMA warp has consumed the hidden
           // K-blocks, re-stage the tile's PE (from the stash) into K-block 0.
