@@ -15,6 +15,8 @@
 // Warp roles (288 threads, persistent, 1 CTA / SM): warps 0-7 convert (coalesced LDG.128 along pixels -> split -> swizzled
 // st.shared) into a 2-stage ring; warp 8 issues the UMMAs; warps 0-3 drain the accumulator at the end of an item.
 // HBM-bound by design (the operands are re-read once per tile/chunk pairing): algorithmic bytes are in DESIGN.md §3.5.
+#include <cuda.h>   // CUtensorMap (types only; the encoder comes through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "wgrad_tc.cuh"
@@ -22,29 +24,36 @@
 namespace gnrf {
 namespace tc {
 
-constexpr int kWgStages = 2;
-constexpr int kWgABytes = 32768;                 // [hi 16 KB | lo 16 KB], 128 rows
-constexpr int kWgBBytes = 65536;                 // [hi 32 KB | lo 32 KB], <= 256 rows
-constexpr int kWgStageBytes = kWgABytes + kWgBBytes;
-constexpr int kWgThreads = 288;
+constexpr int kWgTileBytes = 98304;              // bf16 operand tiles of one K-block: A [hi 16 KB | lo 16 KB] + B [hi 32 KB | lo 32 KB]
+constexpr int kWgABytes = 32768;
+constexpr int kWgStagBytes = 49152;              // fp32 staging of HALF a K-block: (128 + 256) rows x 32 px x 4 B; two slots
+constexpr int kWgThreads = 320;                  // warps 0-7 converters (0-3 also drain), 8 MMA, 9 TMA loader
 constexpr int kWgConvWarps = 8;
-constexpr int kWgMaxIter = (128 + 256) / 2 / kWgConvWarps;   // row pairs per converter warp and K-block
-constexpr int kWgBarFull = 0, kWgBarEmpty = kWgStages, kWgBarAccFull = 2 * kWgStages, kWgBarAccEmpty = kWgBarAccFull + 1,
-              kWgNumBars = kWgBarAccEmpty + 1;
-constexpr int kWgSmemBars = kWgStages * kWgStageBytes;
+constexpr int kWgMaxIter = (128 + 256) / 4 / kWgConvWarps;   // 4-row groups per converter warp and half K-block (12)
+constexpr int kWgBarStgFull = 0, kWgBarStgEmpty = 2, kWgBarTileFull = 4, kWgBarTileEmpty = 5, kWgBarAccFull = 6, kWgBarAccEmpty = 7,
+              kWgNumBars = 8;
+constexpr int kWgSmemStag = kWgTileBytes;
+constexpr int kWgSmemBars = kWgTileBytes + 2 * kWgStagBytes;
 constexpr int kWgSmemMisc = kWgSmemBars + kWgNumBars * 8;
 constexpr int kWgSmemBytes = kWgSmemMisc + 64 + 1024;
 
 struct WgradArgs {
-  const float* dY; long long dy_img_stride;
-  const float* X;  long long x_img_stride;
   int N_dy, K_x, rows_x;      // rows_x = K_x (+1 when the ones row is appended)
   int HW, n_img;
   int chunk_n, n_ch, n_mt, n_split, n_kb_total, n_items;
+  int pitch;                  // staging row pitch in bytes (= TMA box width * 4)
+  int rows_dy_box, rows_x_box, stage_tx_bytes;
   float* partial;             // [n_items][128][chunk_n]
 };
 
-__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradArgs args) {
+// Data path: a K-block (64 pixels) arrives as two HALF K-blocks (32 pixels).  For each half the loader warp issues two TMA tensor
+// loads (dY rows of the 128-row tile, X rows of the chunk; zero fill outside the tensors) into one of two fp32 staging slots; the
+// converter warps read a slot (ld.shared.v4), split to bf16 hi/lo in registers and release the slot at once -- so the TMA of the next
+// half is always in flight while the current one is converted (with a single staging block, or with per-thread LDGs, the load round
+// trip and the conversion were serialised: 5.9 K cycles per K-block against 1.25 K of UMMA work; profiles/r1_wgrad_tc_kernel.md).
+// When both halves are in registers the converters wait for the MMA warp to release the operand tiles and write them.
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradArgs args, const __grid_constant__ CUtensorMap dy_map,
+                                                                 const __grid_constant__ CUtensorMap x_map) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -54,7 +63,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradArgs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kWgStages; ++i) { mbar_init(bar(kWgBarFull + i), kWgConvWarps); mbar_init(bar(kWgBarEmpty + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(kWgBarStgFull + i), 1); mbar_init(bar(kWgBarStgEmpty + i), kWgConvWarps); }
+    mbar_init(bar(kWgBarTileFull), kWgConvWarps);
+    mbar_init(bar(kWgBarTileEmpty), 1);
     mbar_init(bar(kWgBarAccFull), 1);
     mbar_init(bar(kWgBarAccEmpty), 4);
     fence_mbar_init();
@@ -77,58 +88,77 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradArgs
 
   if (warp < kWgConvWarps) {
     // ======================================= converters (+ epilogue on warps 0-3) =======================================
-    const int half = lane >> 4, l16 = lane & 15;
-    const int n_pairs = (128 + args.chunk_n) >> 1;
-    const int n_iter = (n_pairs + kWgConvWarps - 1) / kWgConvWarps;
-    uint32_t slot = 0, phase = 0;
+    // Row assignment: in iteration u, the 8 lanes of quarter q = lane / 8 of warp w handle tile row  u*32 + lane_row  (lane_row =
+    // 4*w + q < 32), 4 pixels (16 B of the 128-B staging row) per lane: rows 0..127 (u < 4) are the dY tile, rows 128.. (u >= 4) the X
+    // chunk.  Everything that does not change from K-block to K-block is hoisted: per-iteration validity as bit masks (per item),
+    // shared-memory addresses as lane constants + u * (compile-time step).
+    const int q = lane >> 3, l8 = lane & 7;
+    const int lane_row = warp * 4 + q;
+    const int n_iter = (128 + args.chunk_n + 31) >> 5;
+    const uint32_t stag_lane = smem_base + kWgSmemStag + (uint32_t)l8 * 16u + (uint32_t)(lane_row * args.pitch);
+    const uint32_t stag_step = (uint32_t)(32 * args.pitch);
+    // tile byte offset of (row lane_row, pixels l8*4..+3 of half 0): 8 B at 16-byte chunk (l8 / 2) XOR (row & 7)
+    const uint32_t tile_row = smem_base + a_row_offset(lane_row);
+    const uint32_t sw = (uint32_t)lane_row & 7u;
+    uint32_t ph = 0;   // parity of the next completion of stg_full[h] / tile_empty (one K-block = one phase of each)
     int it = 0;
     for (int item = blockIdx.x; item < args.n_items; item += gridDim.x, ++it) {
       int img, mt, ch, kb0, kb1;
       decode(item, img, mt, ch, kb0, kb1);
       const int m0 = mt * 128, n0 = ch * args.chunk_n;
-      const float* dy_img = args.dY + (size_t)img * args.dy_img_stride;
-      const float* x_img = args.X + (size_t)img * args.x_img_stride;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        const int p = kb * 64 + l16 * 4;
-        const bool p_ok = p < args.HW;
-        // issue EVERY load of this K-block (<= 24 x 16 B per lane, ~96 KB per CTA in flight) before touching shared memory: the
-        // loads do not depend on the ring, only the stores below wait for the stage to be released by the MMA warp
-        float4 v[kWgMaxIter];
-#pragma unroll
-        for (int u = 0; u < kWgMaxIter; ++u) {
-          const int row = (u * kWgConvWarps + warp) * 2 + half;
-          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (u < n_iter && p_ok) {
-            if (row < 128) {
-              if (m0 + row < args.N_dy) v[u] = __ldg(reinterpret_cast<const float4*>(dy_img + (size_t)(m0 + row) * args.HW + p));
-            } else {
-              const int n = n0 + row - 128;
-              if (n < args.K_x) v[u] = __ldg(reinterpret_cast<const float4*>(x_img + (size_t)n * args.HW + p));
-              else if (n < args.rows_x) v[u] = make_float4(1.f, 1.f, 1.f, 1.f);   // the ones row -> bias gradient column
-            }
-          }
+      uint32_t ld_mask = 0u, one_mask = 0u, st_mask = 0u;
+      for (int u = 0; u < n_iter; ++u) {
+        const int row = u * 32 + lane_row;
+        if (row < 128) {
+          if (row < args.rows_dy_box && m0 + row < args.N_dy) ld_mask |= 1u << u;
+          st_mask |= 1u << u;
+        } else if (row < 128 + args.chunk_n) {
+          const int r = row - 128, n = n0 + r;
+          if (n < args.K_x && r < args.rows_x_box) ld_mask |= 1u << u;
+          else if (n >= args.K_x && n < args.rows_x) one_mask |= 1u << u;   // the ones row -> bias gradient column
+          st_mask |= 1u << u;
         }
-        mbar_wait(bar(kWgBarEmpty + slot), phase ^ 1);
-        const uint32_t stage = smem_base + slot * kWgStageBytes;
+      }
+      if (l8 * 16 >= args.pitch) ld_mask = one_mask = 0u;   // HW < 32: this lane's pixels lie beyond the (narrower) TMA box
+      for (int kb = kb0; kb < kb1; ++kb) {
+        uint32_t hw[2][kWgMaxIter][2], lw[2][kWgMaxIter][2];
 #pragma unroll
-        for (int u = 0; u < kWgMaxIter; ++u) {
-          const int row = (u * kWgConvWarps + warp) * 2 + half;
-          if (u < n_iter && row < 128 + args.chunk_n) {
-            uint32_t h0, l0, h1, l1;
-            split2(v[u].x, v[u].y, h0, l0);
-            split2(v[u].z, v[u].w, h1, l1);
-            const int r = row < 128 ? row : row - 128;
-            const uint32_t base = stage + (row < 128 ? 0u : (uint32_t)kWgABytes) + a_row_offset(r) +
-                                  ((((uint32_t)l16 >> 1) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)l16 & 1u) * 8u;
-            const uint32_t lo_off = row < 128 ? 16384u : 32768u;
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(base), "r"(h0), "r"(h1) : "memory");
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(base + lo_off), "r"(l0), "r"(l1) : "memory");
+        for (int h = 0; h < 2; ++h) {
+          const float one = (kb * 64 + h * 32 + l8 * 4 < args.HW) ? 1.0f : 0.0f;   // pixels past the end of the image contribute nothing
+          mbar_wait(bar(kWgBarStgFull + h), ph);
+#pragma unroll
+          for (int u = 0; u < kWgMaxIter; ++u) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((ld_mask >> u) & 1u)   // inside the tensors TMA zero-fills out-of-range pixels itself
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                           : "r"(stag_lane + (uint32_t)(h * kWgStagBytes) + (uint32_t)u * stag_step));
+            else if ((one_mask >> u) & 1u) v = make_float4(one, one, one, one);
+            split2(v.x, v.y, hw[h][u][0], lw[h][u][0]);
+            split2(v.z, v.w, hw[h][u][1], lw[h][u][1]);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(kWgBarStgEmpty + h));    // slot consumed: the loader refills it with the next K-block's half
+        }
+        mbar_wait(bar(kWgBarTileEmpty), ph ^ 1);                   // the MMAs of the previous K-block have read the operand tiles
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          // pixels h*32 + l8*4 .. +3 -> bytes h*64 + l8*8 of the 128-byte row: chunk (h*4 + l8/2) XOR sw, + (l8 & 1) * 8
+          const uint32_t col = ((((uint32_t)(h * 4) + ((uint32_t)l8 >> 1)) ^ sw) << 4) + ((uint32_t)l8 & 1u) * 8u;
+#pragma unroll
+          for (int u = 0; u < kWgMaxIter; ++u) {
+            if ((st_mask >> u) & 1u) {
+              // rows advance by 32 per iteration = 4 swizzle groups = 4096 B; u >= 4 continues in the B tile
+              const uint32_t base = tile_row + col + (u < 4 ? (uint32_t)(u * 4096) : (uint32_t)(kWgABytes + (u - 4) * 4096));
+              const uint32_t lo_off = u < 4 ? 16384u : 32768u;
+              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(base), "r"(hw[h][u][0]), "r"(hw[h][u][1]) : "memory");
+              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(base + lo_off), "r"(lw[h][u][0]), "r"(lw[h][u][1]) : "memory");
+            }
           }
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(kWgBarFull + slot));
-        if (++slot == kWgStages) { slot = 0; phase ^= 1; }
+        if (lane == 0) mbar_arrive(bar(kWgBarTileFull));
+        ph ^= 1;
       }
       if (warp < 4) {
         // drain: thread = accumulator row (dY channel), 32 columns at a time -> partial[item][row][col]
@@ -153,15 +183,47 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradArgs
         if (lane == 0) mbar_arrive(bar(kWgBarAccEmpty));
       }
     }
+  } else if (warp == 9) {
+    // ======================================= TMA loader: two tensor loads per K-block =======================================
+    if (lane == 0) {
+      uint32_t ph = 0;
+      const uint64_t dy_ptr = reinterpret_cast<uint64_t>(&dy_map), x_ptr = reinterpret_cast<uint64_t>(&x_map);
+      for (int item = blockIdx.x; item < args.n_items; item += gridDim.x) {
+        int img, mt, ch, kb0, kb1;
+        decode(item, img, mt, ch, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(bar(kWgBarStgEmpty + h), ph ^ 1);
+            mbar_arrive_expect_tx(bar(kWgBarStgFull + h), (uint32_t)args.stage_tx_bytes);
+            const uint32_t dst = smem_base + kWgSmemStag + (uint32_t)(h * kWgStagBytes);
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+                "l"(dy_ptr), "r"(kb * 64 + h * 32), "r"(mt * 128), "r"(img), "r"(bar(kWgBarStgFull + h))
+                : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                    dst + (uint32_t)(128 * args.pitch)),
+                "l"(x_ptr), "r"(kb * 64 + h * 32), "r"(ch * args.chunk_n), "r"(img), "r"(bar(kWgBarStgFull + h))
+                : "memory");
+          }
+          ph ^= 1;
+        }
+      }
+    }
+    __syncwarp();
   } else {
     // ======================================= MMA issuer =======================================
-    uint32_t slot = 0, phase = 0;
+    uint32_t ph = 0;
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t sbase_u = __shfl_sync(0xffffffffu, smem_base, 0);
     constexpr uint32_t kDescHiSw128 = (uint32_t)((1024 >> 4) | (1u << 14) | (2u << 29));
     constexpr uint32_t kDescLoLboSw = 1u << 16;
     auto mk = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
     const uint32_t idesc = umma_idesc_bf16(128, args.chunk_n);
+    const uint32_t a_hi0 = ((sbase_u >> 4) & 0x3FFFu) | kDescLoLboSw;
+    const uint32_t a_lo0 = a_hi0 + (16384 >> 4);
+    const uint32_t b_hi0 = a_hi0 + (kWgABytes >> 4);
+    const uint32_t b_lo0 = b_hi0 + (32768 >> 4);
     int it = 0;
     for (int item = blockIdx.x; item < args.n_items; item += gridDim.x, ++it) {
       int img, mt, ch, kb0, kb1;
@@ -169,12 +231,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradArgs
       mbar_wait(bar(kWgBarAccEmpty), (uint32_t)((it & 1) ^ 1));
       tc_fence_after_sync();
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(bar(kWgBarFull + slot), phase);
+        mbar_wait(bar(kWgBarTileFull), ph);
         tc_fence_after_sync();
-        const uint32_t a_hi0 = (((sbase_u + slot * kWgStageBytes) >> 4) & 0x3FFFu) | kDescLoLboSw;
-        const uint32_t a_lo0 = a_hi0 + (16384 >> 4);
-        const uint32_t b_hi0 = a_hi0 + (kWgABytes >> 4);
-        const uint32_t b_lo0 = b_hi0 + (32768 >> 4);
         if (elect_one()) {
 #pragma unroll
           for (int kl = 0; kl < 4; ++kl) {
@@ -186,10 +244,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradArgs
             umma_ss(tmem_u, a_lo, b_hi, idesc, 1u);
             umma_ss(tmem_u, a_hi, b_lo, idesc, 1u);
           }
-          umma_commit(bar(kWgBarEmpty + slot));
+          umma_commit(bar(kWgBarTileEmpty));
         }
         __syncwarp();
-        if (++slot == kWgStages) { slot = 0; phase ^= 1; }
+        ph ^= 1;
       }
       if (elect_one()) umma_commit(bar(kWgBarAccFull));
       __syncwarp();
@@ -233,6 +291,21 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int N_dy,
   }
 }
 
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TensorMapEncodeFn>(p);
+  }
+  return fn;
+}
+
 WgradPlan wgrad_plan(int N_dy, int K_x, int n_img, int HW, bool want_bias) {
   WgradPlan pl;
   pl.rows_x = K_x + (want_bias ? 1 : 0);
@@ -264,13 +337,38 @@ int wgrad_tc_launch(const float* dY, long long dy_img_stride, const float* X, lo
     return fail(GNRF_ERR_ARG, "wgrad_tc: HW and image strides must be multiples of 4 floats (vector loads)");
   WgradPlan pl = wgrad_plan(N_dy, K_x, n_img, HW, db_img != nullptr);
   if (ws_bytes < pl.partial_bytes) return fail(GNRF_ERR_ARG, "wgrad_tc: workspace %zu < required %zu bytes", ws_bytes, pl.partial_bytes);
+  if ((reinterpret_cast<uintptr_t>(dY) & 15) != 0 || (reinterpret_cast<uintptr_t>(X) & 15) != 0)
+    return fail(GNRF_ERR_ARG, "wgrad_tc: dY and X must be 16-byte aligned (TMA)");
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  if (enc == nullptr) return fail(GNRF_ERR_CUDA, "wgrad_tc: cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint32_t box_px = (cuuint32_t)(HW < 32 ? HW : 32);   // half a K-block per TMA load
+  const cuuint32_t box_dy = (cuuint32_t)(N_dy < 128 ? N_dy : 128), box_x = (cuuint32_t)(K_x < pl.chunk_n ? K_x : pl.chunk_n);
+  CUtensorMap dy_map, x_map;
+  {
+    const cuuint64_t gdim[3] = {(cuuint64_t)HW, (cuuint64_t)N_dy, (cuuint64_t)n_img};
+    const cuuint64_t gstr[2] = {(cuuint64_t)HW * 4, (cuuint64_t)dy_img_stride * 4};
+    const cuuint32_t box[3] = {box_px, box_dy, 1}, estr[3] = {1, 1, 1};
+    CUresult cr = enc(&dy_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(dY), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(GNRF_ERR_CUDA, "wgrad_tc: cuTensorMapEncodeTiled(dY) failed (%d)", (int)cr);
+  }
+  {
+    const cuuint64_t gdim[3] = {(cuuint64_t)HW, (cuuint64_t)K_x, (cuuint64_t)n_img};
+    const cuuint64_t gstr[2] = {(cuuint64_t)HW * 4, (cuuint64_t)x_img_stride * 4};
+    const cuuint32_t box[3] = {box_px, box_x, 1}, estr[3] = {1, 1, 1};
+    CUresult cr = enc(&x_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(X), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(GNRF_ERR_CUDA, "wgrad_tc: cuTensorMapEncodeTiled(X) failed (%d)", (int)cr);
+  }
   WgradArgs a;
-  a.dY = dY; a.dy_img_stride = dy_img_stride; a.X = X; a.x_img_stride = x_img_stride;
   a.N_dy = N_dy; a.K_x = K_x; a.rows_x = pl.rows_x; a.HW = HW; a.n_img = n_img;
   a.chunk_n = pl.chunk_n; a.n_ch = pl.n_ch; a.n_mt = pl.n_mt; a.n_split = pl.n_split; a.n_kb_total = pl.n_kb_total; a.n_items = pl.n_items;
+  a.pitch = (int)box_px * 4;
+  a.rows_dy_box = (int)box_dy; a.rows_x_box = (int)box_x;
+  a.stage_tx_bytes = (int)(box_px * 4 * (box_dy + box_x));
   a.partial = static_cast<float*>(ws);
   int grid = pl.n_items < n_sm ? pl.n_items : n_sm;
-  wgrad_tc_kernel<<<grid, kWgThreads, kWgSmemBytes, st>>>(a);
+  wgrad_tc_kernel<<<grid, kWgThreads, kWgSmemBytes, st>>>(a, dy_map, x_map);
   long long total = (long long)pl.n_mt * 128 * pl.n_ch * pl.chunk_n;
   wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a.partial, N_dy, K_x, pl.rows_x, n_img, pl.n_mt, pl.n_ch, pl.n_split,
                                                                      pl.chunk_n, accumulate, dW, db_img, db_sum);
