@@ -88,12 +88,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradArgs
 
   if (warp < kWgConvWarps) {
     // ======================================= converters (+ epilogue on warps 0-3) =======================================
-    // Row assignment: in iteration u, the 8 lanes of quarter q = lane / 8 of warp w handle tile row  u*32 + lane_row  (lane_row =
-    // 4*w + q < 32), 4 pixels (16 B of the 128-B staging row) per lane: rows 0..127 (u < 4) are the dY tile, rows 128.. (u >= 4) the X
+    // Row assignment: in iteration u, the 8 lanes of quarter q = lane / 8 of warp w handle tile row  u*32 + lane_row  (lane_row < 32,
+    // see below), 4 pixels (16 B of the 128-B staging row) per lane: rows 0..127 (u < 4) are the dY tile, rows 128.. (u >= 4) the X
     // chunk.  Everything that does not change from K-block to K-block is hoisted: per-iteration validity as bit masks (per item),
     // shared-memory addresses as lane constants + u * (compile-time step).
+    // The four rows of one warp instruction are r0, r0+2, r0+4, r0+6: with the SWIZZLE_128B chunk XOR (row & 7) the 64-byte half rows
+    // written by st.shared then fall into disjoint bank halves pairwise (2 wavefronts per 256 B; consecutive rows collided 4-way:
+    // ncu showed 50 % of all shared-memory wavefronts as bank conflicts).
     const int q = lane >> 3, l8 = lane & 7;
-    const int lane_row = warp * 4 + q;
+    const int lane_row = (warp >> 1) * 8 + (warp & 1) + 2 * q;
     const int n_iter = (128 + args.chunk_n + 31) >> 5;
     const uint32_t stag_lane = smem_base + kWgSmemStag + (uint32_t)l8 * 16u + (uint32_t)(lane_row * args.pitch);
     const uint32_t stag_step = (uint32_t)(32 * args.pitch);
