@@ -467,3 +467,27 @@ def test_full_gradients_other_shapes_vs_oracle(dev, B, S, n_s, mode, seed):
     tol = lambda k: max(2e-2 if (gp[k].numel() == 1 or "feat_upsample_list" in k) else TOL_GRAD, 3 * s_p)
     bad = {k: v for k, v in errs.items() if v >= tol(k)}
     assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:5]
+
+
+@gpu
+def test_train_path_forward_matches_fused_inference_full_size(dev):
+    """BASELINE config[1] size (64x64 rays x 64 samples -> 512x512, B = 1): the layer-wise differentiable forward and the fused
+    tcgen05 inference kernel are two independent implementations of the same graph; their images must agree to 1e-4."""
+    import gazenerf_b200 as G
+    from bench import synthetic_inputs
+    opt = G.BaseOptions()
+    torch.manual_seed(45)
+    net = G.GazeNeRFNet(opt, include_vd=False, hier_sampling=False).to(dev)
+    with torch.no_grad():   # non-vacuous density: scale the density heads, centre them roughly
+        for m in (net.fg_CD_predictor_face, net.fg_CD_predictor_eyes):
+            m.density_module.weight.mul_(30.0)
+            m.density_module.bias.fill_(0.5)
+    kw = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in synthetic_inputs(torch, G, opt, 1, 3).items()}
+    ju = torch.rand(1, 4096, 65, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    with torch.no_grad():
+        ref = net("train", **kw, jitter_u=ju)["coarse_dict"]          # fused inference kernels (no grad)
+    out = net("train", **kw, jitter_u=ju)["coarse_dict"]              # differentiable layer-wise path
+    assert out["merge_img"].grad_fn is not None and ref["merge_img"].grad_fn is None
+    for k in IMG_KEYS:
+        assert float((out[k].detach() - ref[k]).abs().max()) < 1e-4, k
+    assert float((ref["merge_img"] - ref["bg_img"]).abs().max()) > 0.05   # the head is actually visible
