@@ -125,22 +125,30 @@ __global__ void blur3x3_kernel(const float* __restrict__ in, int H, int Wd, long
 }
 
 // rgb[n][j][p] = sum_c W[j][c] net[n][c][p] + b[j] (+ prev[n][j][p]); optional sigmoid (neural_renderer.py:100,106,110).
-__global__ void to_rgb_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ net, int C,
-                              int HW, const float* __restrict__ prev, int do_sigmoid, float* __restrict__ rgb) {
-  extern __shared__ float s_w[];  // [3][C]
+// block = 64 pixels x 4 channel groups (the 64x64 feature map has only 4096 pixels per image: one thread per pixel left most SMs idle)
+__global__ void __launch_bounds__(256) to_rgb_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ net,
+                                                     int C, int HW, const float* __restrict__ prev, int do_sigmoid, float* __restrict__ rgb) {
+  extern __shared__ float s_w[];  // [3][C] weights, then [4][64][3] partial sums
+  float* s_part = s_w + 3 * C;
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_w[i] = W[i];
   __syncthreads();
-  int n = blockIdx.y;
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= HW) return;
-  const float* x = net + (size_t)n * C * HW + p;
+  const int n = blockIdx.y;
+  const int px = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int p = blockIdx.x * 64 + px;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-  for (int c = 0; c < C; ++c) {
-    float v = x[(size_t)c * HW];
-    a0 = fmaf(s_w[c], v, a0);
-    a1 = fmaf(s_w[C + c], v, a1);
-    a2 = fmaf(s_w[2 * C + c], v, a2);
+  if (p < HW) {
+    const float* x = net + (size_t)n * C * HW + p;
+    for (int c = grp; c < C; c += 4) {
+      float v = x[(size_t)c * HW];
+      a0 = fmaf(s_w[c], v, a0);
+      a1 = fmaf(s_w[C + c], v, a1);
+      a2 = fmaf(s_w[2 * C + c], v, a2);
+    }
   }
+  s_part[(grp * 64 + px) * 3 + 0] = a0; s_part[(grp * 64 + px) * 3 + 1] = a1; s_part[(grp * 64 + px) * 3 + 2] = a2;
+  __syncthreads();
+  if (grp != 0 || p >= HW) return;
+  for (int g = 1; g < 4; ++g) { a0 += s_part[(g * 64 + px) * 3 + 0]; a1 += s_part[(g * 64 + px) * 3 + 1]; a2 += s_part[(g * 64 + px) * 3 + 2]; }
   float r[3] = {a0 + bias[0], a1 + bias[1], a2 + bias[2]};
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
@@ -343,8 +351,8 @@ static int nr_forward_bufs(const float* const* params, const unsigned char* pack
   for (int i = 0; i < 8 * n_blocks + 2; ++i) GNRF_CHECK_ARG(params[i] != nullptr);
 
   auto launch_rgb = [&](const float* w, const float* b, const float* net, int Cn, int HW, const float* prev, int sig, float* dst) {
-    dim3 grid(ceil_div(HW, 256), N);
-    to_rgb_kernel<<<grid, 256, 3 * Cn * sizeof(float), st>>>(w, b, net, Cn, HW, prev, sig, dst);
+    dim3 grid(ceil_div(HW, 64), N);
+    to_rgb_kernel<<<grid, 256, (3 * Cn + 4 * 64 * 3) * sizeof(float), st>>>(w, b, net, Cn, HW, prev, sig, dst);
   };
   auto launch_up = [&](const float* src, int H, float* dst) {
     long long total = (long long)N * 3 * 4 * H * H;
