@@ -339,7 +339,32 @@ def main():
     dev_kw = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host_kw.items()}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def step(kw):
+    # N > 1: the all-gather of the rendered images is fused into the last neural-render kernel (multimem.st over the NVSwitch multicast
+    # address / peer stores over NVLink + one device barrier per step, gazenerf_b200/dist.py PeerAllGather); NCCL is the fallback when
+    # symmetric memory cannot be set up (and for the hierarchical workload, which renders two image sets)
+    peer, gather_mode = None, "single GPU"
+    if world > 1:
+        gather_mode = "batch-sharded, one NCCL all-gather of the rendered images per step"
+        if not hier:
+            try:
+                from gazenerf_b200.dist import PeerAllGather
+                peer = PeerAllGather(F, opt.pred_img_size, dev)
+                gather_mode = ("batch-sharded; all-gather fused into the last neural-render kernel (%s) + one device barrier per step"
+                               % ("multimem.st via NVSwitch multicast" if peer.use_multicast else "peer stores over NVLink"))
+            except Exception as e:  # noqa: BLE001 - any rendezvous failure -> plain NCCL
+                peer = None
+                gather_mode += " (symmetric memory unavailable: %s)" % str(e)[:80]
+
+    def step(kw, pre_finish=None):
+        if peer is not None:
+            net.gather_ctx = peer
+            local = net("test", **kw)["coarse_dict"]
+            net.gather_ctx = None
+            if pre_finish is not None:
+                pre_finish()
+            out = peer.finish()
+            out["bg_img"] = local["bg_img"]
+            return out
         out = net("test", **kw)
         out = out["fine_dict"] if hier else out["coarse_dict"]
         if world > 1:
@@ -355,6 +380,16 @@ def main():
         for _ in range(args.warmup):
             step(dev_kw)
         barrier()
+        if peer is not None:
+            # one-time check of the fused gather against the NCCL all-gather of the same local images
+            net.gather_ctx = peer
+            local = net("test", **dev_kw)["coarse_dict"]
+            net.gather_ctx = None
+            fused = {k: v.clone() for k, v in peer.finish().items()}
+            ref = all_gather_images(local, world * F)
+            for k in fused:
+                assert torch.equal(fused[k], ref[k]), "fused all-gather mismatch on %s (rank %d)" % (k, rank)
+            barrier()
         # ---------------- device-resident timing: K steps, L2 flushed (untimed) between steps, CUDA events per step
         net.mlp_events = []
         sampler = ClockSampler(local_rank)
@@ -391,9 +426,13 @@ def main():
         copy_stream = torch.cuda.Stream(device=dev)
         main_stream = torch.cuda.current_stream()
 
+        copied = [None]   # event: the previous step's D2H has drained its (symmetric) source buffer
+
         def e2e_step(i):
             kw = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in pinned.items()}
-            out = step(kw)
+            # fused gather: peers rewrite the buffer of step i-1 once they pass the barrier of step i+1 -> my D2H of step i-1 must be
+            # complete before I enter this step's barrier
+            out = step(kw, pre_finish=(lambda: main_stream.wait_event(copied[0])) if (peer is not None and copied[0] is not None) else None)
             done = torch.cuda.Event()
             done.record(main_stream)
             with torch.cuda.stream(copy_stream):
@@ -401,6 +440,9 @@ def main():
                 for k, v in out.items():
                     host_out[i & 1][k].copy_(v, non_blocking=True)
                     v.record_stream(copy_stream)
+                ev_c = torch.cuda.Event()
+                ev_c.record(copy_stream)
+            copied[0] = ev_c
 
         for i in range(2):
             e2e_step(i)
@@ -436,7 +478,7 @@ def main():
             "config": {"workload": WORKLOAD if not hier else "config[2]: hierarchical coarse(64)+fine(64) sampling at 512x512 (FineSample path), face+eye branches",
                        "faces_per_gpu_per_step": F, "rays": N_RAYS, "samples_per_ray": N_SAMPLES, "mlp_impl": args.mlp_impl,
                        "weights": "reference init, torch.manual_seed(45)", "l2": "256 MiB memset between timed steps (untimed)",
-                       "multi_gpu": "batch-sharded, one all-gather of the rendered images per step" if world > 1 else "single GPU"},
+                       "multi_gpu": gather_mode},
             "roofline": {"bound": "tensor", "kernel": ("whole step: coarse + fine mlp_tc_kernel launches, fine_depths, 2x neural renderer" if hier else "mlp_tc_kernel (+fold, rgb_head)") if args.mlp_impl == "tc" else "mlp_simt_kernel+composite",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": "%s bf16 dense, sustained (kernel timed inside a long step)" % peaks["src"],

@@ -161,6 +161,18 @@ __global__ void __launch_bounds__(256) to_rgb_kernel(const float* __restrict__ W
 }
 
 
+// Fused all-gather of the rendered images (multi-GPU batch sharding, SURVEY §8e / BASELINE config 3): the kernel that produces the
+// final RGB values also stores them into every rank's gathered buffer [3 keys][global batch][3][P*P] -- one multimem.st through the
+// NVSwitch multicast address (NVLS) when available, else one st.global per peer over NVLink -- so no separate collective runs.
+struct GatherDst {
+  float* mc;         // multicast base of the symmetric buffer (nullptr: use peer[])
+  float* peer[8];    // every rank's buffer mapped into this process (peer[rank] = own)
+  int world, rank, b_local, gb;
+};
+__device__ __forceinline__ void multimem_st_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // net = LeakyReLU(Blur(pre)) and rgb = rgb_prev + feat_2_rgb(net) (+ sigmoid) in one pass.
 // Used after an UN-activated feat conv: Blur (depthwise, weights sum to 1, reflect border) commutes with the 1x1 conv and its bias,
 // so LeakyReLU(conv(Blur(x))) == LeakyReLU(Blur(conv(x)))  (neural_renderer.py:103-106, pixel_shuffle_upsample.py:7-16, 41).
@@ -168,7 +180,7 @@ __global__ void __launch_bounds__(256) to_rgb_kernel(const float* __restrict__ W
 __global__ void __launch_bounds__(256) blur_lrelu_rgb_kernel(const float* __restrict__ pre, int C, int H, int Wd,
                                                             const float* __restrict__ rgb_w, const float* __restrict__ rgb_b,
                                                             const float* __restrict__ rgb_prev, int do_sigmoid,
-                                                            float* __restrict__ net, float* __restrict__ rgb) {
+                                                            float* __restrict__ net, float* __restrict__ rgb, const GatherDst gd) {
   extern __shared__ float s_w[];  // [3][C]
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_w[i] = rgb_w[i];
   __syncthreads();
@@ -227,6 +239,16 @@ __global__ void __launch_bounds__(256) blur_lrelu_rgb_kernel(const float* __rest
       for (int i = 0; i < 4; ++i) v[i] = 1.0f / (1.0f + expf(-v[i]));
     }
     *reinterpret_cast<float4*>(rgb + o) = make_float4(v[0], v[1], v[2], v[3]);
+    if (gd.world > 1 && n < 3 * gd.b_local) {
+      // local image n = key * b_local + face  ->  gathered [key][rank * b_local + face][3][HW]
+      const int key = n / gd.b_local, face = n - key * gd.b_local;
+      const size_t og = (((size_t)key * gd.gb + (size_t)gd.rank * gd.b_local + face) * 3 + j) * HW + (size_t)y * Wd + x0;
+      if (gd.mc != nullptr) {
+        multimem_st_v4(gd.mc + og, v[0], v[1], v[2], v[3]);
+      } else {
+        for (int pr = 0; pr < gd.world; ++pr) *reinterpret_cast<float4*>(gd.peer[pr] + og) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
   }
 }
 
@@ -306,6 +328,7 @@ struct NrBufs {
   float* t1[8]; float* sh[8]; float* net[8];
   float* bl; float* rgb_a; float* rgb_b;
   bool keep_last;   // write the last level's activation (needed by the backward only)
+  GatherDst gather; // world <= 1: no fused all-gather
 };
 
 static int nr_forward_bufs(const float* const* params, const unsigned char* packed, const float* featmap, int N, int C, int S, int n_blocks,
@@ -313,7 +336,8 @@ static int nr_forward_bufs(const float* const* params, const unsigned char* pack
 
 // packed == nullptr: fp32 CUDA-core GEMMs; else: tcgen05 bf16x3 GEMMs on the packed weight streams (3 layers per block)
 static int nr_forward(const float* const* params, const unsigned char* packed, const float* featmap, int N, int C, int S, int n_blocks,
-                      int min_feat, float* img, void* workspace, size_t workspace_bytes, gnrf_stream_t stream) {
+                      int min_feat, float* img, void* workspace, size_t workspace_bytes, gnrf_stream_t stream,
+                      const GatherDst* gather = nullptr) {
   GNRF_CHECK_ARG(params && featmap && img && workspace);
   GNRF_CHECK_ARG(N > 0 && C > 0 && S >= 2 && n_blocks >= 1 && n_blocks <= 6);
   GNRF_CHECK_ARG(S % 4 == 0);
@@ -332,6 +356,7 @@ static int nr_forward(const float* const* params, const unsigned char* packed, c
   bufs.rgb_a = reinterpret_cast<float*>(ws + pl.rgb_a);
   bufs.rgb_b = reinterpret_cast<float*>(ws + pl.rgb_b);
   bufs.keep_last = false;
+  bufs.gather = gather ? *gather : GatherDst{};
   return nr_forward_bufs(params, packed, featmap, N, C, S, n_blocks, min_feat, img, bufs, as_stream(stream));
 }
 
@@ -404,7 +429,8 @@ static int nr_forward_bufs(const float* const* params, const unsigned char* pack
       dim3 grid(ceil_div(HW / 4, 256), N);
       // the last level's activation is consumed only by the fused to-RGB head: not written unless the caller keeps it (training)
       blur_lrelu_rgb_kernel<<<grid, 256, 3 * co * sizeof(float), st>>>(bl, co, s, s, rgb_w(i + 1), rgb_bi(i + 1), rgb_up, last ? 1 : 0,
-                                                                      (last && !bufs.keep_last) ? nullptr : net_out, last ? img : rgb_cur);
+                                                                      (last && !bufs.keep_last) ? nullptr : net_out, last ? img : rgb_cur,
+                                                                      last ? bufs.gather : GatherDst{});
       count_launches(1);
     } else {
       {
@@ -523,6 +549,25 @@ extern "C" int gnrf_nr_train_fwd(const float* const* params, const void* packed,
   bufs.rgb_a = reinterpret_cast<float*>(ws + pl.rgb_a);
   bufs.rgb_b = reinterpret_cast<float*>(ws + pl.rgb_b);
   bufs.keep_last = true;
+  bufs.gather = GatherDst{};
   return nr_forward_bufs(params, static_cast<const unsigned char*>(packed), featmap, N, C, S, n_blocks, min_feat, img, bufs,
                          as_stream(stream));
+}
+
+// Same as gnrf_neural_render_tc_fwd, plus the fused all-gather of the first 3 * b_local images (see GatherDst): peer_ptrs = HOST array of
+// `world` device pointers (every rank's symmetric buffer [3][gb][3][P*P] mapped into this process), mc_ptr = its multicast address or NULL.
+// The caller orders buffer reuse / consumption across ranks (gazenerf_b200/dist.py: double buffering + a device barrier per step).
+extern "C" int gnrf_neural_render_tc_fwd_gather(const float* const* params, const void* packed, const float* featmap, int N, int C, int S,
+                                                int n_blocks, int min_feat, float* img, void* workspace, size_t workspace_bytes,
+                                                float* const* peer_ptrs, float* mc_ptr, int world, int rank, int b_local, int gb,
+                                                gnrf_stream_t stream) {
+  GNRF_CHECK_ARG(packed && peer_ptrs);
+  GNRF_CHECK_ARG(world >= 2 && world <= 8 && rank >= 0 && rank < world && b_local >= 1 && gb == world * b_local && N >= 3 * b_local);
+  GatherDst gd;
+  gd.mc = mc_ptr;
+  for (int i = 0; i < 8; ++i) gd.peer[i] = i < world ? peer_ptrs[i] : nullptr;
+  for (int i = 0; i < world; ++i) GNRF_CHECK_ARG(gd.peer[i] != nullptr);
+  gd.world = world; gd.rank = rank; gd.b_local = b_local; gd.gb = gb;
+  return nr_forward(params, static_cast<const unsigned char*>(packed), featmap, N, C, S, n_blocks, min_feat, img, workspace,
+                    workspace_bytes, stream, &gd);
 }

@@ -53,12 +53,54 @@ def all_gather_images(local: Dict[str, torch.Tensor], global_batch: int, group=N
     return out
 
 
+class PeerAllGather(object):
+    """All-gather of the rendered images FUSED into the kernel that writes them (include/gnrf.h, gnrf_neural_render_tc_fwd_gather).
+
+    Every rank owns two symmetric buffers [3 keys][global_batch][3][P][P] (torch symmetric memory: each rank's buffer is mapped into
+    every process; an NVSwitch multicast address covers all of them).  The last neural-render kernel stores each RGB value once to
+    the multicast address (``multimem.st``, NVLS) -- or once per peer over NVLink when multicast is unavailable -- so the whole batch
+    materialises on every GPU without a separate collective.  ``finish()`` runs one device-side barrier (signal pads) on the current
+    stream and returns views of the gathered images.  Two buffers alternate per step: a rank can only be one barrier ahead of its
+    slowest peer, so a peer's reads of step i (stream-ordered before its step i+1) are complete before anyone rewrites that buffer
+    in step i+2.
+    """
+
+    def __init__(self, b_local: int, img_size: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if not 2 <= self.world <= 8:
+            raise RuntimeError("PeerAllGather supports 2..8 ranks of one NVLink / NVSwitch domain")
+        self.b_local, self.gb, self.P = b_local, b_local * self.world, img_size
+        shape = (3, self.gb, 3, img_size, img_size)
+        self.bufs = [symm.empty(shape, dtype=torch.float32, device=device) for _ in range(2)]
+        self.hdls = [symm.rendezvous(b, group) for b in self.bufs]
+        self.use_multicast = all(int(h.multicast_ptr) != 0 for h in self.hdls)
+        self.step = 0
+
+    def current(self):
+        """(peer pointers, multicast pointer or 0) of the buffer the CURRENT step writes."""
+        h = self.hdls[self.step & 1]
+        return [int(p) for p in h.buffer_ptrs], (int(h.multicast_ptr) if self.use_multicast else 0)
+
+    def finish(self) -> Dict[str, torch.Tensor]:
+        """Device barrier across the ranks (on the current stream), then views of this step's gathered images."""
+        i = self.step & 1
+        self.hdls[i].barrier(channel=0)
+        self.step += 1
+        buf = self.bufs[i]
+        return {"merge_img_face": buf[0], "merge_img_eyes": buf[1], "merge_img": buf[2]}
+
+
 class BatchShardedRenderer(object):
     """net("test", **global_kwargs) over a process group: each rank renders its slice, one all-gather returns the batch."""
 
-    def __init__(self, net, group=None):
+    def __init__(self, net, group=None, fused_gather: bool = False):
         self.net = net
         self.group = group
+        self.fused_gather = fused_gather   # gather inside the last neural-render kernel (PeerAllGather) instead of NCCL
+        self._peer: Optional[PeerAllGather] = None
 
     @torch.no_grad()
     def __call__(self, mode: str, **kwargs) -> Dict[str, Dict[str, torch.Tensor]]:
@@ -67,5 +109,18 @@ class BatchShardedRenderer(object):
             return self.net(mode, **kwargs)
         rank = dist.get_rank(self.group)
         gb = kwargs["batch_xy"].shape[0]
-        local = self.net(mode, **shard_inputs(kwargs, rank, world))
+        mine = shard_inputs(kwargs, rank, world)
+        b_local = mine["batch_xy"].shape[0]
+        if self.fused_gather and gb == b_local * world:
+            if self._peer is None or self._peer.b_local != b_local:
+                self._peer = PeerAllGather(b_local, self.net.pred_img_size, mine["batch_xy"].device, self.group)
+            self.net.gather_ctx = self._peer
+            try:
+                local = self.net(mode, **mine)
+            finally:
+                self.net.gather_ctx = None
+            out = self._peer.finish()
+            out["bg_img"] = local["coarse_dict"]["bg_img"]
+            return {"coarse_dict": out}
+        local = self.net(mode, **mine)
         return {"coarse_dict": all_gather_images(local["coarse_dict"], gb, self.group)}

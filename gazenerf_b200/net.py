@@ -156,7 +156,9 @@ def _ptrs(tensors: List[torch.Tensor]):
     return _lib.ptr_array([t.data_ptr() for t in tensors])
 
 
-def neural_render(nr: NeuralRendererParams, x: torch.Tensor) -> torch.Tensor:
+def neural_render(nr: NeuralRendererParams, x: torch.Tensor, gather=None) -> torch.Tensor:
+    """``gather``: a dist.PeerAllGather -- the first 3 * b_local images are also stored into every rank's gathered buffer by the
+    kernel that produces them (fused all-gather over NVLink / NVSwitch multicast)."""
     L = _lib.lib()
     x = _dev_f32(x, "featmap")
     n, c, s, _ = x.shape
@@ -165,7 +167,16 @@ def neural_render(nr: NeuralRendererParams, x: torch.Tensor) -> torch.Tensor:
     ws_bytes = L.gnrf_nr_workspace_bytes(n, c, s, nr.n_blocks, nr.min_feat)
     ws = torch.empty((ws_bytes,), device=x.device, dtype=torch.uint8)
     params = [p.detach() for p in nr.param_list()]
-    if nr.impl == "tc":
+    if gather is not None:
+        if nr.impl != "tc":
+            raise RuntimeError("the fused all-gather is part of the tcgen05 neural-render path (impl='tc')")
+        peers, mc = gather.current()
+        assert n >= 3 * gather.b_local and P == gather.P
+        packed = nr.packed_tc()
+        _lib.check(L.gnrf_neural_render_tc_fwd_gather(_ptrs(params), packed.data_ptr(), x.data_ptr(), n, c, s, nr.n_blocks, nr.min_feat,
+                                                      img.data_ptr(), ws.data_ptr(), ws_bytes, _lib.ptr_array(peers), mc or None, gather.world,
+                                                      gather.rank, gather.b_local, gather.gb, _stream()), "gnrf_neural_render_tc_fwd_gather")
+    elif nr.impl == "tc":
         packed = nr.packed_tc()
         _lib.check(L.gnrf_neural_render_tc_fwd(_ptrs(params), packed.data_ptr(), x.data_ptr(), n, c, s, nr.n_blocks, nr.min_feat,
                                                img.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "gnrf_neural_render_tc_fwd")
@@ -217,6 +228,8 @@ class GazeNeRFNet(nn.Module):
         # is cached per parameter version instead of being re-rendered on every call (set False to re-render every call).
         self.cache_bg_img = True
         self._bg_cache: Optional[Tuple[tuple, torch.Tensor]] = None
+        # multi-GPU: when set (dist.BatchShardedRenderer / bench.py), the coarse images are all-gathered by the kernel that writes them
+        self.gather_ctx = None
 
     # ------------------------------------------------------------------ helpers
     def _tc_supported(self, n_s: int) -> bool:
@@ -305,7 +318,8 @@ class GazeNeRFNet(nn.Module):
                 if self.cache_bg_img:
                     self._bg_cache = (key, bg_img.clone())
             return {"merge_img": imgs[:B], "bg_img": bg_img}
-        imgs = neural_render(self.neural_render, fm)  # ONE batched call over [face | eyes | merge (| bg)]
+        gather = self.gather_ctx if (self.gather_ctx is not None and not self.hier_sampling) else None
+        imgs = neural_render(self.neural_render, fm, gather=gather)  # ONE batched call over [face | eyes | merge (| bg)]
         if bg_img is None:
             bg_img = imgs[3 * B:]
             if self.cache_bg_img:

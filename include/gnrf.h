@@ -141,6 +141,18 @@ int gnrf_neural_render_tc_fwd(const float* const* params, const void* packed, co
                               int n_blocks, int min_feat, float* img, void* workspace, size_t workspace_bytes,
                               gnrf_stream_t stream);
 
+/* Multi-GPU batch sharding (one process per GPU): gnrf_neural_render_tc_fwd with the all-gather of the rendered images FUSED into
+ * the kernel that produces them.  The first 3 * b_local images of the batch (merge_img_face | merge_img_eyes | merge_img of this
+ * rank's faces) are also stored into every rank's gathered buffer [3][gb][3][P*P] -- through the NVSwitch multicast address
+ * (multimem.st, NVLS) when mc_ptr != NULL, else with one store per peer over NVLink.  peer_ptrs: HOST array of `world` device
+ * pointers (each rank's symmetric buffer mapped into this process).  Cross-rank ordering (buffer reuse, consumption) is the caller's:
+ * gazenerf_b200/dist.py double-buffers and runs one device barrier per step.  Replaces the all-gather a multi-GPU caller of
+ * GazeNeRFNet.forward would issue (the reference is single-GPU, trainer/base.py:31-35). */
+int gnrf_neural_render_tc_fwd_gather(const float* const* params, const void* packed, const float* featmap, int N, int C, int S,
+                                     int n_blocks, int min_feat, float* img, void* workspace, size_t workspace_bytes,
+                                     float* const* peer_ptrs, float* mc_ptr, int world, int rank, int b_local, int gb,
+                                     gnrf_stream_t stream);
+
 /* =========================================================================================================
  * Training path (forward that keeps activations + backward).  The reference gets its gradients from torch
  * autograd over the same graph (train.py -> trainer/gazenerf_trainer.py:479-528, loss.backward()); these entry
