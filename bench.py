@@ -56,7 +56,7 @@ class ClockSampler(object):
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -84,6 +84,19 @@ class ClockSampler(object):
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def keep_load_for_sampler(torch, dist, world, dev, ms_per_step, run_step, min_seconds=1.0):
+    """The timed region of the default run lasts ~60 ms, shorter than nvidia-smi's start-up + sampling period: keep running the SAME
+    step (untimed, after the timed region has been closed) until the sampler has had `min_seconds` of this load to look at.  The
+    number of trailing steps is decided by rank 0 and broadcast so that every rank issues the same collectives."""
+    n = torch.tensor([max(0, int(min_seconds * 1e3 / max(ms_per_step, 1e-3)) + 1)], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.broadcast(n, src=0)
+    for _ in range(int(n.item())):
+        run_step()
+    torch.cuda.synchronize()
+    return int(n.item())
 
 
 def synthetic_inputs(torch, G, opt, faces, seed, device="cpu"):
@@ -224,7 +237,10 @@ def run_train(args, torch, G, rank, local_rank, world, dev, dist):
         ev[i][1].record()
     barrier()
     launches = (L.gnrf_launch_count() - launches0) // max(args.steps, 1)
+    tail = keep_load_for_sampler(torch, dist, world, dev, sum(a.elapsed_time(b) for a, b in ev) / max(args.steps, 1), lambda: step(dev_kw, dev_tg))
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "timed steps + %d identical untimed trailing steps" % tail
     total_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -409,10 +425,13 @@ def main():
             ev[i][1].record()
         barrier()
         launches = (L.gnrf_launch_count() - launches0) // max(args.steps, 1)
-        clocks = sampler.stop() if rank == 0 else None
         step_ms = [a.elapsed_time(b) for a, b in ev]
         mlp_ms = [a.elapsed_time(b) for a, b in net.mlp_events]
         net.mlp_events = None
+        tail = keep_load_for_sampler(torch, dist if world > 1 else None, world, dev, sum(step_ms) / max(args.steps, 1), lambda: step(dev_kw))
+        clocks = sampler.stop() if rank == 0 else None
+        if clocks is not None:
+            clocks["window"] = "timed steps + %d identical untimed trailing steps" % tail
         total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
         mlp_avg = torch.tensor([sum(mlp_ms) / max(len(mlp_ms), 1)], device=dev, dtype=torch.float64)
         if world > 1:
