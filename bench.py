@@ -442,10 +442,20 @@ def main():
         # ---------------- end-to-end: pinned host inputs -> H2D -> forward -> D2H of the four images, every step.
         # The D2H of step i (12.6 MB per face) runs on a copy stream behind an event and overlaps the compute of step i+1
         # (double-buffered pinned host images); every step's result still reaches the host inside the timed region.
-        out0 = step(dev_kw)
+        # N > 1: the gathered batch is identical on every rank and all ranks share one host, so each rank copies ITS faces' slice
+        # (and rank 0 the rank-independent bg_img): the host receives every image of the batch exactly once per step
+        def host_part(out):
+            if world == 1:
+                return out
+            part = {k: v[rank * F:(rank + 1) * F] for k, v in out.items() if k != "bg_img"}
+            if rank == 0:
+                part["bg_img"] = out["bg_img"]
+            return part
+
+        out0 = host_part(step(dev_kw))
         host_out = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out0.items()} for _ in range(2)]
         h2d = sum(v.numel() * v.element_size() for v in pinned.values() if torch.is_tensor(v))
-        d2h = sum(v.numel() * v.element_size() for v in host_out[0].values())
+        d2h = sum(v.numel() * v.element_size() for v in host_out[0].values())   # this rank's share (rank 0: + bg_img)
         copy_stream = torch.cuda.Stream(device=dev)
         main_stream = torch.cuda.current_stream()
 
@@ -460,7 +470,7 @@ def main():
             done.record(main_stream)
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(done)
-                for k, v in out.items():
+                for k, v in host_part(out).items():
                     host_out[i & 1][k].copy_(v, non_blocking=True)
                     v.record_stream(copy_stream)
                 ev_c = torch.cuda.Event()
@@ -511,7 +521,8 @@ def main():
                          "kernel_ms": mlp_ms, "algorithmic_flop_per_launch": algo_flop,
                          "executed_mma_tflops": exec_tflops, "executed_frac": exec_tflops / peak,
                          "note": "achieved = reference-as-written FLOPs (3 030 144/point/branch) / time; executed = bf16x3 UMMA FLOPs after exact folds"},
-            "e2e": {"value": faces_total / e2e_s, "unit": "faces/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": faces_total / e2e_s, "unit": "faces/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "per rank; with N > 1 every rank copies its own faces of the gathered batch, so the host receives each image once"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
