@@ -114,3 +114,53 @@ def test_cpu_tensors_fail_loudly():
     s, a, gz = O.synthetic_codes(1)
     with pytest.raises(RuntimeError, match="CUDA"):
         net("test", ru.ray_xy, ru.ray_uv, None, s, a, gz, **ru.base_cam_info)
+
+
+def test_abi_argument_checks_fail_cleanly_without_a_gpu():
+    """Entry points validate their arguments before touching the device: status code + gnrf_last_error(), never an abort."""
+    L = G.lib()
+    assert L.gnrf_conv_tc(None, 0, 0, None, 0, None, None, 0, 0, None, 0, 0, 0.0, None, 0, 0, 1, 1, None) == 1   # GNRF_ERR_ARG
+    assert b"gnrf_conv_tc" in L.gnrf_last_error()
+    assert L.gnrf_wgrad_tc(None, 0, None, 0, 4, 4, 1, 64, None, None, 0, 0, None, 0, None) == 1
+    assert L.gnrf_compose_bwd(*([None] * 7), 1, 3, 4, *([None] * 6), None) == 1
+    assert L.gnrf_neural_render_tc_fwd_gather(None, None, None, 4, 258, 8, 3, 32, None, None, 0, None, None, 2, 0, 1, 2, None) == 1
+    assert L.gnrf_data_loss_fwd(*([None] * 9), 1, 64, 1, 1.0, None, None, None, None) == 1
+    assert L.gnrf_conv_tc_packed_bytes(384, 384) > 2 * 384 * 384 * 2 and L.gnrf_conv_tc_packed_bytes(0, 4) == 0
+    assert L.gnrf_wgrad_tc_workspace_bytes(384, 384, 2, 262144) >= 128 * 208 * 4
+    assert L.gnrf_nr_train_saved_bytes(7, 258, 64, 3, 32) > 0 and L.gnrf_nr_train_bwd_workspace_bytes(7, 258, 64, 3, 32) > 0
+
+
+def test_training_path_effective_tensors_reproduce_the_reference_layers():
+    """gazenerf_b200.train.branch_tensors (host logic, differentiable torch ops): the folded per-face biases and the re-arranged
+    skip-layer / head matrices must give the same pre-activations as the reference layers on their concatenated inputs."""
+    from gazenerf_b200.train import branch_tensors, PE
+    opt = G.BaseOptions({"featmap_size": 8, "featmap_nc": 258, "pred_img_size": 64})
+    torch.manual_seed(3)
+    net = G.GazeNeRFNet(opt, include_vd=False, hier_sampling=False)
+    mlp = net.fg_CD_predictor_face
+    B, n = 2, 5
+    g = torch.Generator().manual_seed(1)
+    shape_ext, appea = torch.randn(B, 181, generator=g), torch.randn(B, 127, generator=g)
+    pe, h4, h7 = torch.randn(B, n, PE, generator=g), torch.randn(B, n, 384, generator=g), torch.randn(B, n, 384, generator=g)
+    T = branch_tensors(mlp, shape_ext, appea)
+    W = lambda name: mlp._modules[name].weight.flatten(1)
+    b = lambda name: mlp._modules[name].bias
+    code = shape_ext[:, None, :].expand(B, n, 181)
+    # layer 0 on cat([pe, codes])  (models/gaze_nerf.py:250-262)
+    ref0 = torch.cat([pe, code], -1) @ W("FeaExt_module_0").t() + b("FeaExt_module_0")
+    assert torch.allclose(pe @ T[0].t() + T[1][:, None, :], ref0, atol=1e-5)
+    # skip layer on cat([pe, codes, h4])  (models/mlp_nerf.py:106-107); operand order of the GEMM is [h4 | pe]
+    ref5 = torch.cat([pe, code, h4], -1) @ W("FeaExt_module_5").t() + b("FeaExt_module_5")
+    assert torch.allclose(torch.cat([h4, pe], -1) @ T[10].t() + T[11][:, None, :], ref5, atol=1e-5)
+    # RGB_layer_0 + density share the input; RGB_layer_1 on cat([rgb0, appea]); RGB_layer_2 with its bias as an extra column
+    r0 = h7 @ T[16].t() + T[17]
+    assert torch.allclose(r0[..., :384], h7 @ W("RGB_layer_0").t() + b("RGB_layer_0"), atol=1e-5)
+    assert torch.allclose(r0[..., 384], (h7 @ W("density_module").t() + b("density_module"))[..., 0], atol=1e-5)
+    ref1 = torch.cat([r0[..., :384], appea[:, None, :].expand(B, n, 127)], -1) @ W("RGB_layer_1").t() + b("RGB_layer_1")
+    assert torch.allclose(r0[..., :384] @ T[18].t() + T[19][:, None, :], ref1, atol=1e-5)
+    hc = torch.relu(ref1)
+    ref2 = hc @ W("RGB_layer_2").t() + b("RGB_layer_2")
+    assert torch.allclose(torch.cat([hc, torch.ones(B, n, 1)], -1) @ T[20].t(), ref2, atol=1e-5)
+    # autograd maps a per-face bias gradient back to codes and weight columns
+    (T[1].sum() + T[19].sum()).backward()
+    assert mlp.FeaExt_module_0.weight.grad[:, PE:].abs().sum() > 0 and mlp.RGB_layer_1.weight.grad[:, 384:].abs().sum() > 0
