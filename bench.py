@@ -175,6 +175,7 @@ def run_train(args, torch, G, rank, local_rank, world, dev, dist):
     F = args.faces_per_gpu
     opt = G.BaseOptions()
     torch.manual_seed(45)
+    from gazenerf_b200.dist import allreduce_gradients
     from gazenerf_b200.trainer_utils import build_code_and_cam
 
     net = G.GazeNeRFNet(opt, include_vd=False, hier_sampling=False).to(dev).train()
@@ -186,7 +187,7 @@ def run_train(args, torch, G, rank, local_rank, world, dev, dist):
     lr = 1e-4   # README.md:30 of the reference
     optim = torch.optim.Adam([{"params": list(net.parameters()), "lr": lr}, {"params": list(off.values()), "lr": lr * 1.5},
                               {"params": [d_eul, d_tv], "lr": lr * 0.1}])
-    params = [p for p in net.parameters()] + list(off.values()) + [d_eul, d_tv]
+    params = [p for p in net.parameters()]   # shared by all ranks (averaged); code offsets / camera deltas belong to this rank's faces
     loss_fn = G.GazeNeRFLoss(eye_loss_importance=1.0, vgg_importance=1.0, use_vgg_loss=False, use_l1_loss=True)
     host_kw = synthetic_inputs(torch, G, opt, F, seed=rank)
     host_tg = synthetic_targets(torch, F, opt.pred_img_size, seed=rank)
@@ -208,11 +209,7 @@ def run_train(args, torch, G, rank, local_rank, world, dev, dist):
         optim.zero_grad(set_to_none=True)
         loss.backward()
         if world > 1:   # data-parallel: one flat all-reduce of the 20 MB of gradients
-            flat = torch._utils._flatten_dense_tensors([p.grad for p in params])
-            dist.all_reduce(flat)
-            flat /= world
-            for p, gsync in zip(params, torch._utils._unflatten_dense_tensors(flat, [p.grad for p in params])):
-                p.grad.copy_(gsync)
+            allreduce_gradients(params)
         optim.step()
         return loss.detach()
 

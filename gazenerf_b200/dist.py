@@ -53,6 +53,24 @@ def all_gather_images(local: Dict[str, torch.Tensor], global_batch: int, group=N
     return out
 
 
+def allreduce_gradients(params, group=None) -> None:
+    """Data-parallel training: average the gradients of `params` over the ranks with ONE flat all-reduce (the network has 5.0 M
+    parameters = 20 MB).  Parameters whose .grad is None on this rank contribute zeros, so every rank issues the same
+    collective.  In place."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return
+    grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
+    flat = torch._utils._flatten_dense_tensors(grads)
+    dist.all_reduce(flat, group=group)
+    flat /= world
+    for p, g, synced in zip(params, grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+        if p.grad is None:
+            p.grad = synced.clone()
+        else:
+            g.copy_(synced)
+
+
 class PeerAllGather(object):
     """All-gather of the rendered images FUSED into the kernel that writes them (include/gnrf.h, gnrf_neural_render_tc_fwd_gather).
 

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from gazenerf_b200.dist import all_gather_images, shard_inputs, shard_range
+from gazenerf_b200.dist import all_gather_images, allreduce_gradients, shard_inputs, shard_range
 
 
 def test_shard_range_partitions_batch():
@@ -36,6 +36,15 @@ def _worker(rank, world, port, gb, q):
         local["bg_img"] = torch.ones(1, 3, P, P)
         out = all_gather_images(local, gb)
         ok = all(torch.equal(out[k], full[k]) for k in full) and out["bg_img"].shape == (1, 3, P, P)
+        # data-parallel gradient averaging: one flat all-reduce; a parameter without a gradient on one rank still takes part
+        params = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2))]
+        params[0].grad = torch.full((3, 4), float(rank + 1))
+        params[1].grad = torch.arange(5.0) * (rank + 1)
+        if rank == 0:
+            params[2].grad = torch.ones(2)
+        allreduce_gradients(params)
+        ok = ok and torch.allclose(params[0].grad, torch.full((3, 4), 1.5)) and torch.allclose(params[1].grad, torch.arange(5.0) * 1.5)
+        ok = ok and torch.allclose(params[2].grad, torch.full((2,), 0.5))
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
