@@ -186,6 +186,43 @@ def neural_render(nr: NeuralRendererParams, x: torch.Tensor, gather=None) -> tor
     return img
 
 
+class GraphedForward(object):
+    """``net("test", ...)`` for fixed shapes captured ONCE into a CUDA graph and replayed (inference serving: the ~23 kernel launches,
+    ctypes calls and tensor allocations of a forward cost ~0.15 ms of host time per call, more than the small kernels at the head of
+    the step take on the GPU).  Inputs are copied into static device buffers, the returned dict holds static output tensors that the
+    next call overwrites.  The packed weight buffers are baked into the graph: re-capture after changing parameters."""
+
+    def __init__(self, net: "GazeNeRFNet", mode: str, kwargs: Dict[str, Optional[torch.Tensor]]):
+        if mode != "test":
+            raise ValueError("only the deterministic 'test' forward is captured (train mode draws fresh jitter every call)")
+        if net.gather_ctx is not None or net.keep_stages:
+            raise RuntimeError("graph capture supports the plain single-GPU forward (no fused gather, no stage dumps)")
+        self.net, self.mode = net, mode
+        self.static_in = {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in kwargs.items()}
+        L = _lib.lib()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):   # lazy initialisation (function attributes, packed weights, bg_img cache, t-value tables) outside the capture
+                net(mode, **self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        self._versions = tuple(p._version for p in net.parameters())
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = L.gnrf_launch_count()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.static_out = net(mode, **self.static_in)
+        self.launches_per_replay = int(L.gnrf_launch_count() - n0)
+
+    def __call__(self, **kwargs) -> Dict[str, Dict[str, torch.Tensor]]:
+        if tuple(p._version for p in self.net.parameters()) != self._versions:
+            raise RuntimeError("parameters changed since the graph was captured: call net.graphed(...) again")
+        for k, v in kwargs.items():
+            if torch.is_tensor(v):
+                self.static_in[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
+
+
 class GazeNeRFNet(nn.Module):
     def __init__(self, opt: BaseOptions, include_vd, hier_sampling, mlp_impl: Optional[str] = None) -> None:
         super().__init__()
@@ -402,6 +439,13 @@ class GazeNeRFNet(nn.Module):
                 if self.keep_stages:
                     self.last_stages.update(coarse_stage)
         return res_dict
+
+    def graphed(self, mode, batch_xy, batch_uv, bg_code, shape_code, appea_code, gaze_code, batch_Rmats, batch_Tvecs, batch_inv_inmats,
+                **kwargs) -> GraphedForward:
+        """Capture ``forward(mode, ...)`` for these shapes into a CUDA graph; the result is called with the same keyword tensors."""
+        kw = dict(batch_xy=batch_xy, batch_uv=batch_uv, bg_code=bg_code, shape_code=shape_code, appea_code=appea_code, gaze_code=gaze_code,
+                  batch_Rmats=batch_Rmats, batch_Tvecs=batch_Tvecs, batch_inv_inmats=batch_inv_inmats, **kwargs)
+        return GraphedForward(self, mode, kw)
 
     def _wants_grad(self, train_mode: bool, *inputs) -> bool:
         """"train" with trainable parameters, or any mode with an input that requires grad (codes / gaze / camera)."""

@@ -441,3 +441,25 @@ def test_repeat_calls_and_weight_update_refresh_packed_cache(dev):
     t = lambda k: torch.from_numpy(g[k])
     ref = O.forward(sd, oo, "test", t("in_xy"), t("in_shape"), t("in_appea"), t("in_gaze"), t("in_R"), t("in_T"), t("in_Kinv"))
     assert float((c.cpu() - ref["coarse_dict"]["merge_img"]).abs().max()) < TOL_TIGHT
+
+
+def test_graphed_forward_matches_eager(dev):
+    """net.graphed(): the forward captured into a CUDA graph and replayed with NEW inputs equals the eager forward bit for bit."""
+    g = load_golden("std_dense_test")
+    opt, net = _net_from_golden(g, dev, "tc")
+    kw = _inputs(g, dev)
+    gf = net.graphed("test", **kw)
+    assert gf.launches_per_replay > 10
+    kw2 = dict(kw)
+    kw2["gaze_code"] = kw["gaze_code"] + 0.1
+    kw2["shape_code"] = kw["shape_code"] * 0.5
+    with torch.no_grad():
+        ref = {k: v.clone() for k, v in net("test", **kw2)["coarse_dict"].items()}
+    out = gf(**kw2)["coarse_dict"]
+    torch.cuda.synchronize()
+    for k in ref:
+        assert torch.equal(out[k], ref[k]), k
+    with torch.no_grad():
+        net.neural_render.bg_featmap.mul_(0.9)
+    with pytest.raises(RuntimeError):
+        gf(**kw2)
