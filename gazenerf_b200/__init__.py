@@ -7,6 +7,7 @@ from .options import BaseOptions  # noqa: F401
 from .net import GazeNeRFNet, NeuralRendererParams, RadianceMLP  # noqa: F401
 from .render_utils import RenderUtils  # noqa: F401
 from .losses import GazeNeRFLoss  # noqa: F401
+from .data import SampleStager, sample_to_device  # noqa: F401
 from ._lib import build, lib  # noqa: F401
 
-__all__ = ["BaseOptions", "GazeNeRFNet", "NeuralRendererParams", "RadianceMLP", "RenderUtils", "GazeNeRFLoss", "build", "lib"]
+__all__ = ["BaseOptions", "GazeNeRFNet", "NeuralRendererParams", "RadianceMLP", "RenderUtils", "GazeNeRFLoss", "SampleStager", "sample_to_device", "build", "lib"]

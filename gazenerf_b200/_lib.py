@@ -19,21 +19,22 @@ INCLUDE = os.path.join(_ROOT, "include")
 LIB_PATH = os.path.join(_HERE, "libgnrf.so")
 
 SOURCES = ["abi.cu", "geometry.cu", "mlp_simt.cu", "mlp_tc.cu", "compose.cu", "neural_render.cu", "conv_tc.cu", "wgrad_tc.cu",
-           "train_ops.cu", "nr_train.cu", "loss.cu"]
+           "train_ops.cu", "nr_train.cu", "loss.cu", "data.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "--shared", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fPIC",
     "-Xptxas", "-v", "-diag-suppress=20013,20015",
 ]
+OBJ_DIR = os.path.join(_HERE, "build")
 
 SYMBOLS = [
     "gnrf_abi_version", "gnrf_last_error", "gnrf_device_check", "gnrf_launch_count",
     "gnrf_ray_setup", "gnrf_coarse_depths", "gnrf_fine_depths",
     "gnrf_mlp_simt_fwd", "gnrf_composite_fwd",
     "gnrf_mlp_tc_packed_bytes", "gnrf_mlp_tc_bias_floats", "gnrf_mlp_tc_pack", "gnrf_mlp_tc_fold",
-    "gnrf_mlp_tc_workspace_bytes", "gnrf_mlp_tc_fwd",
+    "gnrf_mlp_tc_workspace_bytes", "gnrf_mlp_tc_fwd", "gnrf_mlp_tc_fwd_debug",
     "gnrf_compose_fwd", "gnrf_nr_workspace_bytes", "gnrf_neural_render_fwd",
     "gnrf_nr_tc_packed_bytes", "gnrf_nr_tc_pack", "gnrf_neural_render_tc_fwd", "gnrf_neural_render_tc_fwd_gather",
     # training path
@@ -42,6 +43,8 @@ SYMBOLS = [
     "gnrf_compose_bwd_blocks", "gnrf_compose_bwd",
     "gnrf_nr_train_saved_bytes", "gnrf_nr_train_fwd", "gnrf_nr_train_bwd_workspace_bytes", "gnrf_nr_train_bwd",
     "gnrf_data_loss_workspace_floats", "gnrf_data_loss_fwd", "gnrf_data_loss_bwd",
+    # dataset sample -> device tensors
+    "gnrf_sample_images_to_device", "gnrf_sample_meta_to_device",
 ]
 
 
@@ -60,22 +63,44 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _compile_one(src: str, obj: str, headers_mtime: float, force: bool):
+    """nvcc -c one source (skipped when the object is newer than the source and every header)."""
+    if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), headers_mtime):
+        return src, 0, "(up to date)\n", None
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-c", "-o", obj, src]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    return src, proc.returncode, proc.stdout, " ".join(cmd)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into gazenerf_b200/libgnrf.so (nvcc cross-compiles without a GPU)."""
+    """Compile every CUDA source for sm_100a (nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo; cross-compiles without a GPU)
+    into gazenerf_b200/libgnrf.so: one object per source, compiled in parallel and re-used while the source and headers are
+    unchanged, then one link."""
     if not force and not _stale():
         return LIB_PATH
-    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    from concurrent.futures import ThreadPoolExecutor
+
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + [os.path.join(INCLUDE, "gnrf.h")]
+    hm = max(os.path.getmtime(h) for h in headers)
+    jobs = [(os.path.join(CSRC, s), os.path.join(OBJ_DIR, s[:-3] + ".o")) for s in SOURCES]
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(lambda j: _compile_one(j[0], j[1], hm, force), jobs))
+    text = ""
+    for src, rc, out, cmd in results:
+        text += "==== %s\n%s\n%s" % (os.path.basename(src), cmd or "", out)
+        if rc != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s" % (src, out))
     tmp = LIB_PATH + ".tmp.%d" % os.getpid()
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-o", tmp] + srcs
-    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", tmp] + [o for _, o in jobs]
+    proc = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + proc.stdout)
+        raise RuntimeError("link failed:\n" + proc.stdout)
     os.replace(tmp, LIB_PATH)
-    log = os.path.join(_HERE, "build.log")
-    with open(log, "w") as f:
-        f.write(" ".join(cmd) + "\n" + proc.stdout)
+    with open(os.path.join(_HERE, "build.log"), "w") as f:
+        f.write(text + "==== link\n" + " ".join(link) + "\n" + proc.stdout)
     if verbose:
-        print(proc.stdout)
+        print(text)
     return LIB_PATH
 
 
@@ -112,6 +137,7 @@ def lib() -> ctypes.CDLL:
     L.gnrf_mlp_tc_workspace_bytes.restype = sz
     L.gnrf_mlp_tc_workspace_bytes.argtypes = [i32, i32, i32]
     L.gnrf_mlp_tc_fwd.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, sz, vp]
+    L.gnrf_mlp_tc_fwd_debug.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, sz, vp, vp, i32, vp]
     L.gnrf_compose_fwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]
     L.gnrf_nr_workspace_bytes.restype = sz
     L.gnrf_nr_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
@@ -145,6 +171,8 @@ def lib() -> ctypes.CDLL:
     L.gnrf_data_loss_workspace_floats.restype = sz
     L.gnrf_data_loss_fwd.argtypes = [vp] * 9 + [i32, i32, i32, f32, vp, vp, vp, vp]
     L.gnrf_data_loss_bwd.argtypes = [vp] * 9 + [i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp]
+    L.gnrf_sample_images_to_device.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]
+    L.gnrf_sample_meta_to_device.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is c.c_int and name not in ("gnrf_abi_version",):

@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <mutex>
 
 namespace gnrf {
 
@@ -20,6 +21,42 @@ int fail(int code, const char* fmt, ...) {
 
 static std::atomic<unsigned long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+// ---- per-device one-time initialisation (see common.cuh) ------------------------------------------------------------
+namespace {
+constexpr int kMaxDevices = 64;
+std::mutex g_once_mutex;
+uint32_t g_once_done[kMaxDevices] = {0};   // bit `key` set: initialised on that device     (guarded by g_once_mutex)
+int g_sm_count[kMaxDevices] = {0};
+}  // namespace
+
+int device_once_begin(int key, int* dev, int* n_sm, bool* need_init) {
+  *need_init = false;
+  GNRF_CUDA(cudaGetDevice(dev));
+  if (*dev < 0 || *dev >= kMaxDevices) return fail(GNRF_ERR_UNSUPPORTED, "device ordinal %d out of range", *dev);
+  g_once_mutex.lock();
+  if (g_sm_count[*dev] == 0) {
+    int n = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, *dev);
+    if (e != cudaSuccess) {
+      g_once_mutex.unlock();
+      return fail(GNRF_ERR_CUDA, "cudaDeviceGetAttribute(MultiProcessorCount) -> %s", cudaGetErrorString(e));
+    }
+    g_sm_count[*dev] = n;
+  }
+  *n_sm = g_sm_count[*dev];
+  if (g_once_done[*dev] & (1u << key)) {
+    g_once_mutex.unlock();
+    return GNRF_OK;
+  }
+  *need_init = true;   // the caller runs its init and then calls device_once_end, which unlocks
+  return GNRF_OK;
+}
+
+void device_once_end(int key, int dev, bool ok) {
+  if (ok) g_once_done[dev] |= (1u << key);
+  g_once_mutex.unlock();
+}
 
 }  // namespace gnrf
 

@@ -33,6 +33,23 @@ void count_launches(int n);  // feeds gnrf_launch_count()
       return ::gnrf::fail(GNRF_ERR_CUDA, "%s: kernel launch failed: %s", __func__, cudaGetErrorString(e__)); \
   } while (0)
 
+// Per-device one-time initialisation (cudaFuncSetAttribute opt-ins are per device / context): runs `init` the first time `key` is
+// seen on the CURRENT device, under a process-wide mutex so that concurrent first calls from several threads are safe.
+// Returns the current device's SM count through *n_sm.  key < 32.
+int device_once_begin(int key, int* dev, int* n_sm, bool* need_init);   // takes the lock when *need_init
+void device_once_end(int key, int dev, bool ok);                        // releases it
+template <class F>
+static inline int device_once(int key, int* n_sm, F&& init) {
+  int dev = 0;
+  bool need = false;
+  int rc = device_once_begin(key, &dev, n_sm, &need);
+  if (rc != GNRF_OK || !need) return rc;
+  rc = init();
+  device_once_end(key, dev, rc == GNRF_OK);
+  return rc;
+}
+enum { kOnceMlpTc = 0, kOnceMlpSimt = 1, kOnceConvTc = 2, kOnceWgradTc = 3, kOnceNrFused = 4, kOnceMlpTrain = 5 };
+
 static inline cudaStream_t as_stream(gnrf_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

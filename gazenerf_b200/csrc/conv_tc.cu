@@ -427,12 +427,13 @@ int conv_tc_launch(const ConvLayerPlan& pl, const unsigned char* packed, const f
 
 int conv_tc_launch_ex(const ConvLayerPlan& pl, const unsigned char* packed, const float* X, float* out, const float* res, int Cres,
                       int n_img, int HW, int Wd, int mode, const ConvExtras& ex, cudaStream_t st) {
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    GNRF_CUDA(cudaGetDevice(&dev));
-    GNRF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    GNRF_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmemBytes));
+  int n_sm = 0;
+  {
+    int rc = device_once(kOnceConvTc, &n_sm, []() -> int {
+      GNRF_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmemBytes));
+      return GNRF_OK;
+    });
+    if (rc != GNRF_OK) return rc;
   }
   ConvArgs a;
   a.X = X;

@@ -302,10 +302,13 @@ extern "C" int gnrf_mlp_simt_fwd(const float* const* params, const float* ray_dl
     prm.b[i] = params[2 * i + 1];
     GNRF_CHECK_ARG(prm.w[i] != nullptr && prm.b[i] != nullptr);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    GNRF_CUDA(cudaFuncSetAttribute(mlp_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimtSmem)));
-    attr_set = true;
+  {
+    int n_sm = 0;
+    int rc = device_once(kOnceMlpSimt, &n_sm, []() -> int {
+      GNRF_CUDA(cudaFuncSetAttribute(mlp_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimtSmem)));
+      return GNRF_OK;
+    });
+    if (rc != GNRF_OK) return rc;
   }
   int tiles_per_face = ceil_div(N_r * N_s, kTP);
   mlp_simt_kernel<<<B * tiles_per_face, kThreads, sizeof(SimtSmem), as_stream(stream)>>>(

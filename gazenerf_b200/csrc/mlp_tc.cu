@@ -780,13 +780,13 @@ __global__ void pack_aux_kernel(PackSrc src, float* __restrict__ aux) {
   for (int i = tid; i < kFeat; i += nth) aux[kAuxB2 + i] = src.b[11][i];
 }
 
-// Stage table (built on the host from for_each_stage, uploaded once per process).
+// Stage record of one ring stage; every CTA of pack_stream_kernel derives its own from for_each_stage (no device-global table, no
+// per-process state: the ABI stays re-entrant across streams and devices).
 struct StageRec {
   uint32_t byte_off;
   uint16_t ks, nk16, n0, nrows;
   uint8_t layer, phase2, pad0, pad1;
 };
-__device__ StageRec g_stage_table[kNumStagesPerTile];
 
 __device__ __forceinline__ float pack_src_value(const PackSrc& src, const float* wf, int layer, int phase2, int n, int k) {
   const int vp = GNRF_PE_DIMS + GNRF_SHAPE_EXT_DIMS;
@@ -804,7 +804,22 @@ __device__ __forceinline__ float pack_src_value(const PackSrc& src, const float*
 // Chunk order inside a K16 slice of `nrows` rows = the no-swizzle K-major core-matrix layout:
 //   chunk = (row / 8) * 16 + k_half * 8 + (row % 8)        (8 rows x 16 B contiguous; K-halves 128 B apart; groups 256 B apart)
 __global__ void pack_stream_kernel(PackSrc src, const float* __restrict__ wf, unsigned char* __restrict__ stream) {
-  const StageRec st = g_stage_table[blockIdx.x];
+  __shared__ StageRec s_st;
+  if (threadIdx.x == 0) {
+    int i = 0;
+    uint32_t off = 0;
+    for_each_stage([&](const StageInfo& si) {
+      if (i == (int)blockIdx.x) {
+        s_st.byte_off = off;
+        s_st.ks = (uint16_t)si.ks; s_st.nk16 = (uint16_t)si.nk16; s_st.n0 = (uint16_t)si.n0; s_st.nrows = (uint16_t)si.nrows;
+        s_st.layer = (uint8_t)si.layer; s_st.phase2 = (uint8_t)si.phase2; s_st.pad0 = 0; s_st.pad1 = 0;
+      }
+      ++i;
+      off += si.bytes;
+    });
+  }
+  __syncthreads();
+  const StageRec st = s_st;
   const int chunks_per_slice = st.nrows * 2;
   const int chunks_per_half = chunks_per_slice * st.nk16;   // W_hi slices first, then the W_lo slices
   for (int c = threadIdx.x; c < 2 * chunks_per_half; c += blockDim.x) {
@@ -875,22 +890,6 @@ extern "C" int gnrf_mlp_tc_pack(const float* const* params, void* packed, gnrf_s
   unsigned char* p = static_cast<unsigned char*>(packed);
   float* aux = reinterpret_cast<float*>(p + kStreamBytes);
   cudaStream_t st = as_stream(stream);
-  static bool table_ready = false;
-  if (!table_ready) {
-    static StageRec host_table[kNumStagesPerTile];
-    int i = 0;
-    uint32_t off = 0;
-    for_each_stage([&](const StageInfo& si) {
-      StageRec& r = host_table[i++];
-      r.byte_off = off;
-      r.ks = (uint16_t)si.ks; r.nk16 = (uint16_t)si.nk16; r.n0 = (uint16_t)si.n0; r.nrows = (uint16_t)si.nrows;
-      r.layer = (uint8_t)si.layer; r.phase2 = (uint8_t)si.phase2; r.pad0 = 0; r.pad1 = 0;
-      off += si.bytes;
-    });
-    if (i != kNumStagesPerTile || off != kStreamBytes) return fail(GNRF_ERR_CUDA, "gnrf_mlp_tc_pack: stage table mismatch (%d, %u)", i, off);
-    GNRF_CUDA(cudaMemcpyToSymbolAsync(g_stage_table, host_table, sizeof(host_table), 0, cudaMemcpyHostToDevice, st));
-    table_ready = true;
-  }
   fuse_head_kernel<<<kL8N, 128, 0, st>>>(src, aux);
   pack_aux_kernel<<<148, 256, 0, st>>>(src, aux);
   pack_stream_kernel<<<kNumStagesPerTile, 256, 0, st>>>(src, aux + kAuxWf, p);
@@ -916,10 +915,10 @@ extern "C" size_t gnrf_mlp_tc_workspace_bytes(int n_branch, int B, int N_r) {
   return hc + (size_t)kMaxGrid * 65 * kTile * sizeof(uint32_t);
 }
 
-extern "C" int gnrf_mlp_tc_fwd(int n_branch, const void* const* packed, const float* const* bias, const float* ray_dl,
-                               const float* tvecs, const float* z_edges, int B, int N_r, int N_s, float* const* feat_ray,
-                               float* const* bg_alpha, float* const* weights, void* workspace, size_t workspace_bytes,
-                               gnrf_stream_t stream) {
+extern "C" int gnrf_mlp_tc_fwd_debug(int n_branch, const void* const* packed, const float* const* bias, const float* ray_dl,
+                                     const float* tvecs, const float* z_edges, int B, int N_r, int N_s, float* const* feat_ray,
+                                     float* const* bg_alpha, float* const* weights, void* workspace, size_t workspace_bytes,
+                                     float* dbg_dump, long long* timeline, int cluster_size, gnrf_stream_t stream) {
   GNRF_CHECK_ARG(packed && bias && ray_dl && tvecs && z_edges && feat_ray && bg_alpha && workspace);
   GNRF_CHECK_ARG(n_branch == 1 || n_branch == 2);
   GNRF_CHECK_ARG(B > 0 && N_r > 0 && N_s > 0);
@@ -929,15 +928,16 @@ extern "C" int gnrf_mlp_tc_fwd(int n_branch, const void* const* packed, const fl
   if (workspace_bytes < gnrf_mlp_tc_workspace_bytes(n_branch, B, N_r))
     return fail(GNRF_ERR_ARG, "gnrf_mlp_tc_fwd: workspace too small");
   cudaStream_t st = as_stream(stream);
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    GNRF_CUDA(cudaGetDevice(&dev));
-    GNRF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    GNRF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    GNRF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    GNRF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    GNRF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  int n_sm = 0;
+  {
+    int rc = device_once(kOnceMlpTc, &n_sm, []() -> int {
+      GNRF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      GNRF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      GNRF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      GNRF_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      return GNRF_OK;
+    });
+    if (rc != GNRF_OK) return rc;
   }
   FwdArgs a;
   float* ws = static_cast<float*>(workspace);
@@ -961,24 +961,11 @@ extern "C" int gnrf_mlp_tc_fwd(int n_branch, const void* const* packed, const fl
   a.n_items = n_branch * B * a.tiles_per_face;
   a.pe_stash = reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(workspace) +
                                            (((size_t)n_branch * B * N_r * (kH2 + 1) * sizeof(float) + 255) & ~(size_t)255));
-  a.dbg = nullptr;
-  {
-    const char* e = getenv("GNRF_TC_DEBUG_PTR");  // test hook: device pointer (decimal) of a [10][128][384] fp32 dump buffer
-    if (e != nullptr) a.dbg = reinterpret_cast<float*>(strtoull(e, nullptr, 10));
-  }
-  a.prof = nullptr;
-  {
-    const char* e = getenv("GNRF_TC_PROF_PTR");  // test hook: device pointer (decimal) of a [4][10][16] int64 timeline buffer
-    if (e != nullptr) a.prof = reinterpret_cast<long long*>(strtoull(e, nullptr, 10));
-  }
-  // cluster size: CTAs of a cluster share every weight stage through TMA multicast (default 2; GNRF_TC_CLUSTER=1|2)
-  int csize = 2;
-  {
-    const char* e = getenv("GNRF_TC_CLUSTER");
-    if (e != nullptr) csize = atoi(e);
-    if (csize != 1 && csize != 2) csize = 2;
-    while (csize > 1 && ((B * a.tiles_per_face) % csize != 0 || a.n_items / csize < 1)) csize >>= 1;
-  }
+  a.dbg = dbg_dump;    // optional [10][128][384] fp32 dump of tile 0's activations
+  a.prof = timeline;   // optional [4][10][16] int64 clock64 timeline of CTA 0
+  // cluster size: CTAs of a cluster share every weight stage through TMA multicast (default 2)
+  int csize = (cluster_size == 1) ? 1 : 2;
+  while (csize > 1 && ((B * a.tiles_per_face) % csize != 0 || a.n_items / csize < 1)) csize >>= 1;
   int grid = (a.n_items / csize) * csize < n_sm ? (a.n_items / csize) * csize : n_sm;
   if (grid > kMaxGrid) grid = kMaxGrid;
   grid -= grid % csize;
@@ -1021,4 +1008,12 @@ extern "C" int gnrf_mlp_tc_fwd(int n_branch, const void* const* packed, const fl
   GNRF_LAUNCH_CHECK();
   count_launches(2);
   return GNRF_OK;
+}
+
+extern "C" int gnrf_mlp_tc_fwd(int n_branch, const void* const* packed, const float* const* bias, const float* ray_dl,
+                               const float* tvecs, const float* z_edges, int B, int N_r, int N_s, float* const* feat_ray,
+                               float* const* bg_alpha, float* const* weights, void* workspace, size_t workspace_bytes,
+                               gnrf_stream_t stream) {
+  return gnrf_mlp_tc_fwd_debug(n_branch, packed, bias, ray_dl, tvecs, z_edges, B, N_r, N_s, feat_ray, bg_alpha, weights, workspace,
+                               workspace_bytes, nullptr, nullptr, 2, stream);
 }

@@ -329,12 +329,13 @@ WgradPlan wgrad_plan(int N_dy, int K_x, int n_img, int HW, bool want_bias) {
 
 int wgrad_tc_launch(const float* dY, long long dy_img_stride, const float* X, long long x_img_stride, int N_dy, int K_x, int n_img,
                     int HW, float* dW, float* db_img, int db_sum, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    GNRF_CUDA(cudaGetDevice(&dev));
-    GNRF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    GNRF_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+  int n_sm = 0;
+  {
+    int rc = device_once(kOnceWgradTc, &n_sm, []() -> int {
+      GNRF_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+      return GNRF_OK;
+    });
+    if (rc != GNRF_OK) return rc;
   }
   if (HW % 4 != 0 || dy_img_stride % 4 != 0 || x_img_stride % 4 != 0)
     return fail(GNRF_ERR_ARG, "wgrad_tc: HW and image strides must be multiples of 4 floats (vector loads)");

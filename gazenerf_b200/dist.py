@@ -102,22 +102,30 @@ class PeerAllGather(object):
         h = self.hdls[self.step & 1]
         return [int(p) for p in h.buffer_ptrs], (int(h.multicast_ptr) if self.use_multicast else 0)
 
-    def finish(self) -> Dict[str, torch.Tensor]:
-        """Device barrier across the ranks (on the current stream), then views of this step's gathered images."""
+    def finish(self, alias: bool = False) -> Dict[str, torch.Tensor]:
+        """Device barrier across the ranks (on the current stream), then this step's gathered images.
+
+        ``alias=False`` (default) returns fresh tensors (one D2D copy), like the NCCL path.  ``alias=True`` returns zero-copy VIEWS of
+        the symmetric buffer: peers overwrite it remotely two steps later, so the caller must have finished reading it -- on this
+        stream, or behind an event it waits on before entering the next-but-one step -- by then (bench.py does this for its D2H)."""
         i = self.step & 1
-        self.hdls[i].barrier(channel=0)
+        with torch.cuda.device(self.bufs[i].device):
+            self.hdls[i].barrier(channel=0)
         self.step += 1
         buf = self.bufs[i]
+        if not alias:
+            buf = buf.clone()
         return {"merge_img_face": buf[0], "merge_img_eyes": buf[1], "merge_img": buf[2]}
 
 
 class BatchShardedRenderer(object):
     """net("test", **global_kwargs) over a process group: each rank renders its slice, one all-gather returns the batch."""
 
-    def __init__(self, net, group=None, fused_gather: bool = False):
+    def __init__(self, net, group=None, fused_gather: bool = False, alias_outputs: bool = False):
         self.net = net
         self.group = group
         self.fused_gather = fused_gather   # gather inside the last neural-render kernel (PeerAllGather) instead of NCCL
+        self.alias_outputs = alias_outputs  # fused path: return views of the symmetric buffer (see PeerAllGather.finish)
         self._peer: Optional[PeerAllGather] = None
 
     @torch.no_grad()
@@ -127,18 +135,29 @@ class BatchShardedRenderer(object):
             return self.net(mode, **kwargs)
         rank = dist.get_rank(self.group)
         gb = kwargs["batch_xy"].shape[0]
+        if gb < world:   # checked on every rank BEFORE any collective: a rank with no face would otherwise leave its peers blocked
+            raise ValueError("global batch %d < world size %d: every rank needs at least one face" % (gb, world))
         mine = shard_inputs(kwargs, rank, world)
         b_local = mine["batch_xy"].shape[0]
-        if self.fused_gather and gb == b_local * world:
+        # the fused gather lives in the coarse, all-three-images neural-render call: hierarchical nets (two image sets) and
+        # only_merge callers take the NCCL path, as do ragged shards
+        fused_ok = (self.fused_gather and gb == b_local * world and not self.net.hier_sampling and not kwargs.get("only_merge", False))
+        if fused_ok:
             if self._peer is None or self._peer.b_local != b_local:
                 self._peer = PeerAllGather(b_local, self.net.pred_img_size, mine["batch_xy"].device, self.group)
             self.net.gather_ctx = self._peer
+            self.net.gather_used = False
             try:
                 local = self.net(mode, **mine)
             finally:
                 self.net.gather_ctx = None
-            out = self._peer.finish()
+            if not self.net.gather_used:
+                raise RuntimeError("fused gather requested but the forward did not run the gathering neural-render kernel")
+            out = self._peer.finish(alias=self.alias_outputs)
             out["bg_img"] = local["coarse_dict"]["bg_img"]
             return {"coarse_dict": out}
         local = self.net(mode, **mine)
-        return {"coarse_dict": all_gather_images(local["coarse_dict"], gb, self.group)}
+        res = {"coarse_dict": all_gather_images(local["coarse_dict"], gb, self.group)}
+        if "fine_dict" in local:
+            res["fine_dict"] = all_gather_images(local["fine_dict"], gb, self.group)
+        return res

@@ -206,7 +206,7 @@ class GraphedForward(object):
             for _ in range(2):   # lazy initialisation (function attributes, packed weights, bg_img cache, t-value tables) outside the capture
                 net(mode, **self.static_in)
         torch.cuda.current_stream().wait_stream(side)
-        self._versions = tuple(p._version for p in net.parameters())
+        self._versions = tuple((p.data_ptr(), p._version) for p in net.parameters())
         self.graph = torch.cuda.CUDAGraph()
         n0 = L.gnrf_launch_count()
         with torch.no_grad(), torch.cuda.graph(self.graph):
@@ -214,7 +214,7 @@ class GraphedForward(object):
         self.launches_per_replay = int(L.gnrf_launch_count() - n0)
 
     def __call__(self, **kwargs) -> Dict[str, Dict[str, torch.Tensor]]:
-        if tuple(p._version for p in self.net.parameters()) != self._versions:
+        if tuple((p.data_ptr(), p._version) for p in self.net.parameters()) != self._versions:
             raise RuntimeError("parameters changed since the graph was captured: call net.graphed(...) again")
         for k, v in kwargs.items():
             if torch.is_tensor(v):
@@ -261,14 +261,25 @@ class GazeNeRFNet(nn.Module):
         self.keep_stages = False
         # bench hook: when a list, (start, end) CUDA events bracketing the radiance-MLP launches are appended per forward
         self.mlp_events: Optional[list] = None
+        self.tc_debug = None   # developer hook: (dump tensor | None, timeline tensor | None, cluster size) -> gnrf_mlp_tc_fwd_debug
         # bg_img = NeuralRenderer(bg_featmap) depends on parameters only (models/gaze_nerf.py:175-176); in no-grad inference it
         # is cached per parameter version instead of being re-rendered on every call (set False to re-render every call).
         self.cache_bg_img = True
         self._bg_cache: Optional[Tuple[tuple, torch.Tensor]] = None
         # multi-GPU: when set (dist.BatchShardedRenderer / bench.py), the coarse images are all-gathered by the kernel that writes them
         self.gather_ctx = None
+        self.gather_used = False   # set by _images when the gathering neural-render kernel actually ran
 
     # ------------------------------------------------------------------ helpers
+    def invalidate_caches(self) -> None:
+        """Drop the derived caches (packed tcgen05 weight streams, cached bg_img).  They are keyed on (data_ptr, Parameter._version):
+        optimizer steps, ``load_state_dict`` and in-place ops on the Parameter are seen automatically, writes through ``p.data``
+        (which do not bump ``_version``) are NOT -- call this after such a write."""
+        self._tc_cache.clear()
+        self._bg_cache = None
+        if hasattr(self.neural_render, "_tc_pack"):
+            object.__setattr__(self.neural_render, "_tc_pack", None)
+
     def _tc_supported(self, n_s: int) -> bool:
         return self.mlp_h_channel == 384 and self.featmap_nc == 258 and n_s >= 1 and TC_TILE % n_s == 0
 
@@ -311,10 +322,15 @@ class GazeNeRFNet(nn.Module):
             ws_bytes = L.gnrf_mlp_tc_workspace_bytes(2, B, n_r)
             ws = torch.empty((max(ws_bytes, 1),), device=dev, dtype=torch.uint8)
             wp = _lib.ptr_array([w.data_ptr() for w in wts]) if wts is not None else None
-            _lib.check(L.gnrf_mlp_tc_fwd(2, _lib.ptr_array([p.data_ptr() for p in packed]), _lib.ptr_array([b.data_ptr() for b in bias]),
-                                         ray_dl.data_ptr(), tvecs.data_ptr(), z_edges.data_ptr(), B, n_r, n_s,
-                                         _lib.ptr_array([f.data_ptr() for f in feat]), _lib.ptr_array([a.data_ptr() for a in alpha]),
-                                         wp, ws.data_ptr(), ws_bytes, _stream()), "gnrf_mlp_tc_fwd")
+            args = (2, _lib.ptr_array([p.data_ptr() for p in packed]), _lib.ptr_array([b.data_ptr() for b in bias]),
+                    ray_dl.data_ptr(), tvecs.data_ptr(), z_edges.data_ptr(), B, n_r, n_s,
+                    _lib.ptr_array([f.data_ptr() for f in feat]), _lib.ptr_array([a.data_ptr() for a in alpha]), wp, ws.data_ptr(), ws_bytes)
+            if self.tc_debug is None:
+                _lib.check(L.gnrf_mlp_tc_fwd(*args, _stream()), "gnrf_mlp_tc_fwd")
+            else:   # developer instrumentation (tests/tc_timeline.py): (dump tensor or None, timeline tensor or None, cluster size)
+                dbg, prof, csize = self.tc_debug
+                _lib.check(L.gnrf_mlp_tc_fwd_debug(*args, dbg.data_ptr() if dbg is not None else None,
+                                                   prof.data_ptr() if prof is not None else None, int(csize), _stream()), "gnrf_mlp_tc_fwd_debug")
         elif impl == "simt":
             feat_pts = torch.empty((B, n_r, n_s, C), device=dev, dtype=torch.float32)
             sigma_pts = torch.empty((B, n_r, n_s), device=dev, dtype=torch.float32)
@@ -357,6 +373,7 @@ class GazeNeRFNet(nn.Module):
             return {"merge_img": imgs[:B], "bg_img": bg_img}
         gather = self.gather_ctx if (self.gather_ctx is not None and not self.hier_sampling) else None
         imgs = neural_render(self.neural_render, fm, gather=gather)  # ONE batched call over [face | eyes | merge (| bg)]
+        self.gather_used = gather is not None
         if bg_img is None:
             bg_img = imgs[3 * B:]
             if self.cache_bg_img:

@@ -7,7 +7,8 @@ radiance MLPs (models/mlp_nerf.py:95-119) -> alpha composite (utils/model_utils.
 (models/gaze_nerf.py:175-203) -> neural renderer (models/neural_renderer.py:98-113) -- is evaluated layer by layer on
 channel-major activations kept in HBM (B200: 180 GB; ~4 GB per face and branch at 64x64x64), every dense layer and both of
 its gradients on tcgen05 tensor cores (conv_tc.cu forward / input gradient, wgrad_tc.cu weight gradient, bf16x3 split
-precision), everything else in streaming CUDA kernels (train_ops.cu, nr_train.cu).
+precision), everything else in streaming CUDA kernels (train_ops.cu, nr_train.cu).  The tape holds two Functions: FeatureMapFn
+(rays -> feature maps) and NeuralRenderFn (feature maps -> images).
 
 Exact rewrites used (identities of the reference graph, as in the inference kernel):
   * the per-face code columns of FeaExt_module_0 / FeaExt_module_5 / RGB_layer_1 are folded into per-face bias vectors.  The
@@ -178,18 +179,18 @@ def _branch_backward(o: _Ops, T: Sequence[torch.Tensor], sv: Dict[str, torch.Ten
     return g  # type: ignore[return-value]
 
 
-class RenderTrainFn(torch.autograd.Function):
-    """images [3B+1, 3, P, P] = (merge_img_face | merge_img_eyes | merge_img | bg_img) with gradients to every argument tensor."""
+class FeatureMapFn(torch.autograd.Function):
+    """rays -> positional encoding -> both radiance MLPs -> composite -> compose:  feature maps [3B+1, C, S, S] =
+    (merge_face | eyes_planes | merge | bg_featmap), with gradients to every argument tensor."""
 
     @staticmethod
     def forward(ctx, cfg, xy, rmats, tvecs, kinv, gaze, z_edges, bg_featmap, *tensors):
-        net, H, C, S, n_s = cfg["net"], cfg["H"], cfg["C"], cfg["S"], cfg["n_s"]
-        nr = net.neural_render
+        H, C, S, n_s = cfg["H"], cfg["C"], cfg["S"], cfg["n_s"]
         B, n_r = xy.shape[0], xy.shape[2]
         o = _Ops(xy.device)
         L = o.L
         T = [t.detach().contiguous() for t in tensors]
-        Tf, Te, Tn = T[:N_BRANCH_T], T[N_BRANCH_T:2 * N_BRANCH_T], T[2 * N_BRANCH_T:]
+        Tf, Te = T[:N_BRANCH_T], T[N_BRANCH_T:2 * N_BRANCH_T]
         ray_dl = o.empty(B, n_r, 4)
         _lib.check(L.gnrf_ray_setup(xy.data_ptr(), rmats.data_ptr(), kinv.data_ptr(), B, n_r, ray_dl.data_ptr(), o.st), "gnrf_ray_setup")
         sv_f = _branch_forward(o, Tf, B, n_r, n_s, H, C, ray_dl, tvecs, z_edges)
@@ -200,42 +201,23 @@ class RenderTrainFn(torch.autograd.Function):
         _lib.check(L.gnrf_compose_fwd(sv_f["feat"].data_ptr(), sv_f["bg_alpha"].data_ptr(), sv_e["feat"].data_ptr(), sv_e["bg_alpha"].data_ptr(),
                                       bg.data_ptr(), gaze.data_ptr(), B, C, S * S, fm.data_ptr(), o.st), "gnrf_compose_fwd")
         fm[3 * B].copy_(bg[0])
-        Pimg = S << nr.n_blocks
-        imgs = o.empty(n_img, 3, Pimg, Pimg)
-        saved_bytes = L.gnrf_nr_train_saved_bytes(n_img, C, S, nr.n_blocks, nr.min_feat)
-        saved = torch.empty((saved_bytes,), device=xy.device, dtype=torch.uint8)
-        packed = nr.packed_tc()
-        _lib.check(L.gnrf_nr_train_fwd(_lib.ptr_array([t.data_ptr() for t in Tn]), packed.data_ptr(), fm.data_ptr(), n_img, C, S, nr.n_blocks,
-                                       nr.min_feat, imgs.data_ptr(), saved.data_ptr(), saved_bytes, o.st), "gnrf_nr_train_fwd")
         ctx.cfg = cfg
-        ctx.keep = dict(xy=xy, rmats=rmats, kinv=kinv, gaze=gaze, z_edges=z_edges, bg=bg, ray_dl=ray_dl, T=T, sv_f=sv_f, sv_e=sv_e, fm=fm,
-                        imgs=imgs, saved=saved)
+        ctx.keep = dict(xy=xy, rmats=rmats, kinv=kinv, gaze=gaze, z_edges=z_edges, bg=bg, ray_dl=ray_dl, T=T, sv_f=sv_f, sv_e=sv_e)
         if cfg.get("stages") is not None:
             cfg["stages"].update({"feat_face": sv_f["feat"], "feat_eyes": sv_e["feat"], "bg_alpha_face": sv_f["bg_alpha"],
                                   "bg_alpha_eyes": sv_e["bg_alpha"], "w_face": sv_f["w"], "w_eyes": sv_e["w"], "featmaps": fm})
-        return imgs
+        return fm
 
     @staticmethod
-    def backward(ctx, g_imgs):
+    def backward(ctx, g_fm):
         cfg, k = ctx.cfg, ctx.keep
-        net, H, C, S, n_s = cfg["net"], cfg["H"], cfg["C"], cfg["S"], cfg["n_s"]
-        nr = net.neural_render
+        H, C, S, n_s = cfg["H"], cfg["C"], cfg["S"], cfg["n_s"]
         xy, ray_dl, z_edges, T = k["xy"], k["ray_dl"], k["z_edges"], k["T"]
         B, n_r = xy.shape[0], xy.shape[2]
         o = _Ops(xy.device)
         L = o.L
-        Tf, Te, Tn = T[:N_BRANCH_T], T[N_BRANCH_T:2 * N_BRANCH_T], T[2 * N_BRANCH_T:]
-        n_img = 3 * B + 1
-        g_imgs = g_imgs.contiguous().float()
-        # ---- neural renderer
-        g_fm = o.empty(n_img, C, S, S)
-        g_n = [torch.empty_like(t) for t in Tn]
-        ws_bytes = L.gnrf_nr_train_bwd_workspace_bytes(n_img, C, S, nr.n_blocks, nr.min_feat)
-        ws = torch.empty((ws_bytes,), device=xy.device, dtype=torch.uint8)
-        _lib.check(L.gnrf_nr_train_bwd(_lib.ptr_array([t.data_ptr() for t in Tn]), k["fm"].data_ptr(), k["saved"].data_ptr(),
-                                       k["imgs"].data_ptr(), g_imgs.data_ptr(), n_img, C, S, nr.n_blocks, nr.min_feat, g_fm.data_ptr(),
-                                       _lib.ptr_array([t.data_ptr() for t in g_n]), ws.data_ptr(), ws_bytes, o.st), "gnrf_nr_train_bwd")
-        del ws
+        Tf, Te = T[:N_BRANCH_T], T[N_BRANCH_T:2 * N_BRANCH_T]
+        g_fm = g_fm.contiguous().float()
         # ---- compose
         P2 = S * S
         sv_f, sv_e = k["sv_f"], k["sv_e"]
@@ -262,16 +244,76 @@ class RenderTrainFn(torch.autograd.Function):
         cs = contrib.sum(1)
         g_R, g_T = cs[:, :9].reshape(B, 3, 3), cs[:, 9:].reshape(B, 3)
         ctx.keep = None
-        grads = [None, None, g_R, g_T, None, g_gaze, None, g_bg] + g_f + g_e + g_n
+        grads = [None, None, g_R, g_T, None, g_gaze, None, g_bg] + g_f + g_e
         need = ctx.needs_input_grad
         return tuple(gr if (i < len(need) and need[i]) else None for i, gr in enumerate(grads))
 
 
-def forward_train(net, xy, rmats, tvecs, kinv, gaze, shape_ext, appea, z_edges, stages=None) -> torch.Tensor:
-    """Differentiable render: returns images [3B+1,3,P,P].  ``shape_ext`` / ``appea`` / ``gaze`` / ``rmats`` / ``tvecs`` may require
-    grad (the reference optimises code offsets and camera deltas, trainer/gazenerf_trainer.py:338-405)."""
+class NeuralRenderFn(torch.autograd.Function):
+    """feature maps [N, C, S, S] -> images [N, 3, P, P] (models/neural_renderer.py:98-113) with gradients to the maps and the
+    renderer's parameters."""
+
+    @staticmethod
+    def forward(ctx, cfg, fm, *tensors):
+        net, C, S = cfg["net"], cfg["C"], cfg["S"]
+        nr = net.neural_render
+        o = _Ops(fm.device)
+        L = o.L
+        Tn = [t.detach().contiguous() for t in tensors]
+        fm = fm.detach().contiguous()
+        n_img = fm.shape[0]
+        Pimg = S << nr.n_blocks
+        imgs = o.empty(n_img, 3, Pimg, Pimg)
+        saved_bytes = L.gnrf_nr_train_saved_bytes(n_img, C, S, nr.n_blocks, nr.min_feat)
+        saved = torch.empty((saved_bytes,), device=fm.device, dtype=torch.uint8)
+        packed = nr.packed_tc()
+        _lib.check(L.gnrf_nr_train_fwd(_lib.ptr_array([t.data_ptr() for t in Tn]), packed.data_ptr(), fm.data_ptr(), n_img, C, S, nr.n_blocks,
+                                       nr.min_feat, imgs.data_ptr(), saved.data_ptr(), saved_bytes, o.st), "gnrf_nr_train_fwd")
+        ctx.cfg = cfg
+        ctx.keep = dict(Tn=Tn, fm=fm, imgs=imgs, saved=saved)
+        return imgs
+
+    @staticmethod
+    def backward(ctx, g_imgs):
+        cfg, k = ctx.cfg, ctx.keep
+        net, C, S = cfg["net"], cfg["C"], cfg["S"]
+        nr = net.neural_render
+        Tn, fm = k["Tn"], k["fm"]
+        o = _Ops(fm.device)
+        L = o.L
+        n_img = fm.shape[0]
+        g_imgs = g_imgs.contiguous().float()
+        g_fm = o.empty(n_img, C, S, S)
+        g_n = [torch.empty_like(t) for t in Tn]
+        ws_bytes = L.gnrf_nr_train_bwd_workspace_bytes(n_img, C, S, nr.n_blocks, nr.min_feat)
+        ws = torch.empty((ws_bytes,), device=fm.device, dtype=torch.uint8)
+        _lib.check(L.gnrf_nr_train_bwd(_lib.ptr_array([t.data_ptr() for t in Tn]), fm.data_ptr(), k["saved"].data_ptr(),
+                                       k["imgs"].data_ptr(), g_imgs.data_ptr(), n_img, C, S, nr.n_blocks, nr.min_feat, g_fm.data_ptr(),
+                                       _lib.ptr_array([t.data_ptr() for t in g_n]), ws.data_ptr(), ws_bytes, o.st), "gnrf_nr_train_bwd")
+        ctx.keep = None
+        grads = [None, g_fm] + g_n
+        need = ctx.needs_input_grad
+        return tuple(gr if (i < len(need) and need[i]) else None for i, gr in enumerate(grads))
+
+
+def render_featmaps(net, xy, rmats, tvecs, kinv, gaze, shape_ext, appea, z_edges, stages=None) -> torch.Tensor:
+    """Differentiable rays -> feature maps [3B+1, C, S, S] (merge_face | eyes_planes | merge | bg_featmap)."""
     tf = branch_tensors(net.fg_CD_predictor_face, shape_ext, appea)
     te = branch_tensors(net.fg_CD_predictor_eyes, shape_ext, appea)
-    tn = [p if p.dim() == 1 else p.flatten(1) for p in net.neural_render.param_list()]
     cfg = {"net": net, "H": net.mlp_h_channel, "C": net.featmap_nc, "S": net.featmap_size, "n_s": net.num_sample_coarse, "stages": stages}
-    return RenderTrainFn.apply(cfg, xy, rmats, tvecs, kinv, gaze, z_edges, net.neural_render.bg_featmap, *tf, *te, *tn)
+    return FeatureMapFn.apply(cfg, xy, rmats, tvecs, kinv, gaze, z_edges, net.neural_render.bg_featmap, *tf, *te)
+
+
+def neural_render_train(net, fm: torch.Tensor) -> torch.Tensor:
+    """Differentiable feature maps -> images through the neural renderer."""
+    tn = [p if p.dim() == 1 else p.flatten(1) for p in net.neural_render.param_list()]
+    cfg = {"net": net, "C": net.featmap_nc, "S": net.featmap_size}
+    return NeuralRenderFn.apply(cfg, fm, *tn)
+
+
+def forward_train(net, xy, rmats, tvecs, kinv, gaze, shape_ext, appea, z_edges, stages=None) -> torch.Tensor:
+    """Differentiable render: returns images [3B+1,3,P,P].  ``shape_ext`` / ``appea`` / ``gaze`` / ``rmats`` / ``tvecs`` may require
+    grad (the reference optimises code offsets and camera deltas, trainer/gazenerf_trainer.py:338-405).  Two chained
+    ``autograd.Function``s: rays -> feature maps, feature maps -> images."""
+    fm = render_featmaps(net, xy, rmats, tvecs, kinv, gaze, shape_ext, appea, z_edges, stages=stages)
+    return neural_render_train(net, fm)

@@ -10,7 +10,9 @@
  *   - plain pointers + ints only; every pointer is a DEVICE pointer on the current CUDA device unless the
  *     parameter is documented "host"; float = IEEE fp32; tensors are dense, row-major in the stated shape.
  *   - no allocation, no ownership transfer: the caller owns every input, output and workspace buffer.
- *   - work is enqueued on `stream` (a cudaStream_t passed as void*); calls are asynchronous and re-entrant.
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); calls are asynchronous and re-entrant: the library keeps no
+ *     device-global tables and reads no environment variables; the only process state is the launch counter, the thread-local
+ *     error string and a mutex-guarded per-device "shared-memory opt-in done" bitmask (any device, any thread may call first).
  *   - return 0 on success, a GNRF_ERR_* code otherwise; gnrf_last_error() returns a thread-local message.
  *     No exception or abort ever crosses the boundary (the reference's train loop swallows exceptions per
  *     batch, trainer/gazenerf_trainer.py:576-582 -- the Python wrapper raises RuntimeError from the code).
@@ -112,6 +114,13 @@ int gnrf_mlp_tc_fwd(int n_branch, const void* const* packed, const float* const*
                     const float* tvecs, const float* z_edges, int B, int N_r, int N_s, float* const* feat_ray,
                     float* const* bg_alpha, float* const* weights, void* workspace, size_t workspace_bytes,
                     gnrf_stream_t stream);
+/* Developer variant of gnrf_mlp_tc_fwd with explicit instrumentation arguments (no environment variables, no hidden state):
+ * dbg_dump (nullable) [10][128][384] fp32 dump of tile 0's per-layer activations; timeline (nullable) [4][10][16] int64 clock64
+ * stamps of CTA 0 (tests/tc_timeline.py); cluster_size 1 or 2 (CTAs sharing each weight stage by TMA multicast; 2 = default). */
+int gnrf_mlp_tc_fwd_debug(int n_branch, const void* const* packed, const float* const* bias, const float* ray_dl,
+                          const float* tvecs, const float* z_edges, int B, int N_r, int N_s, float* const* feat_ray,
+                          float* const* bg_alpha, float* const* weights, void* workspace, size_t workspace_bytes, float* dbg_dump,
+                          long long* timeline, int cluster_size, gnrf_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Feature-map compose: background blend, gaze rotation of channel triplets, max-merge.
@@ -238,6 +247,26 @@ int gnrf_data_loss_bwd(const float* img_face, const float* img_eyes, const float
                        const float* face_mask, const float* full_eye, const float* left_eye, const float* right_eye, int B, int HW,
                        int use_l1, float bg_value, const float* sums, const float* g_terms, float* g_img_face, float* g_img_eyes,
                        float* g_img, float* g_bg_img, gnrf_stream_t stream);
+
+/* =========================================================================================================
+ * Dataset sample -> device tensors (the step before the path).  Replaces the per-item transforms of
+ * GazeDataset.__getitem__ (datasets/eth_xgaze.py:308-360) and GazeNeRFTrainer.prepare_data (trainer/gazenerf_trainer.py:250-337)
+ * on the raw HDF5 records (schema: dataset_pre_processing.py:260-380).  All pointers are DEVICE pointers to the raw u8 / f64 arrays
+ * (the caller uploads the records as stored: 0.98 MB per sample instead of 6 MB of fp32 tensors).
+ *   face_patch_bgr u8 [B,H,W,3] -> img f32 [B,3,H,W] = RGB / 255;   head_mask u8 [B,H,W] -> cv2.erode(3x3 ones, erode_iterations)
+ *   -> f32 [B,1,H,W] (mask VALUES are kept, e.g. 0 / 255);   left / right eye masks -> f32 [B,1,H,W].   W % 4 == 0.
+ * ========================================================================================================= */
+int gnrf_sample_images_to_device(const uint8_t* face_patch_bgr, const uint8_t* head_mask, const uint8_t* left_eye_mask,
+                                 const uint8_t* right_eye_mask, int B, int H, int W, int erode_iterations, float* img,
+                                 float* head_mask_f, float* left_eye_mask_f, float* right_eye_mask_f, gnrf_stream_t stream);
+/* code_row0 f64 [306] (row 0 of the subject's latent_codes), code_rows f64 [B,306] (the samples' own rows; only [279:] = illumination
+ * is taken from them, eth_xgaze.py:346-347), pitchyaw f64 [B,2], c2w_Rmat f64 [B,3,3], c2w_Tvec f64 [B,3], inmat f64 [B,3,3]
+ *   -> iden f32 [B,100], expr [B,79], text [B,100], illu [B,27], gaze [B,2], rmats [B,3,3], tvecs [B,3,1],
+ *      inv_inmats [B,3,3] = inverse of inmat with rows 0,1 scaled by featmap_size / img_size (f64 arithmetic, then cast). */
+int gnrf_sample_meta_to_device(const double* code_row0, const double* code_rows, const double* pitchyaw, const double* c2w_Rmat,
+                               const double* c2w_Tvec, const double* inmat, int B, int featmap_size, int img_size, float* iden,
+                               float* expr, float* text, float* illu, float* gaze, float* rmats, float* tvecs, float* inv_inmats,
+                               gnrf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -557,3 +557,70 @@ def synthetic_loss_inputs(batch: int, size: int, seed: int = 0):
     left, right = box(0.38, 0.46, 0.30, 0.44), box(0.38, 0.46, 0.56, 0.70)
     full_eye = box(0.36, 0.48, 0.28, 0.72)
     return pred, gt, face, full_eye, left, right
+
+
+# --------------------------------------------------------------------------------------
+# dataset sample -> tensors (datasets/eth_xgaze.py:308-360 + trainer/gazenerf_trainer.py:250-337)
+# --------------------------------------------------------------------------------------
+def synthetic_hdf5_records(batch: int, size: int = 512, seed: int = 0) -> Dict[str, np.ndarray]:
+    """Random records in the HDF5 schema of dataset_pre_processing.py:260-380 (dtypes as stored: u8 images / masks, f64 parameters)."""
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:size, 0:size]
+    c = (size - 1) / 2.0
+    head = (((yy - c) / (0.42 * size)) ** 2 + ((xx - c) / (0.34 * size)) ** 2 < 1.0)
+    head_mask = np.stack([np.roll(head, rng.randint(-size // 5, size // 5), axis=rng.randint(2)) for _ in range(batch)]).astype(np.uint8) * 255
+    head_mask[:, :3, :] = 255                       # touches the border: cv2's erosion ignores out-of-image taps
+    head_mask[rng.rand(batch, size, size) < 0.002] = 0   # pin-holes that the 5x5 erosion grows
+    box = lambda y0, y1, x0, x1: ((yy >= y0 * size) & (yy < y1 * size) & (xx >= x0 * size) & (xx < x1 * size))
+    left = np.repeat(box(0.38, 0.46, 0.30, 0.44)[None], batch, 0).astype(np.uint8) * 255
+    right = np.repeat(box(0.38, 0.46, 0.56, 0.70)[None], batch, 0).astype(np.uint8) * 255
+    inmat = np.tile(np.array([[1600.0, 0.0, 256.0], [0.0, 1600.0, 256.0], [0.0, 0.0, 1.0]]), (batch, 1, 1)) + rng.randn(batch, 3, 3) * [[30, 0, 5], [0, 30, 5], [0, 0, 0]]
+    rmat = np.linalg.qr(rng.randn(batch, 3, 3))[0]
+    return {
+        "face_patch": rng.randint(0, 256, (batch, size, size, 3)).astype(np.uint8),   # BGR
+        "head_mask": head_mask, "left_eye_mask": left, "right_eye_mask": right,
+        "latent_codes_row0": rng.randn(306) * 0.5, "latent_codes": rng.randn(batch, 306) * 0.5,
+        "pitchyaw_head": rng.rand(batch, 2) - 0.5, "c2w_Rmat": rmat, "c2w_Tvec": rng.randn(batch, 3) + [0.0, 0.0, 12.0], "inmat": inmat,
+    }
+
+
+def dataset_sample_tensors(rec: Dict[str, np.ndarray], featmap_size: int, opt: Optional[OracleOptions] = None) -> Dict[str, Tensor]:
+    """What the reference's DataLoader item + ``prepare_data`` leave on the trainer, computed the way the reference computes it.
+
+    Per item (datasets/eth_xgaze.py:326-360): ``image[:, :, [2,1,0]]`` then ``ToPILImage -> ToTensor`` (:12) = u8 HWC -> f32 CHW / 255;
+    ``cv2.erode(head_mask, ones((3,3), u8), iterations=2)``; ``code = latent_codes[0]`` with ``[279:]`` from the item's row.
+    Per batch (trainer/gazenerf_trainer.py:256-336): masks ``unsqueeze(1)``; the 306-d code split 100 | 79 | 100 | 27 and cast to float;
+    ``inmat[:, :2, :] *= featmap_size / img_size`` and its closed-form inverse in f64, cast to float.
+    Third-party ops are called, not restated: cv2.erode (OpenCV) and the uint8 -> float / 255 of torchvision's ToTensor."""
+    import cv2
+
+    opt = opt or OracleOptions()
+    b, size = rec["face_patch"].shape[0], rec["face_patch"].shape[1]
+    imgs, heads = [], []
+    for i in range(b):
+        rgb = rec["face_patch"][i][:, :, [2, 1, 0]]
+        imgs.append(torch.from_numpy(np.ascontiguousarray(rgb)).permute(2, 0, 1).contiguous().to(torch.float32).div(255))
+        heads.append(torch.from_numpy(cv2.erode(rec["head_mask"][i], np.ones((3, 3), dtype=np.uint8), iterations=2)))
+    code = np.repeat(rec["latent_codes_row0"][None].copy(), b, 0)
+    code[:, 279:] = rec["latent_codes"][:, 279:]
+    code = torch.from_numpy(code)
+    i0, i1, i2 = opt.iden_code_dims, opt.iden_code_dims + opt.expr_code_dims, opt.iden_code_dims + opt.expr_code_dims + opt.text_code_dims
+    k = torch.from_numpy(rec["inmat"].copy())
+    k[:, :2, :] *= featmap_size / size
+    kinv = torch.zeros_like(k)
+    kinv[:, 0, 0] = 1.0 / k[:, 0, 0]
+    kinv[:, 1, 1] = 1.0 / k[:, 1, 1]
+    kinv[:, 0, 2] = -(k[:, 0, 2] / k[:, 0, 0])
+    kinv[:, 1, 2] = -(k[:, 1, 2] / k[:, 1, 1])
+    kinv[:, 2, 2] = 1.0
+    f = lambda t: t.type(torch.FloatTensor)
+    return {
+        "img_tensor": torch.stack(imgs, 0),
+        "head_mask_tensor": torch.stack(heads, 0).unsqueeze(1),
+        "left_eye_mask_tensor": torch.from_numpy(rec["left_eye_mask"]).unsqueeze(1),
+        "right_eye_mask_tensor": torch.from_numpy(rec["right_eye_mask"]).unsqueeze(1),
+        "base_iden": f(code[:, :i0]), "base_expr": f(code[:, i0:i1]), "base_text": f(code[:, i1:i2]), "base_illu": f(code[:, i2:]),
+        "base_gaze_direction": f(torch.from_numpy(rec["pitchyaw_head"])),
+        "cam_info": {"batch_Rmats": f(torch.from_numpy(rec["c2w_Rmat"])), "batch_Tvecs": f(torch.from_numpy(rec["c2w_Tvec"]).unsqueeze(-1)),
+                     "batch_inv_inmats": f(kinv)},
+    }

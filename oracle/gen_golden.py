@@ -15,7 +15,9 @@ Fixtures
                 reference init under torch.manual_seed(45) (train.py:53); weights are NOT stored (20 MB) --
                 only per-parameter checksums; tests rebuild them with the drop-in module's identical init.
                 variants: ref-init "test", dense-density "test", dense-density "train" (jitter).
-  fine_*.npz    FineSample on the coarse weights of the above (config-3 building block), int64 indices included.
+  fine_*        FineSample on the coarse weights of the above (config-3 building block), int64 indices included.
+  mid_dense_test.npz  hidden=384, featmap_nc=258, 16x16 rays x 64 samples (2 rays per 128-point tile of the fused kernel), 128x128
+                image, B=2, dense density, FineSample with num_sample_fine=64 (the config-3 sample counts); slim (no per-point arrays).
 """
 import os
 import sys
@@ -84,7 +86,7 @@ def make_dense(net, xy, shape, appea, gaze, cam, n_s, scale=30.0):
     return np.array(biases, dtype=np.float64)
 
 
-def run_case(net, opt, mode, xy, uv, shape, appea, gaze, cam, dense, seed_rng=None):
+def run_case(net, opt, mode, xy, uv, shape, appea, gaze, cam, dense, seed_rng=None, n_fine=8, slim=False):
     from utils.model_utils import FineSample  # reference
 
     b = xy.shape[0]
@@ -125,7 +127,7 @@ def run_case(net, opt, mode, xy, uv, shape, appea, gaze, cam, dense, seed_rng=No
             if br == "face":
                 w_face = w
         # FineSample (the only working part of the hier path), deterministic u
-        fopt = types.SimpleNamespace(num_sample_fine=8)
+        fopt = types.SimpleNamespace(num_sample_fine=n_fine)
         fs = FineSample(fopt)(w_face, smp, False)
         for k in ("pts", "zvals", "z_dists"):
             out["fine_" + k] = np32(fs[k])
@@ -133,8 +135,12 @@ def run_case(net, opt, mode, xy, uv, shape, appea, gaze, cam, dense, seed_rng=No
         tw = w_face[:, :, :, 1:-1].reshape(-1, n_s - 2)
         pdf = tw / torch.sum(tw + 1e-5, dim=-1, keepdim=True)
         cdf = F.pad(torch.cumsum(pdf, dim=-1), pad=[1, 0, 0, 0], mode="constant", value=0.0).contiguous()
-        u = torch.linspace(0.0, 1.0, steps=9).view(1, 9).expand(cdf.size(0), 9).contiguous()
+        u = torch.linspace(0.0, 1.0, steps=n_fine + 1).view(1, n_fine + 1).expand(cdf.size(0), n_fine + 1).contiguous()
         out["fine_inds"] = torch.searchsorted(cdf, u, right=True).numpy().astype(np.int64)
+    if slim:  # mid-size fixture: keep what the parity tests read, drop the bulky per-point arrays
+        for k in ("smp_pts", "pe", "mlp_feat_face", "mlp_feat_eyes", "mlp_sigma_face", "mlp_sigma_eyes", "fine_pts", "fine_z_dists",
+                  "depth_face", "depth_eyes"):
+            out.pop(k, None)
     out["in_xy"] = np32(xy)
     out["in_shape"] = np32(shape)
     out["in_appea"] = np32(appea)
@@ -148,6 +154,8 @@ def run_case(net, opt, mode, xy, uv, shape, appea, gaze, cam, dense, seed_rng=No
 
 
 def main():
+    only = set(sys.argv[1:])   # e.g. `python oracle/gen_golden.py mid` regenerates just that fixture family (tiny | std | mid)
+    want = lambda name: not only or name in only
     install_kornia_shim()
     sys.path.insert(0, REF)
     os.chdir(REF)  # RenderUtils opens configs/... relative to cwd (utils/render_utils.py:36)
@@ -169,6 +177,15 @@ def main():
         return ru, ru.ray_xy.expand(b, -1, -1), ru.ray_uv.expand(b, -1, -1), shape, appea, gaze, cam
 
     # ---------------- tiny: all weights stored ----------------
+    if want("tiny"):
+        _gen_tiny(BaseOptions, GazeNeRFNet, inputs)
+    if want("std"):
+        _gen_std(BaseOptions, GazeNeRFNet, inputs)
+    if want("mid"):
+        _gen_mid(BaseOptions, GazeNeRFNet, inputs)
+
+
+def _gen_tiny(BaseOptions, GazeNeRFNet, inputs):
     opt = BaseOptions({"featmap_size": 8, "featmap_nc": 48, "pred_img_size": 64})
     opt.num_sample_coarse = 8
     opt.mlp_hidden_nchannels = 32
@@ -189,6 +206,9 @@ def main():
     np.savez_compressed(os.path.join(OUT, "tiny.npz"), **out)
     print("tiny.npz", sum(v.nbytes for v in out.values()) // 1024, "KiB raw")
 
+
+
+def _gen_std(BaseOptions, GazeNeRFNet, inputs):
     # ---------------- std: real layer widths, weights by seed ----------------
     opt = BaseOptions({"featmap_size": 8, "featmap_nc": 258, "pred_img_size": 64})
     opt.num_sample_coarse = 8
@@ -206,6 +226,24 @@ def main():
         out.update(chk)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
         print(name, sum(v.nbytes for v in out.values()) // 1024, "KiB raw")
+
+
+
+def _gen_mid(BaseOptions, GazeNeRFNet, inputs):
+    # ---------------- mid: 16x16 rays x 64 samples, reference-anchored multi-ray-per-tile case ----------------
+    opt = BaseOptions({"featmap_size": 16, "featmap_nc": 258, "pred_img_size": 128})
+    opt.num_sample_coarse = 64
+    torch.manual_seed(45)
+    net = GazeNeRFNet(opt, include_vd=False, hier_sampling=False).eval()
+    chk = {"chk/" + k: np.array([float(v.double().sum()), float(v.double().abs().sum())]) for k, v in net.state_dict().items()}
+    ru, xy, uv, shape, appea, gaze, cam = inputs(opt, 2)
+    dense_bias = make_dense(net, xy, shape, appea, gaze, cam, opt.num_sample_coarse, scale=4.0)
+    out = run_case(net, opt, "test", xy, uv, shape, appea, gaze, cam, dense=True, n_fine=64, slim=True)
+    out["dense_bias"] = dense_bias
+    out["dense_scale"] = np.array([4.0])
+    out.update(chk)
+    np.savez_compressed(os.path.join(OUT, "mid_dense_test.npz"), **out)
+    print("mid_dense_test", sum(v.nbytes for v in out.values()) // 1024, "KiB raw")
 
 
 if __name__ == "__main__":

@@ -9,10 +9,10 @@ import bench
 
 dev = torch.device("cuda:0")
 prof = torch.zeros(4 * 10 * 16, dtype=torch.int64, device=dev)
-os.environ["GNRF_TC_PROF_PTR"] = str(prof.data_ptr())
 opt = G.BaseOptions()
 torch.manual_seed(45)
 net = G.GazeNeRFNet(opt, include_vd=False, hier_sampling=False).to(dev).eval()
+net.tc_debug = (None, prof, 2)   # -> gnrf_mlp_tc_fwd_debug(..., timeline = prof, cluster_size = 2)
 kw = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in bench.synthetic_inputs(torch, G, opt, 1, 0).items()}
 for _ in range(3):
     net("test", **kw)

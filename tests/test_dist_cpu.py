@@ -63,3 +63,62 @@ def test_all_gather_images_world2_gloo(gb):
         assert p.exitcode == 0
     res = sorted(q.get(timeout=10) for _ in range(2))
     assert res == [(0, True), (1, True)]
+
+
+class _StubNet(object):
+    """Stands in for GazeNeRFNet in the host-logic test of BatchShardedRenderer (CPU, gloo): images are a function of the codes."""
+
+    def __init__(self, hier):
+        self.hier_sampling, self.pred_img_size, self.gather_ctx, self.gather_used = hier, 4, None, False
+
+    def __call__(self, mode, **kw):
+        b = kw["batch_xy"].shape[0]
+        img = lambda s: (kw["shape_code"][:, :1].view(b, 1, 1, 1) + s).expand(b, 3, 4, 4).contiguous()
+        d = {"merge_img_face": img(0.0), "merge_img_eyes": img(1.0), "merge_img": img(2.0), "bg_img": torch.ones(1, 3, 4, 4)}
+        out = {"coarse_dict": d}
+        if self.hier_sampling:
+            out["fine_dict"] = {k: v + 10.0 for k, v in d.items()}
+        return out
+
+
+def _renderer_worker(rank, world, port, q):
+    from gazenerf_b200.dist import BatchShardedRenderer
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ok = True
+        gb = 5   # ragged: 3 + 2
+        kw = {"batch_xy": torch.zeros(gb, 2, 4), "shape_code": torch.arange(gb).float().view(gb, 1).expand(gb, 179).contiguous(), "batch_uv": None}
+        # hierarchical net with fused_gather requested: must take the collective path and return BOTH dicts for the whole batch
+        r = BatchShardedRenderer(_StubNet(hier=True), fused_gather=True)
+        out = r("test", **kw)
+        want = torch.arange(gb).float().view(gb, 1, 1, 1).expand(gb, 3, 4, 4)
+        ok = ok and torch.equal(out["coarse_dict"]["merge_img"], want + 2.0) and torch.equal(out["fine_dict"]["merge_img_eyes"], want + 11.0)
+        # only_merge callers never enter the fused path either
+        out = BatchShardedRenderer(_StubNet(hier=False), fused_gather=True)("test", only_merge=True, **kw)
+        ok = ok and torch.equal(out["coarse_dict"]["merge_img_face"], want)
+        # global batch smaller than the world: every rank raises BEFORE any collective (no rank is left blocked)
+        small = {"batch_xy": torch.zeros(1, 2, 4), "shape_code": torch.zeros(1, 179), "batch_uv": None}
+        try:
+            BatchShardedRenderer(_StubNet(hier=False))("test", **small)
+            ok = False
+        except ValueError:
+            pass
+        dist.barrier()   # still in step with the peer
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_batch_sharded_renderer_host_logic_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 17
+    procs = [ctx.Process(target=_renderer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert sorted(q.get(timeout=10) for _ in range(2)) == [(0, True), (1, True)]

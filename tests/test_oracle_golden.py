@@ -126,3 +126,42 @@ def test_jitter_matches_reference():
     s = O.sample_points(xy, R, T, K, opt.num_sample_coarse, opt.world_z1, opt.world_z2, jitter_u=torch.from_numpy(g["jitter_u"]))
     assert np.array_equal(s["zvals"].numpy(), g["smp_zvals"])
     assert np.array_equal(s["pts"].numpy(), g["smp_pts"])
+
+
+def _mid_state_dict(g):
+    """Weights of the mid fixture: the drop-in module's reference-identical seeded init (checksums stored in the fixture) +
+    the dense-density variant with the fixture's scale / biases."""
+    import gazenerf_b200 as G
+    meta = g["meta"]
+    opt = G.BaseOptions({"featmap_size": int(meta[0]), "featmap_nc": int(meta[1]), "pred_img_size": int(meta[2])})
+    opt.num_sample_coarse = int(meta[3])
+    torch.manual_seed(45)
+    net = G.GazeNeRFNet(opt, include_vd=False, hier_sampling=False)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    for k, v in sd.items():
+        chk = g["chk/" + k]
+        assert abs(float(v.double().sum()) - chk[0]) <= 1e-9 * max(1.0, abs(chk[1])), k
+    return O.densify(sd, *g["dense_bias"], scale=float(g["dense_scale"][0]))
+
+
+def test_mid_size_reference_golden_16x16x64():
+    """16x16 rays x 64 samples (two rays per 128-point tile of the fused kernel), real layer widths, B = 2: the oracle against the
+    reference's own outputs -- features, bg_alpha, weights, the four 128x128 images and FineSample(64) int64 indices."""
+    g = load_golden("mid_dense_test")
+    opt = _opt(g["meta"], n_fine=64)
+    sd = _mid_state_dict(g)
+    xy, shape, appea, gaze, R, T, K = _inputs(g)
+    out = O.forward(sd, opt, "test", xy, shape, appea, gaze, R, T, K, return_stages=True)
+    st = out["stages"]
+    b = xy.shape[0]
+    for name in ("face", "eyes"):
+        assert rel_l2(st["feat_" + name].reshape(b, 258, -1), g["feat_" + name]) < TOL, name
+        assert max_rel(st["bg_alpha_" + name].reshape(b, 1, -1), g["bg_alpha_" + name]) < 2e-5, name
+        assert rel_l2(st["w_" + name], g["w_" + name]) < 1e-5, name
+    for k in ("merge_img_face", "merge_img_eyes", "merge_img", "bg_img"):
+        assert float((out["coarse_dict"][k] - torch.from_numpy(g["img_" + k])).abs().max()) < 5e-6, k
+    fs = O.fine_sample(torch.from_numpy(g["w_face"]), st["zvals"], st["ray_o"], st["ray_d"], st["ray_l"], n_fine=64)
+    assert np.array_equal(fs["inds"].numpy(), g["fine_inds"])   # integer work: bit-exact
+    assert np.array_equal(fs["zvals"].numpy(), g["fine_zvals"])
+    assert fs["zvals"].shape[-1] == 64 + 64
+    assert 0.1 < float(g["bg_alpha_face"].mean()) < 0.9   # non-vacuous
