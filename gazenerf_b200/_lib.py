@@ -36,7 +36,8 @@ SYMBOLS = [
     "gnrf_mlp_tc_packed_bytes", "gnrf_mlp_tc_bias_floats", "gnrf_mlp_tc_pack", "gnrf_mlp_tc_fold",
     "gnrf_mlp_tc_workspace_bytes", "gnrf_mlp_tc_fwd", "gnrf_mlp_tc_fwd_debug",
     "gnrf_compose_fwd", "gnrf_nr_workspace_bytes", "gnrf_neural_render_fwd",
-    "gnrf_nr_tc_packed_bytes", "gnrf_nr_tc_pack", "gnrf_neural_render_tc_fwd", "gnrf_neural_render_tc_fwd_gather",
+    "gnrf_nr_tc_packed_bytes", "gnrf_nr_tc_pack", "gnrf_neural_render_tc_fwd", "gnrf_neural_render_tc_layerwise_fwd",
+    "gnrf_neural_render_tc_fwd_gather",
     # training path
     "gnrf_conv_tc_packed_bytes", "gnrf_conv_tc_pack", "gnrf_conv_tc", "gnrf_wgrad_tc_workspace_bytes", "gnrf_wgrad_tc",
     "gnrf_pe_fwd", "gnrf_pe_bwd", "gnrf_composite_cm_fwd", "gnrf_composite_cm_bwd", "gnrf_geom_bwd",
@@ -146,6 +147,7 @@ def lib() -> ctypes.CDLL:
     L.gnrf_nr_tc_packed_bytes.argtypes = [i32, i32, i32]
     L.gnrf_nr_tc_pack.argtypes = [vp, i32, i32, i32, vp, vp]
     L.gnrf_neural_render_tc_fwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, sz, vp]
+    L.gnrf_neural_render_tc_layerwise_fwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, sz, vp]
     L.gnrf_neural_render_tc_fwd_gather.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, sz, vp, vp, i32, i32, i32, i32, vp]
     i64 = c.c_longlong
     L.gnrf_conv_tc_packed_bytes.restype = sz

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "conv_tc.cuh"
 #include "nr_plan.cuh"
+#include "nr_fused.cuh"
 
 namespace gnrf {
 
@@ -318,9 +319,55 @@ static NrPlan nr_plan(int N, int C, int S, int n_blocks, int min_feat) {
 
 using namespace gnrf;
 
+// ---- fused path (nr_fused.cuh): two kernels per level + the final blur / to-RGB pass ------------------------------------------
+static inline int nr_width(int C, int i, int min_feat) { return (C >> i) > min_feat ? (C >> i) : min_feat; }
+
+// the fused kernels cover this configuration: every level fits their smem / TMEM budgets and every level's pixel count is a
+// multiple of the 128-pixel tile
+static bool nr_fused_supported(int C, int S, int n_blocks, int min_feat) {
+  if (n_blocks < 1 || n_blocks > 4 || (S * S) % nrf::kTile != 0 || S % 4 != 0) return false;
+  for (int i = 0; i < n_blocks; ++i)
+    if (!nrf::level_supported(nrf::level_geom(nr_width(C, i, min_feat), nr_width(C, i + 1, min_feat)))) return false;
+  return true;
+}
+static size_t nr_fused_pack_bytes(int C, int n_blocks, int min_feat) {
+  size_t tot = 0;
+  for (int i = 0; i < n_blocks; ++i) tot += nrf::level_pack(nrf::level_geom(nr_width(C, i, min_feat), nr_width(C, i + 1, min_feat))).total;
+  return tot;
+}
+struct NrFusedPlan {
+  size_t t1, x, pre[2], rgb[2], rgb_up, total;
+};
+static NrFusedPlan nr_fused_plan(int N, int C, int S, int n_blocks, int min_feat) {
+  size_t m_t1 = 0, m_x = 0, m_pre = 0;
+  for (int i = 0; i < n_blocks; ++i) {
+    const nrf::LevelGeom g = nrf::level_geom(nr_width(C, i, min_feat), nr_width(C, i + 1, min_feat));
+    const size_t hw = ((size_t)S << i) * ((size_t)S << i);
+    m_t1 = max(m_t1, (size_t)N * (hw / nrf::kTile) * g.k2_steps * nrf::kStepBytes);
+    if (i > 0) m_x = max(m_x, (size_t)N * g.ci * hw * sizeof(float));
+    m_pre = max(m_pre, (size_t)N * g.co * 4 * hw * sizeof(float));
+  }
+  const size_t P = (size_t)S << n_blocks;
+  const size_t m_rgb = (size_t)N * 3 * P * P * sizeof(float);
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  NrFusedPlan p;
+  size_t off = 0;
+  p.t1 = off; off += al(m_t1);
+  p.x = off; off += al(m_x);
+  p.pre[0] = off; off += al(m_pre);
+  p.pre[1] = off; off += al(m_pre);
+  p.rgb[0] = off; off += al(m_rgb);
+  p.rgb[1] = off; off += al(m_rgb);
+  p.rgb_up = off; off += al(m_rgb);
+  p.total = off;
+  return p;
+}
+
 extern "C" size_t gnrf_nr_workspace_bytes(int N, int C, int S, int n_blocks, int min_feat) {
   if (N <= 0 || C <= 0 || S <= 0 || n_blocks < 0) return 0;
-  return nr_plan(N, C, S, n_blocks, min_feat).total;
+  size_t need = nr_plan(N, C, S, n_blocks, min_feat).total;
+  if (nr_fused_supported(C, S, n_blocks, min_feat)) need = max(need, nr_fused_plan(N, C, S, n_blocks, min_feat).total);
+  return need;
 }
 
 // per-level buffers of one forward: aliased across levels for inference (nr_plan), distinct for training (nr_train_plan)
@@ -335,12 +382,86 @@ static int nr_forward_bufs(const float* const* params, const unsigned char* pack
                            int min_feat, float* img, const NrBufs& bufs, cudaStream_t st);
 
 // packed == nullptr: fp32 CUDA-core GEMMs; else: tcgen05 bf16x3 GEMMs on the packed weight streams (3 layers per block)
+static size_t nr_conv_pack_bytes(int C, int n_blocks, int min_feat);
+
+// Fused forward: per level nrf_a (x on load -> W1 GEMM -> t1 tiles + running RGB) and nrf_b (W2 GEMM -> drain -> W3 GEMM -> pre), then the
+// final pass  img = sigmoid(Blur(up2(R)) + toRGB(LReLU(Blur(pre))))  (models/neural_renderer.py:98-113).
+static int nr_forward_fused(const float* const* params, const unsigned char* fpack, const float* featmap, int N, int C, int S, int n_blocks,
+                            int min_feat, float* img, void* workspace, size_t workspace_bytes, cudaStream_t st, const GatherDst* gather) {
+  const NrFusedPlan pl = nr_fused_plan(N, C, S, n_blocks, min_feat);
+  if (workspace_bytes < pl.total)
+    return fail(GNRF_ERR_ARG, "gnrf_neural_render_tc_fwd: workspace %zu < required %zu bytes", workspace_bytes, pl.total);
+  for (int i = 0; i < 8 * n_blocks + 2; ++i) GNRF_CHECK_ARG(params[i] != nullptr);
+  int n_sm = 0;
+  {
+    int rc = device_once(kOnceNrFused, &n_sm, []() -> int {
+      GNRF_CUDA(cudaFuncSetAttribute(nrf::nrf_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nrf::kSmemBudget));
+      GNRF_CUDA(cudaFuncSetAttribute(nrf::nrf_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nrf::kSmemBudget));
+      return GNRF_OK;
+    });
+    if (rc != GNRF_OK) return rc;
+  }
+  char* ws = static_cast<char*>(workspace);
+  unsigned char* t1 = reinterpret_cast<unsigned char*>(ws + pl.t1);
+  float* xbuf = reinterpret_cast<float*>(ws + pl.x);
+  float* pre[2] = {reinterpret_cast<float*>(ws + pl.pre[0]), reinterpret_cast<float*>(ws + pl.pre[1])};
+  float* rgb[2] = {reinterpret_cast<float*>(ws + pl.rgb[0]), reinterpret_cast<float*>(ws + pl.rgb[1])};
+  float* rgb_up = reinterpret_cast<float*>(ws + pl.rgb_up);
+  int s = S;
+  for (int i = 0; i < n_blocks; ++i) {
+    const int ci = nr_width(C, i, min_feat), co = nr_width(C, i + 1, min_feat);
+    const nrf::LevelGeom g = nrf::level_geom(ci, co);
+    const int n_tiles = N * (s * s / nrf::kTile);
+    nrf::AArgs a;
+    a.src = i == 0 ? featmap : pre[(i - 1) & 1];
+    a.blur = i == 0 ? 0 : 1;
+    a.x_out = i == 0 ? nullptr : xbuf;
+    a.pack = fpack;
+    a.t1 = t1;
+    a.rgb_out = rgb[i & 1];
+    a.rgb_prev = i == 0 ? nullptr : rgb[(i - 1) & 1];
+    a.ci = ci; a.co = co; a.H = s; a.W = s; a.n_img = N;
+    // >= 120 KB of dynamic smem per CTA: one CTA per SM, so its 512-column TMEM allocation never waits for a neighbour
+    nrf::nrf_a_kernel<<<min(n_tiles, n_sm), nrf::kAThreads, max(nrf::nrf_a_smem_bytes(g), 120 * 1024), st>>>(a);
+    nrf::BArgs b;
+    b.t1 = t1;
+    b.pack = fpack;
+    b.xres = i == 0 ? featmap : xbuf;
+    b.pre = pre[i & 1];
+    b.ci = ci; b.co = co; b.H = s; b.W = s; b.n_img = N;
+    const int n_items = n_tiles * (4 / g.qg);
+    nrf::nrf_b_kernel<<<min(n_items, n_sm), nrf::kBThreads, max(nrf::nrf_b_smem_bytes(g), 120 * 1024), st>>>(b);
+    GNRF_LAUNCH_CHECK();
+    count_launches(2);
+    fpack += nrf::level_pack(g).total;
+    s *= 2;
+  }
+  // final: Blur(up2(R_{nb-1})) (3 channels), then img = sigmoid(. + toRGB_nb(LReLU(Blur(pre_{nb-1})))), all-gather fused when requested
+  {
+    const int co = nr_width(C, n_blocks, min_feat);
+    const int hs = s / 2;
+    nrf::ub_kernel<<<dim3(ceil_div(s * s, 256), N * 3), 256, 0, st>>>(rgb[(n_blocks - 1) & 1], hs, hs, rgb_up);
+    dim3 grid(ceil_div(s * s / 4, 256), N);
+    blur_lrelu_rgb_kernel<<<grid, 256, 3 * co * sizeof(float), st>>>(pre[(n_blocks - 1) & 1], co, s, s, params[4 * n_blocks + 2 * n_blocks],
+                                                                    params[4 * n_blocks + 2 * n_blocks + 1], rgb_up, 1, nullptr, img,
+                                                                    gather ? *gather : GatherDst{});
+    GNRF_LAUNCH_CHECK();
+    count_launches(2);
+  }
+  return GNRF_OK;
+}
+
+// allow_fused == false: the layer-wise conv_tc path (also taken for feature maps the fused kernels do not cover, i.e. fewer than 128
+// pixels per image), kept as an on-device cross-check of the fused kernels
 static int nr_forward(const float* const* params, const unsigned char* packed, const float* featmap, int N, int C, int S, int n_blocks,
                       int min_feat, float* img, void* workspace, size_t workspace_bytes, gnrf_stream_t stream,
-                      const GatherDst* gather = nullptr) {
+                      const GatherDst* gather = nullptr, bool allow_fused = true) {
   GNRF_CHECK_ARG(params && featmap && img && workspace);
   GNRF_CHECK_ARG(N > 0 && C > 0 && S >= 2 && n_blocks >= 1 && n_blocks <= 6);
   GNRF_CHECK_ARG(S % 4 == 0);
+  if (packed != nullptr && allow_fused && nr_fused_supported(C, S, n_blocks, min_feat))
+    return nr_forward_fused(params, packed + nr_conv_pack_bytes(C, n_blocks, min_feat), featmap, N, C, S, n_blocks, min_feat, img, workspace,
+                            workspace_bytes, as_stream(stream), gather);
   NrPlan pl = nr_plan(N, C, S, n_blocks, min_feat);
   if (workspace_bytes < pl.total)
     return fail(GNRF_ERR_ARG, "gnrf_neural_render_fwd: workspace %zu < required %zu bytes", workspace_bytes, pl.total);
@@ -463,7 +584,8 @@ extern "C" int gnrf_neural_render_fwd(const float* const* params, const float* f
   return nr_forward(params, nullptr, featmap, N, C, S, n_blocks, min_feat, img, workspace, workspace_bytes, stream);
 }
 
-extern "C" size_t gnrf_nr_tc_packed_bytes(int C, int n_blocks, int min_feat) {
+// packed = [per-layer conv_tc streams (layer-wise path: training forward, small feature maps)] [fused per-level images (nr_fused.cuh)]
+static size_t gnrf_nr_tc_packed_bytes_conv(int C, int n_blocks, int min_feat) {
   size_t tot = 0;
   for (int i = 0; i < n_blocks; ++i) {
     int ci = (C >> i) > min_feat ? (C >> i) : min_feat;
@@ -471,6 +593,12 @@ extern "C" size_t gnrf_nr_tc_packed_bytes(int C, int n_blocks, int min_feat) {
     tot += tc::conv_layer_plan(2 * ci, ci).total_bytes + tc::conv_layer_plan(4 * ci, 2 * ci).total_bytes + tc::conv_layer_plan(co, ci).total_bytes;
   }
   return tot;
+}
+static size_t nr_conv_pack_bytes(int C, int n_blocks, int min_feat) { return gnrf_nr_tc_packed_bytes_conv(C, n_blocks, min_feat); }
+
+extern "C" size_t gnrf_nr_tc_packed_bytes(int C, int n_blocks, int min_feat) {
+  if (C <= 0 || n_blocks < 1 || n_blocks > 6) return 0;
+  return nr_conv_pack_bytes(C, n_blocks, min_feat) + nr_fused_pack_bytes(C, n_blocks, min_feat);
 }
 
 extern "C" int gnrf_nr_tc_pack(const float* const* params, int C, int n_blocks, int min_feat, void* packed, gnrf_stream_t stream) {
@@ -490,6 +618,21 @@ extern "C" int gnrf_nr_tc_pack(const float* const* params, int C, int n_blocks, 
       dst += pl[l].total_bytes;
     }
   }
+  // fused per-level images (weights of level i: PSU layer_1 / layer_2, feat_layers[i], and the to-RGB head of the level's INPUT)
+  for (int i = 0; i < n_blocks; ++i) {
+    int ci = (C >> i) > min_feat ? (C >> i) : min_feat;
+    int co = (C >> (i + 1)) > min_feat ? (C >> (i + 1)) : min_feat;
+    nrf::PackArgs pa;
+    pa.w1 = params[4 * i]; pa.b1 = params[4 * i + 1]; pa.w2 = params[4 * i + 2]; pa.b2 = params[4 * i + 3];
+    pa.w3 = params[4 * n_blocks + 2 * (n_blocks + 1) + 2 * i]; pa.b3 = params[4 * n_blocks + 2 * (n_blocks + 1) + 2 * i + 1];
+    pa.wrgb = params[4 * n_blocks + 2 * i]; pa.brgb = params[4 * n_blocks + 2 * i + 1];
+    GNRF_CHECK_ARG(pa.wrgb && pa.brgb);
+    pa.dst = dst;
+    nrf::nrf_pack_kernel<<<148, 256, 0, as_stream(stream)>>>(pa, ci, co);
+    GNRF_LAUNCH_CHECK();
+    count_launches(1);
+    dst += nrf::level_pack(nrf::level_geom(ci, co)).total;
+  }
   return GNRF_OK;
 }
 
@@ -499,6 +642,14 @@ extern "C" int gnrf_neural_render_tc_fwd(const float* const* params, const void*
   GNRF_CHECK_ARG(packed);
   return nr_forward(params, static_cast<const unsigned char*>(packed), featmap, N, C, S, n_blocks, min_feat, img, workspace,
                     workspace_bytes, stream);
+}
+
+extern "C" int gnrf_neural_render_tc_layerwise_fwd(const float* const* params, const void* packed, const float* featmap, int N, int C,
+                                                   int S, int n_blocks, int min_feat, float* img, void* workspace, size_t workspace_bytes,
+                                                   gnrf_stream_t stream) {
+  GNRF_CHECK_ARG(packed);
+  return nr_forward(params, static_cast<const unsigned char*>(packed), featmap, N, C, S, n_blocks, min_feat, img, workspace,
+                    workspace_bytes, stream, nullptr, false);
 }
 
 // ------------------------------------------------------------------------------------------------- training forward

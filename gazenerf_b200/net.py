@@ -92,7 +92,9 @@ class NeuralRendererParams(nn.Module):
         assert out_dim == 3 and final_actvn
         self.bg_type, self.featmap_size, self.n_feat, self.min_feat = bg_type, featmap_size, feat_nc, min_feat
         self.n_blocks = int(math.log2(img_size) - math.log2(featmap_size))
-        self.impl = "tc"  # "tc": tcgen05 bf16x3 convs (default) | "simt": fp32 CUDA-core convs
+        # "tc": tcgen05 bf16x3, fused level kernels where the shape allows (default) | "tc_layerwise": one tcgen05 launch per 1x1 conv |
+        # "simt": fp32 CUDA-core convs
+        self.impl = "tc"
         w = lambda i: max(feat_nc // (2 ** i), min_feat)
         self.feat_upsample_list = nn.ModuleList([_PixelShuffleUpsampleParams(w(i)) for i in range(self.n_blocks)])
         self.rgb_upsample = nn.Sequential(nn.Identity(), _Blur())  # index 1 carries the "f" buffer
@@ -176,10 +178,11 @@ def neural_render(nr: NeuralRendererParams, x: torch.Tensor, gather=None) -> tor
         _lib.check(L.gnrf_neural_render_tc_fwd_gather(_ptrs(params), packed.data_ptr(), x.data_ptr(), n, c, s, nr.n_blocks, nr.min_feat,
                                                       img.data_ptr(), ws.data_ptr(), ws_bytes, _lib.ptr_array(peers), mc or None, gather.world,
                                                       gather.rank, gather.b_local, gather.gb, _stream()), "gnrf_neural_render_tc_fwd_gather")
-    elif nr.impl == "tc":
+    elif nr.impl in ("tc", "tc_layerwise"):
         packed = nr.packed_tc()
-        _lib.check(L.gnrf_neural_render_tc_fwd(_ptrs(params), packed.data_ptr(), x.data_ptr(), n, c, s, nr.n_blocks, nr.min_feat,
-                                               img.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "gnrf_neural_render_tc_fwd")
+        fn = L.gnrf_neural_render_tc_fwd if nr.impl == "tc" else L.gnrf_neural_render_tc_layerwise_fwd
+        _lib.check(fn(_ptrs(params), packed.data_ptr(), x.data_ptr(), n, c, s, nr.n_blocks, nr.min_feat,
+                      img.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "gnrf_neural_render_tc_fwd")
     else:
         _lib.check(L.gnrf_neural_render_fwd(_ptrs(params), x.data_ptr(), n, c, s, nr.n_blocks, nr.min_feat, img.data_ptr(),
                                             ws.data_ptr(), ws_bytes, _stream()), "gnrf_neural_render_fwd")

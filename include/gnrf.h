@@ -140,15 +140,22 @@ size_t gnrf_nr_workspace_bytes(int N, int C, int S, int n_blocks, int min_feat);
 int gnrf_neural_render_fwd(const float* const* params, const float* featmap, int N, int C, int S, int n_blocks,
                            int min_feat, float* img, void* workspace, size_t workspace_bytes, gnrf_stream_t stream);
 
-/* Same computation with the 1x1 convolutions of the PixelShuffleUpsample blocks and feat_layers on tcgen05 tensor cores
- * (bf16x3 split precision, fp32 accumulate in TMEM; csrc/conv_tc.cu).  gnrf_nr_tc_pack re-arranges those 3*n_blocks weight
- * matrices (hi/lo split, UMMA core-matrix K-slices) into `packed` (gnrf_nr_tc_packed_bytes, 128-byte aligned); redo after
- * every weight update.  params / workspace as for gnrf_neural_render_fwd (the to-RGB heads stay fp32). */
+/* Same computation on tcgen05 tensor cores (bf16x3 split precision, fp32 accumulate in TMEM).  gnrf_nr_tc_pack re-arranges the
+ * weight matrices (hi/lo split, UMMA core-matrix K-slices) into `packed` (gnrf_nr_tc_packed_bytes, 128-byte aligned); redo after
+ * every weight update.  params / workspace as for gnrf_neural_render_fwd.
+ * gnrf_neural_render_tc_fwd runs the FUSED level kernels (csrc/nr_fused.cuh: per level, x = LeakyReLU(Blur(.)) formed on load -> W1 GEMM
+ * (+ to-RGB rows) -> t1 in UMMA operand form; W2 GEMM -> drain -> W3 GEMM with the 4ci-wide pixel-shuffled tensor never leaving the
+ * SM) whenever every level has a multiple of 128 pixels per image and fits the kernels' smem / TMEM budgets (true for the reference
+ * configuration 258 ch, 64x64 -> 512x512), else the layer-wise path; gnrf_neural_render_tc_layerwise_fwd always runs the layer-wise
+ * path (one conv_tc_kernel launch per 1x1 convolution, csrc/conv_tc.cu), kept as an on-device cross-check. */
 size_t gnrf_nr_tc_packed_bytes(int C, int n_blocks, int min_feat);
 int gnrf_nr_tc_pack(const float* const* params, int C, int n_blocks, int min_feat, void* packed, gnrf_stream_t stream);
 int gnrf_neural_render_tc_fwd(const float* const* params, const void* packed, const float* featmap, int N, int C, int S,
                               int n_blocks, int min_feat, float* img, void* workspace, size_t workspace_bytes,
                               gnrf_stream_t stream);
+int gnrf_neural_render_tc_layerwise_fwd(const float* const* params, const void* packed, const float* featmap, int N, int C, int S,
+                                        int n_blocks, int min_feat, float* img, void* workspace, size_t workspace_bytes,
+                                        gnrf_stream_t stream);
 
 /* Multi-GPU batch sharding (one process per GPU): gnrf_neural_render_tc_fwd with the all-gather of the rendered images FUSED into
  * the kernel that produces them.  The first 3 * b_local images of the batch (merge_img_face | merge_img_eyes | merge_img of this

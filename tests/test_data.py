@@ -41,7 +41,7 @@ def test_sample_to_device_vs_oracle(B, size):
     for _ in range(2):   # staging buffers are re-used
         got = stager(rec)
     torch.cuda.synchronize()
-    assert stager.h2d_bytes() < 0.2 * sum(v.numel() * 4 for k, v in got.items() if torch.is_tensor(v))   # raw records, not fp32 tensors
+    assert stager.h2d_bytes() < 0.3 * sum(v.numel() * 4 for k, v in got.items() if torch.is_tensor(v))   # raw records, not fp32 tensors
     for k in ("img_tensor", "base_iden", "base_expr", "base_text", "base_illu", "base_gaze_direction"):
         assert got[k].dtype == torch.float32 and torch.equal(got[k].cpu(), ref[k]), k
     for k in ("head_mask_tensor", "left_eye_mask_tensor", "right_eye_mask_tensor"):

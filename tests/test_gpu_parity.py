@@ -189,8 +189,8 @@ def test_compose_vs_oracle(dev):
 
 
 # ----------------------------------------------------------------------------------------------- neural renderer
-@pytest.mark.parametrize("impl", ["simt", "tc"])
-@pytest.mark.parametrize("C,Ssz,nb", [(48, 8, 3), (258, 8, 3), (258, 16, 2)])
+@pytest.mark.parametrize("impl", ["simt", "tc", "tc_layerwise"])
+@pytest.mark.parametrize("C,Ssz,nb", [(48, 8, 3), (258, 8, 3), (258, 16, 2), (258, 32, 2), (96, 16, 3)])
 def test_neural_render_vs_oracle(dev, C, Ssz, nb, impl):
     torch.manual_seed(11)
     nr = G.NeuralRendererParams(feat_nc=C, featmap_size=Ssz, img_size=Ssz << nb)
@@ -198,7 +198,7 @@ def test_neural_render_vs_oracle(dev, C, Ssz, nb, impl):
     x = torch.randn(3, C, Ssz, Ssz)
     ref = O.neural_render(sd, x, nb)
     nr = nr.to(dev)
-    nr.impl = impl  # fp32 CUDA-core convs | tcgen05 bf16x3 convs
+    nr.impl = impl  # fp32 CUDA-core convs | tcgen05 bf16x3: fused level kernels where supported (S*S % 128 == 0) | layer-wise convs
     img = nr(x.to(dev)).cpu()
     assert img.shape == ref.shape
     assert float((img - ref).abs().max()) < 2e-5
