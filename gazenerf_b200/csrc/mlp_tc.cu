@@ -844,29 +844,34 @@ __global__ void pack_stream_kernel(PackSrc src, const float* __restrict__ wf, un
   }
 }
 
-// per-face biases: bias[b] = base + code / appearance contributions (fold i)
-__global__ void fold_kernel(const float* __restrict__ aux, const float* __restrict__ shape_ext, const float* __restrict__ appea,
-                            float* __restrict__ bias) {
+// per-face biases: bias[b] = base + code / appearance contributions (fold i).  One warp per output row: the lanes stride over the
+// 181 code (127 appearance) columns of the row, so the weight reads are coalesced; rows without a fold are plain copies.
+constexpr int kFoldWarps = 8;
+__global__ void __launch_bounds__(kFoldWarps * 32) fold_kernel(const float* __restrict__ aux, const float* __restrict__ shape_ext,
+                                                             const float* __restrict__ appea, float* __restrict__ bias) {
   const int b = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * kFoldWarps + (threadIdx.x >> 5);
   if (i >= kBiasFloats) return;
-  float v = aux[kAuxBaseBias + i];
   const int layer = i / kHidden;
   const int n = i - layer * kHidden;
+  const float* w = nullptr;
+  const float* c = nullptr;
+  int len = 0;
   if (layer == 0 || layer == 5) {
-    const float* w = aux + (layer == 0 ? kAuxW0c : kAuxW5c) + (size_t)n * GNRF_SHAPE_EXT_DIMS;
-    const float* c = shape_ext + (size_t)b * GNRF_SHAPE_EXT_DIMS;
-    float acc = 0.0f;
-    for (int k = 0; k < GNRF_SHAPE_EXT_DIMS; ++k) acc = fmaf(w[k], c[k], acc);
-    v += acc;
+    w = aux + (layer == 0 ? kAuxW0c : kAuxW5c) + (size_t)n * GNRF_SHAPE_EXT_DIMS;
+    c = shape_ext + (size_t)b * GNRF_SHAPE_EXT_DIMS;
+    len = GNRF_SHAPE_EXT_DIMS;
   } else if (layer == 8 && n < kH2) {
-    const float* w = aux + kAuxW1c + (size_t)n * GNRF_APPEA_DIMS;
-    const float* c = appea + (size_t)b * GNRF_APPEA_DIMS;
-    float acc = 0.0f;
-    for (int k = 0; k < GNRF_APPEA_DIMS; ++k) acc = fmaf(w[k], c[k], acc);
-    v += acc;
+    w = aux + kAuxW1c + (size_t)n * GNRF_APPEA_DIMS;
+    c = appea + (size_t)b * GNRF_APPEA_DIMS;
+    len = GNRF_APPEA_DIMS;
   }
-  bias[(size_t)b * kBiasFloats + i] = v;
+  float acc = 0.0f;
+  for (int k = lane; k < len; k += 32) acc = fmaf(__ldg(w + k), __ldg(c + k), acc);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) bias[(size_t)b * kBiasFloats + i] = aux[kAuxBaseBias + i] + acc;
 }
 
 }  // namespace tc
@@ -902,8 +907,8 @@ extern "C" int gnrf_mlp_tc_fold(const void* packed, const float* shape_ext, cons
                                 gnrf_stream_t stream) {
   GNRF_CHECK_ARG(packed && shape_ext && appea && bias && B > 0);
   const float* aux = reinterpret_cast<const float*>(static_cast<const unsigned char*>(packed) + kStreamBytes);
-  dim3 grid(ceil_div(kBiasFloats, 128), B);
-  fold_kernel<<<grid, 128, 0, as_stream(stream)>>>(aux, shape_ext, appea, bias);
+  dim3 grid(ceil_div(kBiasFloats, kFoldWarps), B);
+  fold_kernel<<<grid, kFoldWarps * 32, 0, as_stream(stream)>>>(aux, shape_ext, appea, bias);
   GNRF_LAUNCH_CHECK();
   count_launches(1);
   return GNRF_OK;

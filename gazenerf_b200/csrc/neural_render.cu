@@ -178,10 +178,12 @@ __device__ __forceinline__ void multimem_st_v4(float* addr, float a, float b, fl
 // Used after an UN-activated feat conv: Blur (depthwise, weights sum to 1, reflect border) commutes with the 1x1 conv and its bias,
 // so LeakyReLU(conv(Blur(x))) == LeakyReLU(Blur(conv(x)))  (neural_renderer.py:103-106, pixel_shuffle_upsample.py:7-16, 41).
 // One thread = 4 consecutive x of one row, all channels (float4 loads/stores; edge taps come from the neighbours' cache lines).
+// rgb_coarse (optional, instead of rgb_prev): the running RGB one level down [N][3][H/2][Wd/2]; its Blur(up2(.)) is formed here.
 __global__ void __launch_bounds__(256) blur_lrelu_rgb_kernel(const float* __restrict__ pre, int C, int H, int Wd,
                                                             const float* __restrict__ rgb_w, const float* __restrict__ rgb_b,
                                                             const float* __restrict__ rgb_prev, int do_sigmoid,
-                                                            float* __restrict__ net, float* __restrict__ rgb, const GatherDst gd) {
+                                                            float* __restrict__ net, float* __restrict__ rgb, const GatherDst gd,
+                                                            const float* __restrict__ rgb_coarse = nullptr) {
   extern __shared__ float s_w[];  // [3][C]
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_w[i] = rgb_w[i];
   __syncthreads();
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(256) blur_lrelu_rgb_kernel(const float* __rest
   for (int j = 0; j < 3; ++j)
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[j][i] = 0.0f;
-#pragma unroll 2
+#pragma unroll 4
   for (int c = 0; c < C; ++c) {
     const float* pc = pl + (size_t)c * HW;
     float col[6];  // vertically blurred columns x0-1 .. x0+4 (weights 1,2,1)
@@ -234,6 +236,10 @@ __global__ void __launch_bounds__(256) blur_lrelu_rgb_kernel(const float* __rest
     if (rgb_prev != nullptr) {
       const float4 pr = *reinterpret_cast<const float4*>(rgb_prev + o);
       v[0] += pr.x; v[1] += pr.y; v[2] += pr.z; v[3] += pr.w;
+    } else if (rgb_coarse != nullptr) {
+      const float* cp = rgb_coarse + ((size_t)n * 3 + j) * (HW >> 2);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] += nrf::up2_blur_at(cp, H >> 1, Wd >> 1, y, x0 + i);
     }
     if (do_sigmoid) {
 #pragma unroll
@@ -406,7 +412,6 @@ static int nr_forward_fused(const float* const* params, const unsigned char* fpa
   float* xbuf = reinterpret_cast<float*>(ws + pl.x);
   float* pre[2] = {reinterpret_cast<float*>(ws + pl.pre[0]), reinterpret_cast<float*>(ws + pl.pre[1])};
   float* rgb[2] = {reinterpret_cast<float*>(ws + pl.rgb[0]), reinterpret_cast<float*>(ws + pl.rgb[1])};
-  float* rgb_up = reinterpret_cast<float*>(ws + pl.rgb_up);
   int s = S;
   for (int i = 0; i < n_blocks; ++i) {
     const int ci = nr_width(C, i, min_feat), co = nr_width(C, i + 1, min_feat);
@@ -439,14 +444,12 @@ static int nr_forward_fused(const float* const* params, const unsigned char* fpa
   // final: Blur(up2(R_{nb-1})) (3 channels), then img = sigmoid(. + toRGB_nb(LReLU(Blur(pre_{nb-1})))), all-gather fused when requested
   {
     const int co = nr_width(C, n_blocks, min_feat);
-    const int hs = s / 2;
-    nrf::ub_kernel<<<dim3(ceil_div(s * s, 256), N * 3), 256, 0, st>>>(rgb[(n_blocks - 1) & 1], hs, hs, rgb_up);
     dim3 grid(ceil_div(s * s / 4, 256), N);
     blur_lrelu_rgb_kernel<<<grid, 256, 3 * co * sizeof(float), st>>>(pre[(n_blocks - 1) & 1], co, s, s, params[4 * n_blocks + 2 * n_blocks],
-                                                                    params[4 * n_blocks + 2 * n_blocks + 1], rgb_up, 1, nullptr, img,
-                                                                    gather ? *gather : GatherDst{});
+                                                                    params[4 * n_blocks + 2 * n_blocks + 1], nullptr, 1, nullptr, img,
+                                                                    gather ? *gather : GatherDst{}, rgb[(n_blocks - 1) & 1]);
     GNRF_LAUNCH_CHECK();
-    count_launches(2);
+    count_launches(1);
   }
   return GNRF_OK;
 }
