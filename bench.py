@@ -249,7 +249,7 @@ def synthetic_targets(torch, faces, size, seed, device="cpu"):
     return {"gt": gt, "head": head, "left_eye": le, "right_eye": re, "full_eye": ((le + re) > 0).float()}
 
 
-def run_train(env, steps, warmup, F, with_e2e=True):
+def run_train(env, steps, warmup, F, with_e2e=True, graph=True):
     torch, G, dev, world, rank = env.torch, env.G, env.dev, env.world, env.rank
     L = G.lib()
     opt = G.BaseOptions()
@@ -265,7 +265,7 @@ def run_train(env, steps, warmup, F, with_e2e=True):
     d_tv = torch.zeros(F, 3, 1, device=dev, requires_grad=True)
     lr = 1e-4   # README.md:30 of the reference
     optim = torch.optim.Adam([{"params": list(net.parameters()), "lr": lr}, {"params": list(off.values()), "lr": lr * 1.5},
-                              {"params": [d_eul, d_tv], "lr": lr * 0.1}])
+                              {"params": [d_eul, d_tv], "lr": lr * 0.1}], capturable=bool(graph))
     params = [p for p in net.parameters()]   # shared by all ranks (averaged); code offsets / camera deltas belong to this rank's faces
     loss_fn = G.GazeNeRFLoss(eye_loss_importance=1.0, vgg_importance=1.0, use_vgg_loss=False, use_l1_loss=True)
     host_kw = synthetic_inputs(torch, G, opt, F, seed=rank)
@@ -277,10 +277,30 @@ def run_train(env, steps, warmup, F, with_e2e=True):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
-    def step(kw, tg):
+    def split(kw):
         base = {"iden": kw["shape_code"][:, :100], "expr": kw["shape_code"][:, 100:], "text": kw["appea_code"][:, :100],
                 "illu": kw["appea_code"][:, 100:], "gaze": kw["gaze_code"]}
-        cam = {k: kw[k] for k in ("batch_Rmats", "batch_Tvecs", "batch_inv_inmats")}
+        return base, {k: kw[k] for k in ("batch_Rmats", "batch_Tvecs", "batch_inv_inmats")}
+
+    gs = None
+    graph_note = "eager launches"
+    if graph:
+        # the whole step (code / camera assembly, render, loss, backward, [gradient all-reduce,] Adam, on-device jitter) as ONE CUDA graph
+        try:
+            from gazenerf_b200.trainer_utils import GraphedTrainStep
+            b0, c0 = split(dev_kw)
+            gs = GraphedTrainStep(net, loss_fn, optim, dev_kw["batch_xy"], {k: v.contiguous() for k, v in b0.items()}, off, c0, dev_tg, d_eul, d_tv,
+                                  post_backward=(lambda: allreduce_gradients(params)) if world > 1 else None)
+            graph_note = "one CUDA graph replay per step (GraphedTrainStep: %d libgnrf launches + the eager-torch glue captured)" % gs.launches_per_replay
+        except Exception as e:  # noqa: BLE001 - fall back to eager launches and say so
+            gs = None
+            graph_note = "eager launches (graph capture failed: %s)" % str(e)[:120]
+
+    def step(kw, tg):
+        if gs is not None:
+            b, c = split(kw)
+            return gs.step(b, c, tg)["total_loss"]
+        base, cam = split(kw)
         code_info, opt_code, cam_info, delta_cam = build_code_and_cam(base, off, cam, 0, F, d_eul, d_tv)
         pred = net("train", kw["batch_xy"], None, **code_info, **cam_info)
         loss = loss_fn.calc_total_loss(delta_cam, opt_code, pred, tg["gt"], tg["head"], tg["full_eye"], tg["left_eye"], tg["right_eye"],
@@ -308,6 +328,8 @@ def run_train(env, steps, warmup, F, with_e2e=True):
         ev[i][1].record()
     env.barrier()
     launches = (L.gnrf_launch_count() - launches0) // max(steps, 1)
+    if gs is not None:
+        launches = gs.launches_per_replay   # replayed kernels are not seen by the launch counter
     ms = sum(a.elapsed_time(b) for a, b in ev)
     tail = keep_load_for_sampler(env, ms / max(steps, 1), lambda: step(dev_kw, dev_tg))
     clocks = sampler.stop() if rank == 0 else None
@@ -350,6 +372,7 @@ def run_train(env, steps, warmup, F, with_e2e=True):
         "dtype": "bf16x3 split (fp32 accumulate) on tensor cores for every GEMM (forward, dX, dW); f32 elsewhere", "data": "synthetic",
         "config": {"workload": "config[4]: full train step (trainer perform_fitting): build_code_and_cam -> two-branch render + neural renderer -> GazeNeRFLoss (l1, no VGG) -> backward to weights, code offsets, camera deltas -> Adam",
                    "faces_per_gpu_per_step": F, "rays": N_RAYS, "samples_per_ray": 64, "l2": "256 MiB memset between timed steps (untimed)",
+                   "launch": graph_note,
                    "multi_gpu": "data parallel, one flat gradient all-reduce per step" if world > 1 else "single GPU",
                    "precision_note": "config[4] allows bf16; this path keeps the bf16x3 split so gradients match fp32 autograd to 5e-3"},
         "roofline": {"bound": "tensor", "kernel": "whole step (conv_tc_kernel forward/dX + wgrad_tc_kernel dW dominate)", "achieved": achieved,
@@ -598,6 +621,7 @@ def main():
     ap.add_argument("--ref-budget-s", type=int, default=300, help="--impl reference: stop issuing timed steps after this many seconds")
     ap.add_argument("--workload", default="render", choices=["render", "train", "hier", "c0"])
     ap.add_argument("--graph", action="store_true", help="single-GPU render: replay the forward from a captured CUDA graph (net.graphed)")
+    ap.add_argument("--no-train-graph", action="store_true", help="train workload: eager launches instead of the captured step (GraphedTrainStep)")
     args = ap.parse_args()
     if args.workload == "train" and args.faces_per_gpu == 1:
         args.faces_per_gpu = 2   # config[4]: batch = 2
@@ -627,7 +651,7 @@ def main():
     env = Env(torch, G, rank, local_rank, world, dev, dist)
 
     if args.workload == "train":
-        line = run_train(env, args.steps, args.warmup, args.faces_per_gpu)
+        line = run_train(env, args.steps, args.warmup, args.faces_per_gpu, graph=not args.no_train_graph)
     else:
         line = run_render(env, args, args.steps, args.warmup, args.faces_per_gpu, workload=args.workload)
         if args.workload == "render" and world == 1 and not args.no_aux and args.mlp_impl == "tc":
@@ -635,7 +659,7 @@ def main():
             aux = {}
             for name, fn in (("hier", lambda: run_render(env, args, 5, 3, 1, workload="hier", with_e2e=False)),
                              ("c0", lambda: run_render(env, args, 5, 3, 1, workload="c0", with_e2e=False)),
-                             ("train", lambda: run_train(env, 5, 3, 2, with_e2e=False))):
+                             ("train", lambda: run_train(env, 5, 3, 2, with_e2e=False, graph=not args.no_train_graph))):
                 try:
                     r = fn()
                     aux[name] = {k: r[k] for k in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "dtype", "config", "roofline",

@@ -1,7 +1,8 @@
 """Drop-in ``GazeNeRFLoss`` (losses/gazenerf_loss.py:190-470) with the data terms fused into libgnrf.
 
-Same constructor, ``calc_total_loss`` / ``calc_data_loss`` / ``calc_cam_loss`` / ``calc_code_loss`` signatures, loss-dict keys and
-weights as the reference.  The five data terms (bg, eyes, face, nonhead, head) come from ONE streaming kernel instead of boolean-mask
+Same constructor, ``calc_total_loss`` / ``calc_cam_loss`` / ``calc_code_loss`` signatures, loss-dict keys and weights as the
+reference.  ``calc_data_loss`` differs on purpose: the reference's (losses/gazenerf_loss.py:294-308) takes the four BOOLEAN masks that
+``calc_total_loss`` derives (:420-424); here it takes the raw float mask tensors and the boolean algebra happens inside the kernel.  The five data terms (bg, eyes, face, nonhead, head) come from ONE streaming kernel instead of boolean-mask
 gathers (each ``res_img[mask]`` in the reference synchronises with the host to size its output), and their image gradients from one
 more (csrc/loss.cu).  The perceptual (VGG16), gaze-angular and patch-GAN terms need networks whose pretrained weights the reference
 downloads at run time (losses/gazenerf_loss.py:49-52); they are out of this path's scope: asking for them raises unless the caller
@@ -91,7 +92,7 @@ class GazeNeRFLoss(object):
         expr_loss = torch.mean(opt_code_dict["expr"] * opt_code_dict["expr"])
         appea_loss = torch.mean(opt_code_dict["appea"] * opt_code_dict["appea"])
         bg_code = opt_code_dict["bg"]
-        bg_loss = torch.as_tensor(0.0, dtype=iden_loss.dtype, device=iden_loss.device) if bg_code is None else torch.mean(bg_code * bg_code)
+        bg_loss = torch.zeros((), dtype=iden_loss.dtype, device=iden_loss.device) if bg_code is None else torch.mean(bg_code * bg_code)
         return {"iden_code": iden_loss, "expr_code": expr_loss, "appea_code": appea_loss, "bg_code": bg_loss}
 
     def calc_data_loss(self, data_dict, gt_rgb, face_mask_tensor, full_eye_mask_tensor, left_eye_mask_tensor, right_eye_mask_tensor,

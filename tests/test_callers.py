@@ -118,3 +118,106 @@ def test_fused_data_loss_matches_reference(use_l1):
         assert rel_l2(v.grad.cpu(), gold["%s/g_%s" % (tag, k)]) < 1e-5, k
     with pytest.raises(NotImplementedError):
         G.GazeNeRFLoss(1.0, 1.0)   # the reference default (VGG perceptual term) needs downloaded weights
+
+
+@pytest.mark.gpu
+def test_graphed_train_step_matches_eager_steps():
+    """build_code_and_cam -> net("train") -> GazeNeRFLoss -> backward -> Adam captured into ONE CUDA graph.
+    With the same (fed) jitter, N replays must leave the network, code offsets and camera deltas where N eager steps leave them, and
+    the graph must contain the libgnrf launches (weight packing included: the weights change on every replay)."""
+    import copy
+    from gazenerf_b200.trainer_utils import GraphedTrainStep
+    from bench import synthetic_inputs, synthetic_targets
+    dev = torch.device("cuda:0")
+    opt = G.BaseOptions({"featmap_size": 16, "featmap_nc": 258, "pred_img_size": 64})
+    opt.num_sample_coarse = 16
+    F = 2
+
+    def make():
+        torch.manual_seed(45)
+        net = G.GazeNeRFNet(opt, include_vd=False, hier_sampling=False).to(dev).train()
+        with torch.no_grad():
+            for m in (net.fg_CD_predictor_face, net.fg_CD_predictor_eyes):
+                m.density_module.weight.mul_(30.0)
+        off = {"iden": torch.zeros(F, 100, device=dev, requires_grad=True), "expr": torch.zeros(F, 79, device=dev, requires_grad=True),
+               "appea": torch.zeros(F, 127, device=dev, requires_grad=True)}
+        d_eul = torch.zeros(F, 3, device=dev, requires_grad=True)
+        d_tv = torch.zeros(F, 3, 1, device=dev, requires_grad=True)
+        optim = torch.optim.Adam([{"params": list(net.parameters()), "lr": 1e-3}, {"params": list(off.values()), "lr": 1.5e-3},
+                                  {"params": [d_eul, d_tv], "lr": 1e-4}], capturable=True)
+        return net, off, d_eul, d_tv, optim
+
+    kw = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in synthetic_inputs(torch, G, opt, F, seed=0).items()}
+    tg = {k: v.to(dev) for k, v in synthetic_targets(torch, F, opt.pred_img_size, seed=0).items()}
+    base = {"iden": kw["shape_code"][:, :100].contiguous(), "expr": kw["shape_code"][:, 100:].contiguous(), "text": kw["appea_code"][:, :100].contiguous(),
+            "illu": kw["appea_code"][:, 100:].contiguous(), "gaze": kw["gaze_code"]}
+    cam = {k: kw[k] for k in ("batch_Rmats", "batch_Tvecs", "batch_inv_inmats")}
+    loss_fn = G.GazeNeRFLoss(eye_loss_importance=1.0, vgg_importance=1.0, use_vgg_loss=False, use_l1_loss=True)
+    ju = [torch.rand(F, 256, 17, device=dev, generator=torch.Generator(device=dev).manual_seed(i)) for i in range(3)]
+    n_steps = 3
+
+    # eager reference run
+    net_e, off_e, de_e, dt_e, optim_e = make()
+    for i in range(n_steps):
+        code_info, opt_code, cam_info, delta_cam = build_code_and_cam(base, off_e, cam, 0, F, de_e, dt_e)
+        pred = net_e("train", kw["batch_xy"], None, **code_info, **cam_info, jitter_u=ju[i])
+        loss = loss_fn.calc_total_loss(delta_cam, opt_code, pred, tg["gt"], tg["head"], tg["full_eye"], tg["left_eye"], tg["right_eye"], None, None, 0, 0)
+        optim_e.zero_grad(set_to_none=True)
+        loss["total_loss"].backward()
+        optim_e.step()
+    loss_e = float(loss["total_loss"])
+
+    # graphed run: warm-up steps are taken on COPIES so that the captured run starts from the same state as the eager one
+    net_g, off_g, de_g, dt_g, optim_g = make()
+    snap = (copy.deepcopy(net_g.state_dict()), {k: v.detach().clone() for k, v in off_g.items()}, de_g.detach().clone(), dt_g.detach().clone(),
+            copy.deepcopy(optim_g.state_dict()))
+    gs = GraphedTrainStep(net_g, loss_fn, optim_g, kw["batch_xy"], base, off_g, cam, tg, de_g, dt_g, jitter_u=ju[0])
+    assert gs.launches_per_replay > 100
+    with torch.no_grad():   # rewind to the initial state (in place: the graph holds these tensors)
+        for k, v in net_g.state_dict().items():
+            v.copy_(snap[0][k])
+        for k in off_g:
+            off_g[k].copy_(snap[1][k])
+        de_g.copy_(snap[2]); dt_g.copy_(snap[3])
+        for st in optim_g.state.values():
+            for k, v in st.items():
+                if torch.is_tensor(v):
+                    v.zero_()
+    net_g.invalidate_caches()
+    for i in range(n_steps):
+        out = gs.step(jitter_u=ju[i])
+    torch.cuda.synchronize()
+    assert abs(float(out["total_loss"]) - loss_e) < 1e-4 * max(1.0, abs(loss_e))
+    worst = max(float((a - b).abs().max()) for a, b in zip(net_g.state_dict().values(), net_e.state_dict().values()))
+    assert worst < 1e-5, worst
+    for a, b in ((off_g["iden"], off_e["iden"]), (off_g["appea"], off_e["appea"]), (de_g, de_e), (dt_g, dt_e)):
+        assert float((a - b).abs().max()) < 1e-5
+    assert float((net_g.fg_CD_predictor_face.FeaExt_module_3.weight - snap[0]["fg_CD_predictor_face.FeaExt_module_3.weight"]).abs().max()) > 1e-4   # it trained
+
+
+@pytest.mark.gpu
+def test_graphed_train_step_draws_jitter_on_device():
+    """Without a fed jitter tensor the stratified draws come from the graph-safe device generator: two replays see different samples."""
+    from gazenerf_b200.trainer_utils import GraphedTrainStep
+    from bench import synthetic_inputs, synthetic_targets
+    dev = torch.device("cuda:0")
+    opt = G.BaseOptions({"featmap_size": 16, "featmap_nc": 258, "pred_img_size": 64})
+    opt.num_sample_coarse = 16
+    torch.manual_seed(45)
+    net = G.GazeNeRFNet(opt, include_vd=False, hier_sampling=False).to(dev).train()
+    with torch.no_grad():
+        for m in (net.fg_CD_predictor_face, net.fg_CD_predictor_eyes):
+            m.density_module.weight.mul_(30.0)
+    off = {"iden": torch.zeros(1, 100, device=dev, requires_grad=True), "expr": torch.zeros(1, 79, device=dev, requires_grad=True),
+           "appea": torch.zeros(1, 127, device=dev, requires_grad=True)}
+    optim = torch.optim.Adam(list(net.parameters()) + list(off.values()), lr=0.0, capturable=True)   # lr = 0: only the jitter differs
+    kw = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in synthetic_inputs(torch, G, opt, 1, seed=0).items()}
+    tg = {k: v.to(dev) for k, v in synthetic_targets(torch, 1, opt.pred_img_size, seed=0).items()}
+    base = {"iden": kw["shape_code"][:, :100].contiguous(), "expr": kw["shape_code"][:, 100:].contiguous(), "text": kw["appea_code"][:, :100].contiguous(),
+            "illu": kw["appea_code"][:, 100:].contiguous(), "gaze": kw["gaze_code"]}
+    cam = {k: kw[k] for k in ("batch_Rmats", "batch_Tvecs", "batch_inv_inmats")}
+    loss_fn = G.GazeNeRFLoss(eye_loss_importance=1.0, vgg_importance=1.0, use_vgg_loss=False, use_l1_loss=True)
+    gs = GraphedTrainStep(net, loss_fn, optim, kw["batch_xy"], base, off, cam, tg)
+    a = float(gs.step()["total_loss"])
+    b = float(gs.step()["total_loss"])
+    assert a != b and abs(a - b) < 0.1 * abs(a)
