@@ -418,13 +418,16 @@ def run_render(env, args, steps, warmup, F, workload="render", with_e2e=True):
                 gather_check = "not run (symmetric memory unavailable)"
                 gather_mode += " (symmetric memory unavailable: %s)" % str(e)[:80]
 
-    graphed = None   # single GPU: the whole forward captured once into a CUDA graph (net.graphed), replayed per step
+    graphed = None   # the whole forward (incl. the fused gather at N > 1) captured once into a CUDA graph (net.graphed), replayed per step
 
     def step(kw, pre_finish=None):
         if peer is not None:   # `peer` is re-bound to None if the self-check below fails
-            net.gather_ctx = peer
-            local = net("test", **kw)["coarse_dict"]
-            net.gather_ctx = None
+            if graphed is not None:
+                local = graphed(**kw)["coarse_dict"]      # replays the graph of the symmetric buffer this step writes
+            else:
+                net.gather_ctx = peer
+                local = net("test", **kw)["coarse_dict"]
+                net.gather_ctx = None
             if pre_finish is not None:
                 pre_finish()
             out = peer.finish(alias=True)
@@ -455,9 +458,16 @@ def run_render(env, args, steps, warmup, F, workload="render", with_e2e=True):
                 peer = None
                 gather_mode = "batch-sharded, one NCCL all-gather of the rendered images per step (fused-gather self-check FAILED, not used)"
             env.barrier()
-        use_graph = world == 1 and args.graph and not hier
+        use_graph = (not args.no_graph) and not hier and (world == 1 or peer is not None)
+        graph_note = "eager launches"
         if use_graph:
-            graphed = net.graphed("test", **dev_kw)
+            try:
+                graphed = net.graphed("test", gather=peer, **dev_kw)
+                graph_note = "one CUDA graph replay per step (net.graphed%s)" % (": one graph per rotating symmetric buffer, fused gather inside" if peer is not None else "")
+            except Exception as e:  # noqa: BLE001 - every rank fails alike (same code path); fall back to eager launches and say so
+                graphed, use_graph = None, False
+                net.gather_ctx = None
+                graph_note = "eager launches (graph capture failed: %s)" % str(e)[:100]
             for _ in range(2):
                 step(dev_kw)
             env.barrier()
@@ -482,9 +492,11 @@ def run_render(env, args, steps, warmup, F, workload="render", with_e2e=True):
             # the capture and time the fused MLP kernel in a few eager steps right after the timed region
             launches = graphed.launches_per_replay
             net.mlp_events = []
+            g_keep, graphed = graphed, None        # a few EAGER steps (same collectives on every rank) to time the fused MLP launch
             for _ in range(5):
                 flush.zero_()
-                net("test", **dev_kw)
+                step(dev_kw)
+            graphed = g_keep
             torch.cuda.synchronize()
         mlp_ms = [a.elapsed_time(b) for a, b in net.mlp_events]
         net.mlp_events = None
@@ -516,15 +528,16 @@ def run_render(env, args, steps, warmup, F, workload="render", with_e2e=True):
             d2h = sum(v.numel() * v.element_size() for v in host_out[0].values())   # this rank's share (rank 0: + bg_img)
             copy_stream = torch.cuda.Stream(device=dev)
             main_stream = torch.cuda.current_stream()
-            copied = [None]   # event: the previous step's D2H has drained its (symmetric) source buffer
+            copied = [None, None]   # events of the last two steps' D2H copies (they read the aliased symmetric buffers)
             dev_stage, stage_free = [None, None], [None, None]
 
             def e2e_step(i):
                 kw = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in pinned.items()}
-                # fused gather: peers rewrite the buffer of step i-1 once they pass the barrier of step i+1 -> my D2H of step i-1 must be
-                # complete before I enter this step's barrier
+                # fused gather, three rotating buffers: peers rewrite the buffer of step i-2 once they pass the barrier of step i+1, and
+                # they cannot pass it before I enter it -> my D2H of step i-2 must be complete before I enter the barrier of step i
+                # (two whole steps of slack: this wait never blocks in practice)
                 out = step(kw, pre_finish=(lambda: main_stream.wait_event(copied[0])) if (peer is not None and copied[0] is not None) else None)
-                if graphed is not None:
+                if graphed is not None and peer is None:
                     # the graph's static outputs are overwritten by the next replay: stage them (D2D, 12.6 MB) into one of two device
                     # buffers whose previous D2H has completed
                     if dev_stage[i & 1] is None:
@@ -544,7 +557,7 @@ def run_render(env, args, steps, warmup, F, workload="render", with_e2e=True):
                         v.record_stream(copy_stream)
                     ev_c = torch.cuda.Event()
                     ev_c.record(copy_stream)
-                copied[0] = ev_c
+                copied[0], copied[1] = copied[1], ev_c
                 stage_free[i & 1] = ev_c
 
             for i in range(2):
@@ -588,7 +601,7 @@ def run_render(env, args, steps, warmup, F, workload="render", with_e2e=True):
         "config": {"workload": wl, "faces_per_gpu_per_step": F, "rays": N_RAYS, "samples_per_ray": n_s, "mlp_impl": args.mlp_impl,
                    "weights": "reference init, torch.manual_seed(45)", "l2": "256 MiB memset between timed steps (untimed)",
                    "bg_img": "cached per weight version (parameter-only input, models/gaze_nerf.py:175-176): the timed step renders 3 of the 4 images",
-                   "launch": "one CUDA graph replay per step (net.graphed)" if use_graph else "eager launches",
+                   "launch": graph_note,
                    "multi_gpu": gather_mode},
         "roofline": {"bound": "tensor", "kernel": ("whole step: coarse + fine mlp_tc_kernel launches, fine_depths, 2x neural renderer" if hier else "mlp_tc_kernel (+fold, rgb_head)") if args.mlp_impl == "tc" else "mlp_simt_kernel+composite",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
@@ -620,7 +633,8 @@ def main():
     ap.add_argument("--no-aux", action="store_true", help="skip the short hier / train runs attached to the default N=1 line")
     ap.add_argument("--ref-budget-s", type=int, default=300, help="--impl reference: stop issuing timed steps after this many seconds")
     ap.add_argument("--workload", default="render", choices=["render", "train", "hier", "c0"])
-    ap.add_argument("--graph", action="store_true", help="single-GPU render: replay the forward from a captured CUDA graph (net.graphed)")
+    ap.add_argument("--no-graph", action="store_true", help="render workloads: eager launches instead of replaying the forward (incl. the fused "
+                    "all-gather at N > 1) from a captured CUDA graph (net.graphed)")
     ap.add_argument("--no-train-graph", action="store_true", help="train workload: eager launches instead of the captured step (GraphedTrainStep)")
     args = ap.parse_args()
     if args.workload == "train" and args.faces_per_gpu == 1:

@@ -78,12 +78,13 @@ class PeerAllGather(object):
     every process; an NVSwitch multicast address covers all of them).  The last neural-render kernel stores each RGB value once to
     the multicast address (``multimem.st``, NVLS) -- or once per peer over NVLink when multicast is unavailable -- so the whole batch
     materialises on every GPU without a separate collective.  ``finish()`` runs one device-side barrier (signal pads) on the current
-    stream and returns views of the gathered images.  Two buffers alternate per step: a rank can only be one barrier ahead of its
-    slowest peer, so a peer's reads of step i (stream-ordered before its step i+1) are complete before anyone rewrites that buffer
-    in step i+2.
+    stream and returns the gathered images.  ``n_buf`` buffers rotate per step: a rank can only be one barrier ahead of its slowest
+    peer, so a peer's reads of step i (stream-ordered before its step i+1) are complete before anyone rewrites that buffer in step
+    i + n_buf; with the default of three, a caller that reads the aliased buffer on ANOTHER stream (bench.py's D2H copy stream) has two
+    whole steps to finish before it must fence.
     """
 
-    def __init__(self, b_local: int, img_size: int, device, group=None):
+    def __init__(self, b_local: int, img_size: int, device, group=None, n_buf: int = 3):
         import torch.distributed._symmetric_memory as symm
 
         group = group if group is not None else dist.group.WORLD
@@ -92,14 +93,18 @@ class PeerAllGather(object):
             raise RuntimeError("PeerAllGather supports 2..8 ranks of one NVLink / NVSwitch domain")
         self.b_local, self.gb, self.P = b_local, b_local * self.world, img_size
         shape = (3, self.gb, 3, img_size, img_size)
-        self.bufs = [symm.empty(shape, dtype=torch.float32, device=device) for _ in range(2)]
+        self.n_buf = max(2, int(n_buf))
+        self.bufs = [symm.empty(shape, dtype=torch.float32, device=device) for _ in range(self.n_buf)]
         self.hdls = [symm.rendezvous(b, group) for b in self.bufs]
         self.use_multicast = all(int(h.multicast_ptr) != 0 for h in self.hdls)
         self.step = 0
+        self._forced: Optional[int] = None   # set while a CUDA graph is captured for one particular buffer
 
-    def current(self):
-        """(peer pointers, multicast pointer or 0) of the buffer the CURRENT step writes."""
-        h = self.hdls[self.step & 1]
+    def current(self, index: Optional[int] = None):
+        """(peer pointers, multicast pointer or 0) of the buffer the CURRENT step writes (``index``: of that buffer; graph capture)."""
+        if index is None:
+            index = self._forced if self._forced is not None else self.step % self.n_buf
+        h = self.hdls[index]
         return [int(p) for p in h.buffer_ptrs], (int(h.multicast_ptr) if self.use_multicast else 0)
 
     def finish(self, alias: bool = False) -> Dict[str, torch.Tensor]:
@@ -108,7 +113,7 @@ class PeerAllGather(object):
         ``alias=False`` (default) returns fresh tensors (one D2D copy), like the NCCL path.  ``alias=True`` returns zero-copy VIEWS of
         the symmetric buffer: peers overwrite it remotely two steps later, so the caller must have finished reading it -- on this
         stream, or behind an event it waits on before entering the next-but-one step -- by then (bench.py does this for its D2H)."""
-        i = self.step & 1
+        i = self.step % self.n_buf
         with torch.cuda.device(self.bufs[i].device):
             self.hdls[i].barrier(channel=0)
         self.step += 1

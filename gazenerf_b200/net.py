@@ -190,17 +190,23 @@ def neural_render(nr: NeuralRendererParams, x: torch.Tensor, gather=None) -> tor
 
 
 class GraphedForward(object):
-    """``net("test", ...)`` for fixed shapes captured ONCE into a CUDA graph and replayed (inference serving: the ~23 kernel launches,
-    ctypes calls and tensor allocations of a forward cost ~0.15 ms of host time per call, more than the small kernels at the head of
-    the step take on the GPU).  Inputs are copied into static device buffers, the returned dict holds static output tensors that the
-    next call overwrites.  The packed weight buffers are baked into the graph: re-capture after changing parameters."""
+    """``net("test", ...)`` for fixed shapes captured ONCE into a CUDA graph and replayed (inference serving: the kernel launches,
+    ctypes calls and tensor allocations of a forward cost more host time than the small kernels at the head of the step take on the
+    GPU).  Inputs are copied into static device buffers, the returned dict holds static output tensors that the next call overwrites.
+    The packed weight buffers are baked into the graph: re-capture after changing parameters.
 
-    def __init__(self, net: "GazeNeRFNet", mode: str, kwargs: Dict[str, Optional[torch.Tensor]]):
+    With ``gather`` (a dist.PeerAllGather) the fused all-gather is part of the capture: one graph per rotating symmetric buffer (its
+    peer / multicast addresses are launch parameters), and a call replays the graph of the buffer the current step writes; the caller
+    then runs ``gather.finish()`` as usual."""
+
+    def __init__(self, net: "GazeNeRFNet", mode: str, kwargs: Dict[str, Optional[torch.Tensor]], gather=None):
         if mode != "test":
             raise ValueError("only the deterministic 'test' forward is captured (train mode draws fresh jitter every call)")
-        if net.gather_ctx is not None or net.keep_stages:
-            raise RuntimeError("graph capture supports the plain single-GPU forward (no fused gather, no stage dumps)")
-        self.net, self.mode = net, mode
+        if net.keep_stages or (gather is None and net.gather_ctx is not None):
+            raise RuntimeError("graph capture: no stage dumps; pass the PeerAllGather as `gather=` instead of setting net.gather_ctx")
+        if gather is not None and (net.hier_sampling or kwargs.get("only_merge")):
+            raise RuntimeError("the fused gather lives in the coarse, all-three-images neural-render call")
+        self.net, self.mode, self.gather = net, mode, gather
         self.static_in = {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in kwargs.items()}
         L = _lib.lib()
         side = torch.cuda.Stream()
@@ -210,11 +216,25 @@ class GraphedForward(object):
                 net(mode, **self.static_in)
         torch.cuda.current_stream().wait_stream(side)
         self._versions = tuple((p.data_ptr(), p._version) for p in net.parameters())
-        self.graph = torch.cuda.CUDAGraph()
-        n0 = L.gnrf_launch_count()
-        with torch.no_grad(), torch.cuda.graph(self.graph):
-            self.static_out = net(mode, **self.static_in)
-        self.launches_per_replay = int(L.gnrf_launch_count() - n0)
+        self.graphs, self.static_outs = [], []
+        n_graphs = gather.n_buf if gather is not None else 1
+        for b in range(n_graphs):
+            g = torch.cuda.CUDAGraph()
+            n0 = L.gnrf_launch_count()
+            if gather is not None:
+                gather._forced = b
+                net.gather_ctx = gather
+            try:
+                with torch.no_grad(), torch.cuda.graph(g):
+                    out = net(mode, **self.static_in)
+            finally:
+                if gather is not None:
+                    gather._forced = None
+                    net.gather_ctx = None
+            self.launches_per_replay = int(L.gnrf_launch_count() - n0)
+            self.graphs.append(g)
+            self.static_outs.append(out)
+        self.graph, self.static_out = self.graphs[0], self.static_outs[0]
 
     def __call__(self, **kwargs) -> Dict[str, Dict[str, torch.Tensor]]:
         if tuple((p.data_ptr(), p._version) for p in self.net.parameters()) != self._versions:
@@ -222,8 +242,9 @@ class GraphedForward(object):
         for k, v in kwargs.items():
             if torch.is_tensor(v):
                 self.static_in[k].copy_(v, non_blocking=True)
-        self.graph.replay()
-        return self.static_out
+        b = (self.gather.step % self.gather.n_buf) if self.gather is not None else 0
+        self.graphs[b].replay()
+        return self.static_outs[b]
 
 
 class GazeNeRFNet(nn.Module):
@@ -461,11 +482,12 @@ class GazeNeRFNet(nn.Module):
         return res_dict
 
     def graphed(self, mode, batch_xy, batch_uv, bg_code, shape_code, appea_code, gaze_code, batch_Rmats, batch_Tvecs, batch_inv_inmats,
-                **kwargs) -> GraphedForward:
-        """Capture ``forward(mode, ...)`` for these shapes into a CUDA graph; the result is called with the same keyword tensors."""
+                gather=None, **kwargs) -> GraphedForward:
+        """Capture ``forward(mode, ...)`` for these shapes into a CUDA graph; the result is called with the same keyword tensors.
+        ``gather``: a dist.PeerAllGather whose fused all-gather becomes part of the captured forward (one graph per symmetric buffer)."""
         kw = dict(batch_xy=batch_xy, batch_uv=batch_uv, bg_code=bg_code, shape_code=shape_code, appea_code=appea_code, gaze_code=gaze_code,
                   batch_Rmats=batch_Rmats, batch_Tvecs=batch_Tvecs, batch_inv_inmats=batch_inv_inmats, **kwargs)
-        return GraphedForward(self, mode, kw)
+        return GraphedForward(self, mode, kw, gather=gather)
 
     def _wants_grad(self, train_mode: bool, *inputs) -> bool:
         """"train" with trainable parameters, or any mode with an input that requires grad (codes / gaze / camera)."""
