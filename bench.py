@@ -603,7 +603,7 @@ def run_render(env, args, steps, warmup, F, workload="render", with_e2e=True):
                    "bg_img": "cached per weight version (parameter-only input, models/gaze_nerf.py:175-176): the timed step renders 3 of the 4 images",
                    "launch": graph_note,
                    "multi_gpu": gather_mode},
-        "roofline": {"bound": "tensor", "kernel": ("whole step: coarse + fine mlp_tc_kernel launches, fine_depths, 2x neural renderer" if hier else "mlp_tc_kernel (+fold, rgb_head)") if args.mlp_impl == "tc" else "mlp_simt_kernel+composite",
+        "roofline": {"bound": "tensor", "kernel": ("whole step: coarse + fine mlp_tc_kernel launches, fine_depths, 2x neural renderer" if hier else "mlp_tc_kernel (+rgb_head_kernel, launched back to back by the same C call)") if args.mlp_impl == "tc" else "mlp_simt_kernel+composite",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "peak_source": "%s bf16 dense, burst (cuBLAS best-of-10; the timed region is K x %.1f ms)" % (peaks["src"], total_ms / steps),
                      "frac_vs_sustained_peak": achieved / peaks["bf16_sustained"], "sustained_peak": peaks["bf16_sustained"],

@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(kAThreads, 1) nrf_a_kernel(const AArgs args) {
   const uint32_t bars = sm_b + kABStages * kABStageBytes;
   auto bar = [&](int i) { return bars + (uint32_t)i * 8u; };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + (bars - smem_base) + kANumBars * 8);
-  float* s_bias1 = reinterpret_cast<float*>(smem_gen + (bars - smem_base) + kANumBars * 8 + 16);   // [n1p]: no global latency in the epilogue
+  float* s_bias1 = reinterpret_cast<float*>(smem_gen + (bars - smem_base) + ((kANumBars * 8 + 16 + 15) & ~15));   // [n1p]: no global latency in the epilogue
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int HW = args.H * args.W;
   const int tiles_per_img = HW / kTile;
@@ -398,14 +398,21 @@ __global__ void __launch_bounds__(kAThreads, 1) nrf_a_kernel(const AArgs args) {
     }
   } else if (warp < 12) {
     // ======================================= loaders: x tile (optionally LReLU(Blur(src))) -> bf16 hi/lo A operand ==========
-    // thread = (pixel row, K half): 8 of the 16 channels of every K16 step = one 16-byte chunk of the hi and of the lo operand.
+    // A sub-step = 8 of the 16 channels of a K16 step = one 16-byte chunk of the hi and of the lo operand of this thread's pixel row;
+    // the two loader groups (4 warps each) share every tile, one K half each.  (Measured alternative, kept switchable: the groups
+    // working on ALTERNATE tiles with both K halves per thread -- same bytes in flight per SM, 6 % slower.)
     const int row = ((warp - 4) & 3) * 32 + lane;
-    const int kh = (warp - 4) >> 2;
+    const int grp = (warp - 4) >> 2;
+    const bool split_tiles = false;
+    const int n_sub = split_tiles ? 2 * g.k1_steps : g.k1_steps;
+    auto sub_k = [&](int s_) { return split_tiles ? (s_ >> 1) : s_; };
+    auto sub_kh = [&](int s_) { return split_tiles ? (s_ & 1) : grp; };
     // whole-row tiles (W a multiple of 128): a warp holds 32 consecutive x of one image row, so the horizontal taps of the separable
     // blur come from the neighbouring lanes (3 coalesced loads per channel instead of 9); lanes 0 / 31 fetch their outer column
     const bool fast = args.blur && (args.W % kTile == 0);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      if (split_tiles && (int)(it & 1) != grp) continue;
       const int buf = (n_abuf == 2) ? (int)(it & 1) : 0;
       const uint32_t use = (n_abuf == 2) ? (it >> 1) : it;
       const int img = tile / tiles_per_img;
@@ -418,10 +425,11 @@ __global__ void __launch_bounds__(kAThreads, 1) nrf_a_kernel(const AArgs args) {
       float* xo = args.x_out ? args.x_out + (size_t)img * args.ci * HW + p : nullptr;
       const size_t o0 = (size_t)ym * args.W, o1 = (size_t)y * args.W, o2 = (size_t)yp * args.W;
       mbar_wait(bar(kABarAEmpty + buf), (use & 1) ^ 1);
-      const uint32_t a_row = sm_a + (uint32_t)(buf * a_bytes) + (uint32_t)((row >> 3) * 256 + (row & 7) * 16 + kh * 128);
+      const uint32_t a_row = sm_a + (uint32_t)(buf * a_bytes) + (uint32_t)((row >> 3) * 256 + (row & 7) * 16);
       // kLB K16 steps per memory round trip (their loads are all issued before the first value is consumed)
       constexpr int kLB = 2;
-      auto emit = [&](int k, const float (&vv)[8]) {   // one K16 step of this thread's 8 channels -> x_out, hi / lo chunks of the A operand
+      auto emit = [&](int sub, const float (&vv)[8]) {   // one sub-step (8 channels) -> x_out, hi / lo chunks of the A operand
+        const int k = sub_k(sub), kh = sub_kh(sub);
         if (xo != nullptr) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -430,29 +438,29 @@ __global__ void __launch_bounds__(kAThreads, 1) nrf_a_kernel(const AArgs args) {
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) split2(vv[2 * j], vv[2 * j + 1], hi[j], lo[j]);
-        const uint32_t d = a_row + (uint32_t)(k * kStepBytes);
+        const uint32_t d = a_row + (uint32_t)(k * kStepBytes + kh * 128);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + 4096), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
       };
       if (!args.blur) {
         // level 0 (one tile per CTA, nothing to overlap with): 6 K16 steps = 48 loads per thread per round trip
         constexpr int kL0 = 6;
-        for (int k0 = 0; k0 < g.k1_steps; k0 += kL0) {
+        for (int k0 = 0; k0 < n_sub; k0 += kL0) {
           float v[kL0][8];
 #pragma unroll
           for (int b = 0; b < kL0; ++b)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const int c = (k0 + b) * 16 + kh * 8 + j;
+              const int c = sub_k(k0 + b) * 16 + sub_kh(k0 + b) * 8 + j;
               const float t = __ldg(sp + (size_t)min(c, args.ci - 1) * HW + p);   // unconditional load (clamped address): no branch, so
               v[b][j] = (c < args.ci) ? t : 0.0f;                                  // all loads of the batch are in flight together
             }
 #pragma unroll
           for (int b = 0; b < kL0; ++b)
-            if (k0 + b < g.k1_steps) emit(k0 + b, v[b]);
+            if (k0 + b < n_sub) emit(k0 + b, v[b]);
         }
       }
-      for (int k0 = 0; args.blur && k0 < g.k1_steps; k0 += kLB) {
+      for (int k0 = 0; args.blur && k0 < n_sub; k0 += kLB) {
         float v[kLB][8];
         if (fast) {
           float m[kLB][8], e[kLB][8];
@@ -460,7 +468,7 @@ __global__ void __launch_bounds__(kAThreads, 1) nrf_a_kernel(const AArgs args) {
           for (int b = 0; b < kLB; ++b)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const int c = (k0 + b) * 16 + kh * 8 + j;
+              const int c = sub_k(k0 + b) * 16 + sub_kh(k0 + b) * 8 + j;
               const float* pc = sp + (size_t)min(c, args.ci - 1) * HW;     // clamped: every load is unconditional (no branches)
               const bool ok = c < args.ci;
               const float t0 = __ldg(pc + o0 + x), t1v = __ldg(pc + o1 + x), t2v = __ldg(pc + o2 + x);
@@ -482,7 +490,7 @@ __global__ void __launch_bounds__(kAThreads, 1) nrf_a_kernel(const AArgs args) {
           for (int b = 0; b < kLB; ++b)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const int c = (k0 + b) * 16 + kh * 8 + j;
+              const int c = sub_k(k0 + b) * 16 + sub_kh(k0 + b) * 8 + j;
               const float* pc = sp + (size_t)min(c, args.ci - 1) * HW;
               const float a = __ldg(pc + o0 + xm) + 2.0f * __ldg(pc + o0 + x) + __ldg(pc + o0 + xp);
               const float bb = __ldg(pc + o1 + xm) + 2.0f * __ldg(pc + o1 + x) + __ldg(pc + o1 + xp);
@@ -492,7 +500,7 @@ __global__ void __launch_bounds__(kAThreads, 1) nrf_a_kernel(const AArgs args) {
         }
 #pragma unroll
         for (int b = 0; b < kLB; ++b)
-          if (k0 + b < g.k1_steps) emit(k0 + b, v[b]);
+          if (k0 + b < n_sub) emit(k0 + b, v[b]);
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -519,25 +527,27 @@ __global__ void __launch_bounds__(kAThreads, 1) nrf_a_kernel(const AArgs args) {
     __syncwarp();
   } else if (warp == 13) {
     // ======================================= MMA issuer ==========================================================================
+    // ONE elected lane runs the whole issue loop (waits included): a per-step elect + __syncwarp + whole-warp mbarrier wait costs more
+    // than the 3 UMMAs of a K16 step take, and the tensor pipe only runs at rate when the UMMAs are issued back to back.
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    uint32_t sb = 0, pb = 0, cc = 0, it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int buf = (n_abuf == 2) ? (int)(it & 1) : 0;
-      const uint32_t use = (n_abuf == 2) ? (it >> 1) : it;
-      mbar_wait(bar(kABarAFull + buf), use & 1);
-      tc_fence_after_sync();
-      const uint32_t a0 = (((sm_a + (uint32_t)(buf * a_bytes)) >> 4) & 0x3FFFu) | kDescLoLboNo;
-      for (int ch = 0; ch < g.n_chunks; ++ch, ++cc) {
-        const int ab = cc & 1;
-        mbar_wait(bar(kABarAccEmpty + ab), ((cc >> 1) & 1) ^ 1);
+    if (elect_one()) {
+      uint32_t sb = 0, pb = 0, cc = 0, it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = (n_abuf == 2) ? (int)(it & 1) : 0;
+        const uint32_t use = (n_abuf == 2) ? (it >> 1) : it;
+        mbar_wait_spin(bar(kABarAFull + buf), use & 1);
         tc_fence_after_sync();
-        const uint32_t d = tmem_u + (uint32_t)(ab * 256);
-        const uint32_t idesc = umma_idesc_bf16(128, g.chunk_n[ch]);
-        const uint32_t slice_u = (uint32_t)((g.chunk_n[ch] * 32) >> 4);
-        for (int k = 0; k < g.k1_steps; ++k) {
-          mbar_wait(bar(kABarBFull + sb), pb);
+        const uint32_t a0 = (((sm_a + (uint32_t)(buf * a_bytes)) >> 4) & 0x3FFFu) | kDescLoLboNo;
+        for (int ch = 0; ch < g.n_chunks; ++ch, ++cc) {
+          const int ab = cc & 1;
+          mbar_wait_spin(bar(kABarAccEmpty + ab), ((cc >> 1) & 1) ^ 1);
           tc_fence_after_sync();
-          if (elect_one()) {
+          const uint32_t d = tmem_u + (uint32_t)(ab * 256);
+          const uint32_t idesc = umma_idesc_bf16(128, g.chunk_n[ch]);
+          const uint32_t slice_u = (uint32_t)((g.chunk_n[ch] * 32) >> 4);
+          for (int k = 0; k < g.k1_steps; ++k) {
+            mbar_wait_spin(bar(kABarBFull + sb), pb);
+            tc_fence_after_sync();
             const uint32_t b0 = (((sm_b + sb * kABStageBytes) >> 4) & 0x3FFFu) | kDescLoLboNo;
             const uint64_t a_hi = mk_desc(a0 + (uint32_t)((k * kStepBytes) >> 4), kDescHiNoSw);
             const uint64_t a_lo = mk_desc(a0 + (uint32_t)((k * kStepBytes + 4096) >> 4), kDescHiNoSw);
@@ -546,17 +556,14 @@ __global__ void __launch_bounds__(kAThreads, 1) nrf_a_kernel(const AArgs args) {
             umma_ss(d, a_lo, b_hi, idesc, 1u);
             umma_ss(d, a_hi, b_lo, idesc, 1u);
             umma_commit(bar(kABarBEmpty + sb));
+            if (++sb == kABStages) { sb = 0; pb ^= 1; }
           }
-          __syncwarp();
-          if (++sb == kABStages) { sb = 0; pb ^= 1; }
-        }
-        if (elect_one()) {
           umma_commit(bar(kABarAccFull + ab));
           if (ch == g.n_chunks - 1) umma_commit(bar(kABarAEmpty + buf));
         }
-        __syncwarp();
       }
     }
+    __syncwarp();
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -583,11 +590,12 @@ struct BArgs {
 
 constexpr int kBASteps = 2;                                   // K16 steps of t1 per A-ring stage
 constexpr int kBAStageBytes = kBASteps * kStepBytes;          // 16 KB
-constexpr int kBMaxAStages = 6, kBMaxBStages = 6;
+constexpr int kBMaxAStages = 8, kBMaxBStages = 8;
+constexpr int kBA3Slots = 6;                                  // ring of K16 steps of the W3 GEMM's A operand (produced by the drain)
 constexpr int kBThreads = 352;                                // warps 0-7 drain, 8 weight TMA, 9 MMA, 10 t1 TMA
 constexpr int kBBarAFull = 0, kBBarAEmpty = kBMaxAStages, kBBarBFull = 2 * kBMaxAStages, kBBarBEmpty = kBBarBFull + kBMaxBStages,
-              kBBarT2Full = kBBarBEmpty + kBMaxBStages, kBBarA3Ready = kBBarT2Full + 1, kBBarPreFull = kBBarA3Ready + 1,
-              kBBarPreFree = kBBarPreFull + 1, kBNumBars = kBBarPreFree + 1;
+              kBBarT2Full = kBBarBEmpty + kBMaxBStages, kBBarA3Ready = kBBarT2Full + 1, kBBarA3Free = kBBarA3Ready + kBA3Slots,
+              kBBarPreFull = kBBarA3Free + kBA3Slots, kBBarPreFree = kBBarPreFull + 1, kBNumBars = kBBarPreFree + 1;
 constexpr int kSmemBudget = 227 * 1024;
 
 // weight ring stage: one K16 slice of the W2 group ([n2 rows x 32 B] hi + lo) or `w3_steps_per_stage` K16 slices of W3
@@ -596,12 +604,15 @@ __host__ __device__ inline int nrf_b_w3_steps_per_stage(const LevelGeom& g) {
   int n = nrf_b_bstage_bytes(g) / (g.cop * 64);
   return n > g.k3_steps ? g.k3_steps : n;
 }
+__host__ __device__ inline int nrf_b_a3_slots(const LevelGeom& g) { return g.n2 / 16 < kBA3Slots ? g.n2 / 16 : kBA3Slots; }
 __host__ __device__ inline int nrf_b_fixed_bytes(const LevelGeom& g) {
-  return g.qg * g.k3_steps * kStepBytes + kBNumBars * 8 + 64 + 1024 + (4 * g.cip + g.cop + 64) * 4;   // W3 operand, barriers, biases
+  return nrf_b_a3_slots(g) * kStepBytes + kBNumBars * 8 + 64 + 1024 + (4 * g.cip + g.cop + 64) * 4;   // W3 operand ring, barriers, biases
 }
-// ring depths from what is left beside the W3 operand: weights first (their slices are re-streamed for every 128-pixel tile)
+// ring depths from what is left: about two thirds for the weights (their slices are re-streamed for every 128-pixel tile and are
+// 2x the bytes of the tile's t1), the rest for t1
 __host__ __device__ inline int nrf_b_b_stages(const LevelGeom& g) {
-  int n = (kSmemBudget - nrf_b_fixed_bytes(g) - 2 * kBAStageBytes) / nrf_b_bstage_bytes(g);
+  const int rem = kSmemBudget - nrf_b_fixed_bytes(g);
+  int n = (rem * 17 / 25) / nrf_b_bstage_bytes(g);
   return n > kBMaxBStages ? kBMaxBStages : n;
 }
 __host__ __device__ inline int nrf_b_a_stages(const LevelGeom& g) {
@@ -633,10 +644,11 @@ __global__ void __launch_bounds__(kBThreads, 1) nrf_b_kernel(const BArgs args) {
   const int w3_stages = (g.k3_steps + w3_sps - 1) / w3_sps;        // ring stages per pass over W3
   const bool w3_shared = (w3_stages == 1);                         // W3 fits ONE stage: loaded once per item, used by every sub-pixel
   const uint32_t sm_a = smem_base, sm_b = sm_a + (uint32_t)(kBAStages * kBAStageBytes), sm_a3 = sm_b + kBBStages * kBBStageBytes;
-  const uint32_t bars = sm_a3 + (uint32_t)(g.qg * g.k3_steps * kStepBytes);
+  const int a3_slots = nrf_b_a3_slots(g);
+  const uint32_t bars = sm_a3 + (uint32_t)(a3_slots * kStepBytes);
   auto bar = [&](int i) { return bars + (uint32_t)i * 8u; };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + (bars - smem_base) + kBNumBars * 8);
-  float* s_bias2 = reinterpret_cast<float*>(smem_gen + (bars - smem_base) + kBNumBars * 8 + 16);   // [4 * cip] permuted (q, c)
+  float* s_bias2 = reinterpret_cast<float*>(smem_gen + (bars - smem_base) + ((kBNumBars * 8 + 16 + 15) & ~15));   // [4 * cip] permuted (q, c)
   float* s_bias3 = s_bias2 + 4 * g.cip + 32;                                                        // [cop]
   for (int i = threadIdx.x; i < 4 * g.cip; i += blockDim.x) s_bias2[i] = reinterpret_cast<const float*>(args.pack + lp.b2)[i];
   for (int i = threadIdx.x; i < g.cop; i += blockDim.x) s_bias3[i] = reinterpret_cast<const float*>(args.pack + lp.b3)[i];
@@ -653,7 +665,7 @@ __global__ void __launch_bounds__(kBThreads, 1) nrf_b_kernel(const BArgs args) {
     for (int i = 0; i < kBMaxAStages; ++i) { mbar_init(bar(kBBarAFull + i), 1); mbar_init(bar(kBBarAEmpty + i), 1); }
     for (int i = 0; i < kBMaxBStages; ++i) { mbar_init(bar(kBBarBFull + i), 1); mbar_init(bar(kBBarBEmpty + i), 1); }
     mbar_init(bar(kBBarT2Full), 1);
-    mbar_init(bar(kBBarA3Ready), 8);
+    for (int i = 0; i < kBA3Slots; ++i) { mbar_init(bar(kBBarA3Ready + i), 4); mbar_init(bar(kBBarA3Free + i), 1); }
     mbar_init(bar(kBBarPreFull), 1);
     mbar_init(bar(kBBarPreFree), 8);
     fence_mbar_init();
@@ -720,11 +732,19 @@ __global__ void __launch_bounds__(kBThreads, 1) nrf_b_kernel(const BArgs args) {
           const float a1 = (c0 + 2 * j + 1 < args.ci) ? lrelu02(__uint_as_float(r[2 * j + 1]) + bv[2 * j + 1]) + rv[2 * j + 1] : 0.0f;
           split2(a0, a1, hi[j], lo[j]);
         }
-        const uint32_t d = a3_row + (uint32_t)(s16 * kStepBytes);   // A3 step index == s16 (sub-pixel qq occupies steps [qq*k3_steps, ...))
+        // ring slot of this step: G = running step counter over the CTA's items (the W3 GEMM consumes the steps in order)
+        const uint32_t G = it * (uint32_t)n_steps + (uint32_t)s16;
+        const uint32_t slot = G % (uint32_t)a3_slots, use = G / (uint32_t)a3_slots;
+        mbar_wait(bar(kBBarA3Free + slot), (use & 1) ^ 1);      // the MMAs that read the slot's previous contents have completed
+        const uint32_t d = a3_row + slot * kStepBytes;
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + 128), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + 4096), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + 4096 + 128), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]) : "memory");
+        fence_proxy_async_smem();      // generic-proxy st.shared -> visible to the tensor core
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(kBBarA3Ready + slot));   // 4 warps (this half's rows 0..127) complete the step
       };
       float rva[16], rvb[16];
       if (half < n_steps) load_res(half, rva);
@@ -739,10 +759,6 @@ __global__ void __launch_bounds__(kBThreads, 1) nrf_b_kernel(const BArgs args) {
           if (s16 + 6 < n_steps) load_res(s16 + 6, rvb);
         }
       }
-      fence_proxy_async_smem();
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(kBBarA3Ready));
       // ---- pre accumulators -> + b3 -> pixel-shuffled store: pre[img][o][2h + qy][2w + qx]
       mbar_wait(bar(kBBarPreFull), it & 1);
       tc_fence_after_sync();
@@ -851,25 +867,23 @@ __global__ void __launch_bounds__(kBThreads, 1) nrf_b_kernel(const BArgs args) {
     }
     __syncwarp();
   } else if (warp == 9) {
-    // ======================================= MMA issuer ==========================================================================
+    // ======================================= MMA issuer (one elected lane runs the whole loop, see nrf_a_kernel) ====================
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
-    const uint32_t idesc2a = umma_idesc_bf16(128, g.n2a), idesc2b = g.n2b ? umma_idesc_bf16(128, g.n2b) : 0u;
-    const uint32_t idesc3 = umma_idesc_bf16(128, g.cop);
-    const uint32_t slice2_u = (uint32_t)((g.n2 * 32) >> 4), slice3_u = (uint32_t)((g.cop * 32) >> 4);
-    const uint32_t off2b_u = (uint32_t)((g.n2a * 32) >> 4);      // rows [n2a, n2) of a slice
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      // ---- W2 GEMM: t2[128 x n2] = t1[128 x 2ci] W2g^T   (the t2 accumulator is free: the previous item's drain completed before
-      //      its W3 GEMM was issued, and that GEMM precedes this one in program order)
-      for (int k = 0; k < g.k2_steps; ++k) {
-        const int kl = k % kBASteps;
-        if (kl == 0) {
-          mbar_wait(bar(kBBarAFull + sa), pa);
+    if (elect_one()) {
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
+      const uint32_t idesc2a = umma_idesc_bf16(128, g.n2a), idesc2b = g.n2b ? umma_idesc_bf16(128, g.n2b) : 0u;
+      const uint32_t idesc3 = umma_idesc_bf16(128, g.cop);
+      const uint32_t slice2_u = (uint32_t)((g.n2 * 32) >> 4), slice3_u = (uint32_t)((g.cop * 32) >> 4);
+      const uint32_t off2b_u = (uint32_t)((g.n2a * 32) >> 4);      // rows [n2a, n2) of a slice
+      const uint32_t n_steps3 = (uint32_t)(g.n2 / 16);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        // ---- W2 GEMM: t2[128 x n2] = t1[128 x 2ci] W2g^T   (the t2 accumulator is free: every K16 step of the previous item's drain
+        //      was awaited by its W3 GEMM, which precedes this GEMM in program order)
+        for (int k = 0; k < g.k2_steps; ++k) {
+          const int kl = k % kBASteps;
+          if (kl == 0) mbar_wait_spin(bar(kBBarAFull + sa), pa);
+          mbar_wait_spin(bar(kBBarBFull + sb), pb);
           tc_fence_after_sync();
-        }
-        mbar_wait(bar(kBBarBFull + sb), pb);
-        tc_fence_after_sync();
-        if (elect_one()) {
           const uint32_t a0 = (((sm_a + sa * kBAStageBytes + (uint32_t)(kl * kStepBytes)) >> 4) & 0x3FFFu) | kDescLoLboNo;
           const uint32_t b0 = (((sm_b + sb * kBBStageBytes) >> 4) & 0x3FFFu) | kDescLoLboNo;
           const uint64_t a_hi = mk_desc(a0, kDescHiNoSw), a_lo = mk_desc(a0 + (4096 >> 4), kDescHiNoSw);
@@ -884,48 +898,44 @@ __global__ void __launch_bounds__(kBThreads, 1) nrf_b_kernel(const BArgs args) {
             umma_ss(d2, a_hi, mk_desc(b0 + slice2_u + off2b_u, kDescHiNoSw), idesc2b, 1u);
           }
           umma_commit(bar(kBBarBEmpty + sb));
-          if (kl == kBASteps - 1 || k == g.k2_steps - 1) umma_commit(bar(kBBarAEmpty + sa));
-        }
-        __syncwarp();
-        if (++sb == (uint32_t)kBBStages) { sb = 0; pb ^= 1; }
-        if (kl == kBASteps - 1 || k == g.k2_steps - 1) {
-          if (++sa == (uint32_t)kBAStages) { sa = 0; pa ^= 1; }
-        }
-      }
-      if (elect_one()) umma_commit(bar(kBBarT2Full));
-      __syncwarp();
-      // ---- W3 GEMM per sub-pixel: pre_q[128 x cop] = t2_q[128 x cip] W3^T
-      mbar_wait(bar(kBBarA3Ready), it & 1);
-      mbar_wait(bar(kBBarPreFree), (it & 1) ^ 1);   // the previous item's pre accumulators have been read
-      tc_fence_after_sync();
-      for (int qq = 0; qq < g.qg; ++qq) {
-        const uint32_t d = tmem_u + pre_base_col + (uint32_t)(qq * g.cop);
-        for (int k = 0; k < g.k3_steps; ++k) {
-          const int kl = k % w3_sps;                       // slice inside the ring stage
-          if (kl == 0 && !(w3_shared && qq > 0)) {
-            mbar_wait(bar(kBBarBFull + sb), pb);
-            tc_fence_after_sync();
+          if (++sb == (uint32_t)kBBStages) { sb = 0; pb ^= 1; }
+          if (kl == kBASteps - 1 || k == g.k2_steps - 1) {
+            umma_commit(bar(kBBarAEmpty + sa));
+            if (++sa == (uint32_t)kBAStages) { sa = 0; pa ^= 1; }
           }
-          const bool last_of_stage = (kl == w3_sps - 1 || k == g.k3_steps - 1);
-          const bool release = last_of_stage && (!w3_shared || qq == g.qg - 1);
-          if (elect_one()) {
-            const uint32_t a0 = (((sm_a3 + (uint32_t)((qq * g.k3_steps + k) * kStepBytes)) >> 4) & 0x3FFFu) | kDescLoLboNo;
+        }
+        umma_commit(bar(kBBarT2Full));
+        // ---- W3 GEMM per sub-pixel: pre_q[128 x cop] = t2_q[128 x cip] W3^T, K16 step by K16 step as the drain produces them
+        mbar_wait_spin(bar(kBBarPreFree), (it & 1) ^ 1);   // the previous item's pre accumulators have been read
+        tc_fence_after_sync();
+        for (int qq = 0; qq < g.qg; ++qq) {
+          const uint32_t d = tmem_u + pre_base_col + (uint32_t)(qq * g.cop);
+          for (int k = 0; k < g.k3_steps; ++k) {
+            const uint32_t G = it * n_steps3 + (uint32_t)(qq * g.k3_steps + k);
+            const uint32_t slot3 = G % (uint32_t)a3_slots, use3 = G / (uint32_t)a3_slots;
+            const int kl = k % w3_sps;                       // slice inside the weight ring stage
+            if (kl == 0 && !(w3_shared && qq > 0)) mbar_wait_spin(bar(kBBarBFull + sb), pb);
+            mbar_wait_spin(bar(kBBarA3Ready + slot3), use3 & 1);
+            tc_fence_after_sync();
+            const bool last_of_stage = (kl == w3_sps - 1 || k == g.k3_steps - 1);
+            const bool release = last_of_stage && (!w3_shared || qq == g.qg - 1);
+            const uint32_t a0 = (((sm_a3 + slot3 * kStepBytes) >> 4) & 0x3FFFu) | kDescLoLboNo;
             const uint32_t b0 = (((sm_b + sb * kBBStageBytes + (uint32_t)(kl * g.cop * 64)) >> 4) & 0x3FFFu) | kDescLoLboNo;
             const uint64_t a_hi = mk_desc(a0, kDescHiNoSw), a_lo = mk_desc(a0 + (4096 >> 4), kDescHiNoSw);
             umma_ss(d, a_hi, mk_desc(b0, kDescHiNoSw), idesc3, k == 0 ? 0u : 1u);
             umma_ss(d, a_lo, mk_desc(b0, kDescHiNoSw), idesc3, 1u);
             umma_ss(d, a_hi, mk_desc(b0 + slice3_u, kDescHiNoSw), idesc3, 1u);
-            if (release) umma_commit(bar(kBBarBEmpty + sb));
-          }
-          __syncwarp();
-          if (release) {
-            if (++sb == (uint32_t)kBBStages) { sb = 0; pb ^= 1; }
+            umma_commit(bar(kBBarA3Free + slot3));
+            if (release) {
+              umma_commit(bar(kBBarBEmpty + sb));
+              if (++sb == (uint32_t)kBBStages) { sb = 0; pb ^= 1; }
+            }
           }
         }
+        umma_commit(bar(kBBarPreFull));
       }
-      if (elect_one()) umma_commit(bar(kBBarPreFull));
-      __syncwarp();
     }
+    __syncwarp();
   }
   tc_fence_before_sync();
   __syncthreads();

@@ -283,7 +283,8 @@ class GazeNeRFNet(nn.Module):
         self._tvals_cache: Dict[Tuple[int, str], torch.Tensor] = {}
         self.last_stages: Optional[Dict[str, torch.Tensor]] = None
         self.keep_stages = False
-        # bench hook: when a list, (start, end) CUDA events bracketing the radiance-MLP launches are appended per forward
+        # bench hook: when a list, (start, end) CUDA events bracketing the fused radiance-MLP launch (gnrf_mlp_tc_fwd: mlp_tc_kernel +
+        # rgb_head_kernel, issued back to back by one C call, so no host gap is inside) are appended per call
         self.mlp_events: Optional[list] = None
         self.tc_debug = None   # developer hook: (dump tensor | None, timeline tensor | None, cluster size) -> gnrf_mlp_tc_fwd_debug
         # bg_img = NeuralRenderer(bg_featmap) depends on parameters only (models/gaze_nerf.py:175-176); in no-grad inference it
@@ -349,12 +350,18 @@ class GazeNeRFNet(nn.Module):
             args = (2, _lib.ptr_array([p.data_ptr() for p in packed]), _lib.ptr_array([b.data_ptr() for b in bias]),
                     ray_dl.data_ptr(), tvecs.data_ptr(), z_edges.data_ptr(), B, n_r, n_s,
                     _lib.ptr_array([f.data_ptr() for f in feat]), _lib.ptr_array([a.data_ptr() for a in alpha]), wp, ws.data_ptr(), ws_bytes)
+            if self.mlp_events is not None:   # bench hook: events around the ONE C call that launches mlp_tc_kernel + rgb_head_kernel
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
             if self.tc_debug is None:
                 _lib.check(L.gnrf_mlp_tc_fwd(*args, _stream()), "gnrf_mlp_tc_fwd")
             else:   # developer instrumentation (tests/tc_timeline.py): (dump tensor or None, timeline tensor or None, cluster size)
                 dbg, prof, csize = self.tc_debug
                 _lib.check(L.gnrf_mlp_tc_fwd_debug(*args, dbg.data_ptr() if dbg is not None else None,
                                                    prof.data_ptr() if prof is not None else None, int(csize), _stream()), "gnrf_mlp_tc_fwd_debug")
+            if self.mlp_events is not None:
+                ev1.record()
+                self.mlp_events.append((ev0, ev1))
         elif impl == "simt":
             feat_pts = torch.empty((B, n_r, n_s, C), device=dev, dtype=torch.float32)
             sigma_pts = torch.empty((B, n_r, n_s), device=dev, dtype=torch.float32)
@@ -442,14 +449,8 @@ class GazeNeRFNet(nn.Module):
 
             impl = self.mlp_impl or "tc"
             impl_c = impl if (impl != "tc" or self._tc_supported(n_s)) else "simt"
-            if self.mlp_events is not None:
-                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                ev0.record()
             feat, alpha, wts = self._render_branches(ray_dl, tvecs, z_edges, shape_ext, appea, n_s, impl_c,
                                                      want_weights=self.hier_sampling or self.keep_stages)
-            if self.mlp_events is not None:
-                ev1.record()
-                self.mlp_events.append((ev0, ev1))
             if self.keep_stages:
                 self.last_stages.update({"ray_dl": ray_dl, "z_edges": z_edges, "feat_face": feat[0], "feat_eyes": feat[1],
                                          "bg_alpha_face": alpha[0], "bg_alpha_eyes": alpha[1], "w_face": wts[0], "w_eyes": wts[1]})
