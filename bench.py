@@ -505,7 +505,7 @@ def run_render(env, args, steps, warmup, F, workload="render", with_e2e=True):
         if clocks is not None:
             clocks["window"] = "timed steps + %d identical untimed trailing steps" % tail
         total_ms = env.max_over_ranks(sum(step_ms))
-        mlp_avg = env.max_over_ranks(sum(mlp_ms) / max(len(mlp_ms), 1))
+        mlp_avg = env.max_over_ranks(sum(mlp_ms) / len(mlp_ms) if mlp_ms else sum(step_ms) / max(steps, 1))   # simt path: whole step
 
         e2e = None
         if with_e2e:

@@ -16,6 +16,11 @@
  *   - return 0 on success, a GNRF_ERR_* code otherwise; gnrf_last_error() returns a thread-local message.
  *     No exception or abort ever crosses the boundary (the reference's train loop swallows exceptions per
  *     batch, trainer/gazenerf_trainer.py:576-582 -- the Python wrapper raises RuntimeError from the code).
+ *
+ * Not covered (by design): the view-direction input of the radiance MLPs (GazeNeRFNet(include_vd=True),
+ * models/gaze_nerf.py:29-30,70-80 -- every reference entry point constructs the network with include_vd=False; the
+ * appearance input of every entry point below is the 127-d per-face code, there is no per-ray view-direction operand) and a
+ * backward for the hierarchical (FineSample) pass (the reference's own hier wiring is dead code, models/gaze_nerf.py:282-318).
  */
 #ifndef GNRF_H_
 #define GNRF_H_
