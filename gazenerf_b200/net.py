@@ -207,7 +207,24 @@ class GraphedForward(object):
         if gather is not None and (net.hier_sampling or kwargs.get("only_merge")):
             raise RuntimeError("the fused gather lives in the coarse, all-three-images neural-render call")
         self.net, self.mode, self.gather = net, mode, gather
-        self.static_in = {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in kwargs.items()}
+        # every float32 input lives in ONE flat static device buffer (views below), so a caller that keeps its host inputs in the same
+        # layout (pack_inputs) feeds a whole step with a single H2D copy instead of one small copy per tensor
+        self.input_layout, off = {}, 0
+        for k, v in kwargs.items():
+            if torch.is_tensor(v):
+                self.input_layout[k] = (off, tuple(v.shape))
+                off += (v.numel() + 3) // 4 * 4          # 16-byte aligned slots
+        dev = next(v.device for v in kwargs.values() if torch.is_tensor(v))
+        self.flat_input = torch.zeros((off,), device=dev, dtype=torch.float32)
+        self.static_in = {}
+        for k, v in kwargs.items():
+            if torch.is_tensor(v):
+                o, shp = self.input_layout[k]
+                view = self.flat_input[o:o + v.numel()].view(shp)
+                view.copy_(v.detach().float())
+                self.static_in[k] = view
+            else:
+                self.static_in[k] = v
         L = _lib.lib()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -242,9 +259,23 @@ class GraphedForward(object):
         for k, v in kwargs.items():
             if torch.is_tensor(v):
                 self.static_in[k].copy_(v, non_blocking=True)
+        return self.replay()
+
+    def replay(self) -> Dict[str, Dict[str, torch.Tensor]]:
+        """Replay on whatever the static input buffers hold (see ``flat_input`` / ``pack_inputs`` / ``static_in``)."""
         b = (self.gather.step % self.gather.n_buf) if self.gather is not None else 0
         self.graphs[b].replay()
         return self.static_outs[b]
+
+    def pack_inputs(self, kwargs: Dict[str, Optional[torch.Tensor]], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Host tensors -> one pinned flat float32 buffer in the layout of ``flat_input``; then per step
+        ``gf.flat_input.copy_(packed, non_blocking=True); gf.replay()`` is ONE host-to-device copy + one graph launch."""
+        if out is None:
+            out = torch.zeros((self.flat_input.numel(),), dtype=torch.float32).pin_memory()
+        for k, (o, shp) in self.input_layout.items():
+            v = kwargs[k]
+            out[o:o + v.numel()].view(shp).copy_(v.detach().float())
+        return out
 
 
 class GazeNeRFNet(nn.Module):
