@@ -35,6 +35,7 @@ SYMBOLS = [
     "gnrf_mlp_simt_fwd", "gnrf_composite_fwd",
     "gnrf_mlp_tc_packed_bytes", "gnrf_mlp_tc_bias_floats", "gnrf_mlp_tc_pack", "gnrf_mlp_tc_fold",
     "gnrf_mlp_tc_workspace_bytes", "gnrf_mlp_tc_fwd", "gnrf_mlp_tc_fwd_debug",
+    "gnrf_mlp_tc_pack_vd", "gnrf_mlp_tc_vd_bias", "gnrf_mlp_tc_fwd_vd",
     "gnrf_compose_fwd", "gnrf_nr_workspace_bytes", "gnrf_neural_render_fwd",
     "gnrf_nr_tc_packed_bytes", "gnrf_nr_tc_pack", "gnrf_neural_render_tc_fwd", "gnrf_neural_render_tc_layerwise_fwd",
     "gnrf_neural_render_tc_fwd_gather",
@@ -138,6 +139,9 @@ def lib() -> ctypes.CDLL:
     L.gnrf_mlp_tc_workspace_bytes.restype = sz
     L.gnrf_mlp_tc_workspace_bytes.argtypes = [i32, i32, i32]
     L.gnrf_mlp_tc_fwd.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, sz, vp]
+    L.gnrf_mlp_tc_pack_vd.argtypes = [vp, i32, vp, vp]
+    L.gnrf_mlp_tc_vd_bias.argtypes = [vp, vp, i32, i32, vp, vp]
+    L.gnrf_mlp_tc_fwd_vd.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, sz, vp]
     L.gnrf_mlp_tc_fwd_debug.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, sz, vp, vp, i32, vp]
     L.gnrf_compose_fwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]
     L.gnrf_nr_workspace_bytes.restype = sz

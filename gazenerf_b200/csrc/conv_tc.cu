@@ -198,10 +198,17 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_tc_kernel(const ConvArgs a
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             if (4 * g < nvalid) {
-              float v0 = lrelu02(__uint_as_float(r[4 * g + 0]) + bv[4 * g + 0]) + rv[4 * g + 0];
-              float v1 = lrelu02(__uint_as_float(r[4 * g + 1]) + bv[4 * g + 1]) + rv[4 * g + 1];
-              float v2 = lrelu02(__uint_as_float(r[4 * g + 2]) + bv[4 * g + 2]) + rv[4 * g + 2];
-              float v3 = lrelu02(__uint_as_float(r[4 * g + 3]) + bv[4 * g + 3]) + rv[4 * g + 3];
+              // the least significant mantissa bit of every stored value carries sign(pre-activation) (1 = negative): the backward
+              // (psu_bwd_kernel) reads the LeakyReLU slope from it instead of recovering it from the cancellation-prone sh - x
+              // (a 1-ulp, 6e-8 relative, perturbation of the forward value)
+              auto psu = [](float z, float res) {
+                const float o = lrelu02(z) + res;
+                return __uint_as_float((__float_as_uint(o) & ~1u) | (z < 0.0f ? 1u : 0u));
+              };
+              float v0 = psu(__uint_as_float(r[4 * g + 0]) + bv[4 * g + 0], rv[4 * g + 0]);
+              float v1 = psu(__uint_as_float(r[4 * g + 1]) + bv[4 * g + 1], rv[4 * g + 1]);
+              float v2 = psu(__uint_as_float(r[4 * g + 2]) + bv[4 * g + 2], rv[4 * g + 2]);
+              float v3 = psu(__uint_as_float(r[4 * g + 3]) + bv[4 * g + 3], rv[4 * g + 3]);
               *reinterpret_cast<float2*>(o) = make_float2(v0, v1);                       // row 2h,   cols 2w, 2w+1
               *reinterpret_cast<float2*>(o + 2 * args.Wd) = make_float2(v2, v3);         // row 2h+1
             }

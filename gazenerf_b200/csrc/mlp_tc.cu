@@ -126,7 +126,9 @@ constexpr size_t kAuxW1c = kAuxW5c + (size_t)kHidden * GNRF_SHAPE_EXT_DIMS;   //
 constexpr size_t kAuxW2t = kAuxW1c + (size_t)kH2 * GNRF_APPEA_DIMS;           // [192][258] RGB_layer_2 transposed
 constexpr size_t kAuxB2 = kAuxW2t + (size_t)kH2 * kFeat;                      // [258]
 constexpr size_t kAuxWf = kAuxB2 + 264;                                       // [208][384] fused last-stage matrix (fp32)
-constexpr size_t kAuxFloats = kAuxWf + (size_t)kL8N * kHidden;
+constexpr int kVdDims = 27;                                                   // view-direction encoding: 3 + 6 * 4 (include_vd=True)
+constexpr size_t kAuxW1v = kAuxWf + (size_t)kL8N * kHidden;                   // [192][27] view-direction columns of RGB_layer_1 (or zeros)
+constexpr size_t kAuxFloats = kAuxW1v + (size_t)kH2 * 32;
 constexpr size_t kPackedBytes = kStreamBytes + kAuxFloats * sizeof(float);
 
 __host__ __device__ inline int bias_offset(int layer) { return layer * kHidden; }
@@ -143,6 +145,7 @@ constexpr int kSmemBytes = kSmemMisc + 64 + 1024;            // + alignment slac
 
 struct BranchArgs {
   const unsigned char* stream;  // packed bf16 stage stream
+  const float* vd_bias;         // [B][N_r][192] per-RAY bias of the last stage (include_vd=True: view-direction columns) or null
   const float* bias;            // [B][kBiasFloats]
   float* hc;                    // [B][N_r][192]  composited hidden
   float* wsum;                  // [B][N_r]
@@ -592,6 +595,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
       acc_phase ^= 1;
       tc_fence_after_sync();
       const float* b8 = bias + bias_offset(8);
+      const float* vdb = br.vd_bias ? br.vd_bias + ((size_t)b * args.N_r + ray) * kH2 : nullptr;   // include_vd: W1[:, 384:411] PE4(d_ray)
       float w_k;
       {
         uint32_t rs;
@@ -632,7 +636,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float h = fmaxf(__uint_as_float(r[j]) + __ldg(b8 + c0 + j), 0.0f);               // ReLU after RGB_layer_1 (:112)
+          float h = fmaxf(__uint_as_float(r[j]) + __ldg(b8 + c0 + j) + (vdb ? __ldg(vdb + c0 + j) : 0.0f), 0.0f);   // ReLU after RGB_layer_1 (:112)
           scratch[row * kScratchLd + c0 + j] = w_k * h;
           if (dump) args.dbg[((size_t)9 * kTile + row) * kHidden + c0 + j] = h;
         }
@@ -729,6 +733,7 @@ __global__ void __launch_bounds__(288) rgb_head_kernel(const HeadArgs ha, int N_
 struct PackSrc {
   const float* w[12];
   const float* b[12];
+  int n_vd;   // 0, or 27: RGB_layer_1's input is [hidden 384 | view-direction encoding 27 | appearance 127] (models/gaze_nerf.py:140-141)
 };
 
 // Wf[n][k] (n < 192) = sum_j W1[n][j] * W0rgb[j][k] (fp64 accumulate);  row 192 = density weights;  rows 193.. = 0.
@@ -737,7 +742,7 @@ __global__ void fuse_head_kernel(PackSrc src, float* __restrict__ aux) {
   const int n = blockIdx.x;  // 0..207
   float* wf = aux + kAuxWf + (size_t)n * kHidden;
   float* base_bias = aux + kAuxBaseBias;
-  const int ld1 = kHidden + GNRF_APPEA_DIMS;
+  const int ld1 = kHidden + src.n_vd + GNRF_APPEA_DIMS;
   if (n < kH2) {
     for (int k = threadIdx.x; k < kHidden; k += blockDim.x) {
       double acc = 0.0;
@@ -769,9 +774,14 @@ __global__ void pack_aux_kernel(PackSrc src, float* __restrict__ aux) {
     aux[kAuxW0c + i] = src.w[0][(size_t)n * vp + GNRF_PE_DIMS + k];
     aux[kAuxW5c + i] = src.w[5][(size_t)n * (vp + kHidden) + GNRF_PE_DIMS + k];
   }
+  const int ld1 = kHidden + src.n_vd + GNRF_APPEA_DIMS;
   for (int i = tid; i < kH2 * GNRF_APPEA_DIMS; i += nth) {
     int n = i / GNRF_APPEA_DIMS, k = i % GNRF_APPEA_DIMS;
-    aux[kAuxW1c + i] = src.w[10][(size_t)n * (kHidden + GNRF_APPEA_DIMS) + kHidden + k];
+    aux[kAuxW1c + i] = src.w[10][(size_t)n * ld1 + kHidden + src.n_vd + k];
+  }
+  for (int i = tid; i < kH2 * 32; i += nth) {
+    int n = i / 32, k = i % 32;
+    aux[kAuxW1v + i] = (k < src.n_vd) ? src.w[10][(size_t)n * ld1 + kHidden + k] : 0.0f;
   }
   for (int i = tid; i < kH2 * kFeat; i += nth) {
     int k = i / kFeat, c = i % kFeat;
@@ -844,6 +854,43 @@ __global__ void pack_stream_kernel(PackSrc src, const float* __restrict__ wf, un
   }
 }
 
+// include_vd=True: per-RAY bias of the last stage  vd_bias[ray][n] = sum_j W1[n][384 + j] * PE4(d_ray)[j]  (n < 192), where PE4 is the
+// reference's Embedder with 4 frequencies + the input on the normalised ray direction (models/gaze_nerf.py:70-80, 240-243;
+// utils/model_utils.py:272-280, 317-318): [d, sin(2^0 d), cos(2^0 d), ..., sin(2^3 d), cos(2^3 d)].  One CTA per 8 rays.
+__global__ void __launch_bounds__(kH2) vd_bias_kernel(const float* __restrict__ aux, const float4* __restrict__ ray_dl, int n_rays,
+                                                    float* __restrict__ vd_bias) {
+  __shared__ float s_pe[8][32];
+  const int r0 = blockIdx.x * 8;
+  if (threadIdx.x < 8 * 3) {
+    const int rl = threadIdx.x / 3, c = threadIdx.x % 3;
+    if (r0 + rl < n_rays) {
+      const float4 dl = ray_dl[r0 + rl];
+      const float x = c == 0 ? dl.x : (c == 1 ? dl.y : dl.z);
+      s_pe[rl][c] = x;
+      float f = 1.0f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float sv, cv;
+        sincosf(__fmul_rn(x, f), &sv, &cv);
+        s_pe[rl][3 + 6 * q + c] = sv;
+        s_pe[rl][6 + 6 * q + c] = cv;
+        f *= 2.0f;
+      }
+    }
+  }
+  __syncthreads();
+  const int n = threadIdx.x;
+  float w[kVdDims];
+#pragma unroll
+  for (int j = 0; j < kVdDims; ++j) w[j] = __ldg(aux + kAuxW1v + (size_t)n * 32 + j);
+  for (int rl = 0; rl < 8 && r0 + rl < n_rays; ++rl) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kVdDims; ++j) acc = fmaf(w[j], s_pe[rl][j], acc);
+    vd_bias[(size_t)(r0 + rl) * kH2 + n] = acc;
+  }
+}
+
 // per-face biases: bias[b] = base + code / appearance contributions (fold i).  One warp per output row: the lanes stride over the
 // 181 code (127 appearance) columns of the row, so the weight reads are coalesced; rows without a fold are plain copies.
 constexpr int kFoldWarps = 8;
@@ -883,10 +930,12 @@ using namespace gnrf::tc;
 extern "C" size_t gnrf_mlp_tc_packed_bytes(void) { return kPackedBytes; }
 extern "C" size_t gnrf_mlp_tc_bias_floats(void) { return kBiasFloats; }
 
-extern "C" int gnrf_mlp_tc_pack(const float* const* params, void* packed, gnrf_stream_t stream) {
+extern "C" int gnrf_mlp_tc_pack_vd(const float* const* params, int n_vd, void* packed, gnrf_stream_t stream) {
   GNRF_CHECK_ARG(params && packed);
+  GNRF_CHECK_ARG(n_vd == 0 || n_vd == kVdDims);
   GNRF_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 127) == 0);
   PackSrc src;
+  src.n_vd = n_vd;
   for (int i = 0; i < 12; ++i) {
     src.w[i] = params[2 * i];
     src.b[i] = params[2 * i + 1];
@@ -900,6 +949,19 @@ extern "C" int gnrf_mlp_tc_pack(const float* const* params, void* packed, gnrf_s
   pack_stream_kernel<<<kNumStagesPerTile, 256, 0, st>>>(src, aux + kAuxWf, p);
   GNRF_LAUNCH_CHECK();
   count_launches(3);
+  return GNRF_OK;
+}
+
+extern "C" int gnrf_mlp_tc_pack(const float* const* params, void* packed, gnrf_stream_t stream) {
+  return gnrf_mlp_tc_pack_vd(params, 0, packed, stream);
+}
+
+extern "C" int gnrf_mlp_tc_vd_bias(const void* packed, const float* ray_dl, int B, int N_r, float* vd_bias, gnrf_stream_t stream) {
+  GNRF_CHECK_ARG(packed && ray_dl && vd_bias && B > 0 && N_r > 0);
+  const float* aux = reinterpret_cast<const float*>(static_cast<const unsigned char*>(packed) + kStreamBytes);
+  vd_bias_kernel<<<ceil_div(B * N_r, 8), kH2, 0, as_stream(stream)>>>(aux, reinterpret_cast<const float4*>(ray_dl), B * N_r, vd_bias);
+  GNRF_LAUNCH_CHECK();
+  count_launches(1);
   return GNRF_OK;
 }
 
@@ -920,10 +982,10 @@ extern "C" size_t gnrf_mlp_tc_workspace_bytes(int n_branch, int B, int N_r) {
   return hc + (size_t)kMaxGrid * 65 * kTile * sizeof(uint32_t);
 }
 
-extern "C" int gnrf_mlp_tc_fwd_debug(int n_branch, const void* const* packed, const float* const* bias, const float* ray_dl,
-                                     const float* tvecs, const float* z_edges, int B, int N_r, int N_s, float* const* feat_ray,
-                                     float* const* bg_alpha, float* const* weights, void* workspace, size_t workspace_bytes,
-                                     float* dbg_dump, long long* timeline, int cluster_size, gnrf_stream_t stream) {
+static int mlp_tc_fwd_impl(int n_branch, const void* const* packed, const float* const* bias, const float* const* vd_bias,
+                           const float* ray_dl, const float* tvecs, const float* z_edges, int B, int N_r, int N_s, float* const* feat_ray,
+                           float* const* bg_alpha, float* const* weights, void* workspace, size_t workspace_bytes, float* dbg_dump,
+                           long long* timeline, int cluster_size, gnrf_stream_t stream) {
   GNRF_CHECK_ARG(packed && bias && ray_dl && tvecs && z_edges && feat_ray && bg_alpha && workspace);
   GNRF_CHECK_ARG(n_branch == 1 || n_branch == 2);
   GNRF_CHECK_ARG(B > 0 && N_r > 0 && N_s > 0);
@@ -951,6 +1013,7 @@ extern "C" int gnrf_mlp_tc_fwd_debug(int n_branch, const void* const* packed, co
     GNRF_CHECK_ARG(packed[j] && bias[j] && feat_ray[j] && bg_alpha[j]);
     a.br[i].stream = static_cast<const unsigned char*>(packed[j]);
     a.br[i].bias = bias[j];
+    a.br[i].vd_bias = vd_bias ? vd_bias[j] : nullptr;
     a.br[i].hc = ws + (size_t)j * B * N_r * (kH2 + 1);
     a.br[i].wsum = a.br[i].hc + (size_t)B * N_r * kH2;
     a.br[i].weights = weights ? weights[j] : nullptr;
@@ -1015,10 +1078,28 @@ extern "C" int gnrf_mlp_tc_fwd_debug(int n_branch, const void* const* packed, co
   return GNRF_OK;
 }
 
+extern "C" int gnrf_mlp_tc_fwd_debug(int n_branch, const void* const* packed, const float* const* bias, const float* ray_dl,
+                                     const float* tvecs, const float* z_edges, int B, int N_r, int N_s, float* const* feat_ray,
+                                     float* const* bg_alpha, float* const* weights, void* workspace, size_t workspace_bytes,
+                                     float* dbg_dump, long long* timeline, int cluster_size, gnrf_stream_t stream) {
+  return mlp_tc_fwd_impl(n_branch, packed, bias, nullptr, ray_dl, tvecs, z_edges, B, N_r, N_s, feat_ray, bg_alpha, weights, workspace,
+                         workspace_bytes, dbg_dump, timeline, cluster_size, stream);
+}
+
 extern "C" int gnrf_mlp_tc_fwd(int n_branch, const void* const* packed, const float* const* bias, const float* ray_dl,
                                const float* tvecs, const float* z_edges, int B, int N_r, int N_s, float* const* feat_ray,
                                float* const* bg_alpha, float* const* weights, void* workspace, size_t workspace_bytes,
                                gnrf_stream_t stream) {
-  return gnrf_mlp_tc_fwd_debug(n_branch, packed, bias, ray_dl, tvecs, z_edges, B, N_r, N_s, feat_ray, bg_alpha, weights, workspace,
-                               workspace_bytes, nullptr, nullptr, 2, stream);
+  return mlp_tc_fwd_impl(n_branch, packed, bias, nullptr, ray_dl, tvecs, z_edges, B, N_r, N_s, feat_ray, bg_alpha, weights, workspace,
+                         workspace_bytes, nullptr, nullptr, 2, stream);
+}
+
+extern "C" int gnrf_mlp_tc_fwd_vd(int n_branch, const void* const* packed, const float* const* bias, const float* const* vd_bias,
+                                  const float* ray_dl, const float* tvecs, const float* z_edges, int B, int N_r, int N_s,
+                                  float* const* feat_ray, float* const* bg_alpha, float* const* weights, void* workspace,
+                                  size_t workspace_bytes, gnrf_stream_t stream) {
+  GNRF_CHECK_ARG(vd_bias);
+  for (int i = 0; i < n_branch && i < 2; ++i) GNRF_CHECK_ARG(vd_bias[i] != nullptr);
+  return mlp_tc_fwd_impl(n_branch, packed, bias, vd_bias, ray_dl, tvecs, z_edges, B, N_r, N_s, feat_ray, bg_alpha, weights, workspace,
+                         workspace_bytes, nullptr, nullptr, 2, stream);
 }

@@ -403,7 +403,7 @@ __global__ void sigmoid_bwd_kernel(const float* __restrict__ g_img, const float*
 }
 
 // Backward of  sh = pixel_shuffle2( LReLU(v) + repeat(x, 4) )  (pixel_shuffle_upsample.py:34-40):
-//   g_pre[n][j][h][w] = g_sh[n][j/4][2h + (j/2)%2][2w + j%2] * slope(v),  slope recovered from sign(sh - x[j % ci]);
+//   g_pre[n][j][h][w] = g_sh[n][j/4][2h + (j/2)%2][2w + j%2] * slope(v),  sign(v) = the LSB the forward epilogue stored in sh (conv_tc.cu);
 //   g_res[n][c][h][w] = sum over the four j == c (mod ci) of the un-shuffled gradient.
 __global__ void psu_bwd_kernel(const float* __restrict__ g_sh, const float* __restrict__ sh, const float* __restrict__ x, int ci, int H,
                                int Wd, long long total, float* __restrict__ g_pre, float* __restrict__ g_res) {
@@ -413,7 +413,6 @@ __global__ void psu_bwd_kernel(const float* __restrict__ g_sh, const float* __re
   const int h = (int)((idx / Wd) % H);
   const int c = (int)((idx / ((long long)Wd * H)) % ci);
   const int n = (int)(idx / ((long long)Wd * H * ci));
-  const float xv = x[idx];
   const size_t HW = (size_t)H * Wd;
   float acc = 0.0f;
 #pragma unroll
@@ -421,8 +420,8 @@ __global__ void psu_bwd_kernel(const float* __restrict__ g_sh, const float* __re
     const int j = c + q * ci;
     const size_t o = ((size_t)n * ci + (j >> 2)) * 4 * HW + (size_t)(2 * h + ((j >> 1) & 1)) * (2 * Wd) + 2 * w + (j & 1);
     const float g = g_sh[o];
-    const float lre = sh[o] - xv;
-    g_pre[((size_t)n * 4 * ci + j) * HW + (size_t)h * Wd + w] = lre >= 0.0f ? g : 0.2f * g;
+    const bool neg = (__float_as_uint(sh[o]) & 1u) != 0u;
+    g_pre[((size_t)n * 4 * ci + j) * HW + (size_t)h * Wd + w] = neg ? 0.2f * g : g;
     acc += g;
   }
   g_res[idx] = acc;

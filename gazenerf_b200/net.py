@@ -281,10 +281,6 @@ class GraphedForward(object):
 class GazeNeRFNet(nn.Module):
     def __init__(self, opt: BaseOptions, include_vd, hier_sampling, mlp_impl: Optional[str] = None) -> None:
         super().__init__()
-        if include_vd:
-            raise NotImplementedError(
-                "include_vd=True (view-direction encoding) is not built: every reference entry point passes "
-                "include_vd=False (train.py:43, evaluate.py); see DESIGN.md 'out of scope'")
         self.hier_sampling = hier_sampling
         self.include_vd = include_vd
         self.opt = opt
@@ -299,7 +295,12 @@ class GazeNeRFNet(nn.Module):
         assert self.base_shape_code_dims + self.base_gaze_dims == 181 and self.base_appea_code_dims == 127, \
             "libgnrf is specialised for the reference's code dims (179 + 2, 127)"
         vp_channels = self.base_shape_code_dims + self.base_gaze_dims + self.vp_n_freqs * 6 + 3
-        vd_channels = self.base_appea_code_dims
+        # include_vd (models/gaze_nerf.py:70-80): the normalised ray direction, encoded with 4 frequencies + the input (27 channels),
+        # is concatenated in front of the appearance code at RGB_layer_1's input.  Supported by the fused tcgen05 inference path
+        # (a per-ray bias term of the last stage); the differentiable path and the literal fp32 path raise.
+        self.vd_n_freqs = 4
+        self.vd_pe_dims = (self.vd_n_freqs * 6 + 3) if include_vd else 0
+        vd_channels = self.base_appea_code_dims + self.vd_pe_dims
         # construction order == models/gaze_nerf.py:87-119 (eyes first) so seeded init matches the reference
         self.fg_CD_predictor_eyes = RadianceMLP(vp_channels, vd_channels, h_channel=self.mlp_h_channel, res_nfeat=self.featmap_nc)
         self.fg_CD_predictor_face = RadianceMLP(vp_channels, vd_channels, h_channel=self.mlp_h_channel, res_nfeat=self.featmap_nc)
@@ -354,7 +355,7 @@ class GazeNeRFNet(nn.Module):
         if hit is not None and hit[0] == key:
             return hit[1]
         packed = torch.empty((L.gnrf_mlp_tc_packed_bytes(),), device=params[0].device, dtype=torch.uint8)
-        _lib.check(L.gnrf_mlp_tc_pack(_ptrs(params), packed.data_ptr(), _stream()), "gnrf_mlp_tc_pack")
+        _lib.check(L.gnrf_mlp_tc_pack_vd(_ptrs(params), int(self.vd_pe_dims), packed.data_ptr(), _stream()), "gnrf_mlp_tc_pack_vd")
         self._tc_cache[name] = (key, packed)
         return packed
 
@@ -381,10 +382,19 @@ class GazeNeRFNet(nn.Module):
             args = (2, _lib.ptr_array([p.data_ptr() for p in packed]), _lib.ptr_array([b.data_ptr() for b in bias]),
                     ray_dl.data_ptr(), tvecs.data_ptr(), z_edges.data_ptr(), B, n_r, n_s,
                     _lib.ptr_array([f.data_ptr() for f in feat]), _lib.ptr_array([a.data_ptr() for a in alpha]), wp, ws.data_ptr(), ws_bytes)
+            vdb = None
+            if self.include_vd:   # per-ray bias of the last stage: W1[:, 384:411] . PE4(ray direction)  (models/gaze_nerf.py:70-80,140-141)
+                vdb = [torch.empty((B, n_r, 192), device=dev, dtype=torch.float32) for _ in range(2)]
+                for i in range(2):
+                    _lib.check(L.gnrf_mlp_tc_vd_bias(packed[i].data_ptr(), ray_dl.data_ptr(), B, n_r, vdb[i].data_ptr(), _stream()),
+                               "gnrf_mlp_tc_vd_bias")
             if self.mlp_events is not None:   # bench hook: events around the ONE C call that launches mlp_tc_kernel + rgb_head_kernel
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
-            if self.tc_debug is None:
+            if vdb is not None:
+                _lib.check(L.gnrf_mlp_tc_fwd_vd(args[0], args[1], args[2], _lib.ptr_array([v.data_ptr() for v in vdb]), *args[3:], _stream()),
+                           "gnrf_mlp_tc_fwd_vd")
+            elif self.tc_debug is None:
                 _lib.check(L.gnrf_mlp_tc_fwd(*args, _stream()), "gnrf_mlp_tc_fwd")
             else:   # developer instrumentation (tests/tc_timeline.py): (dump tensor or None, timeline tensor or None, cluster size)
                 dbg, prof, csize = self.tc_debug
@@ -394,6 +404,9 @@ class GazeNeRFNet(nn.Module):
                 ev1.record()
                 self.mlp_events.append((ev0, ev1))
         elif impl == "simt":
+            if self.include_vd:
+                raise NotImplementedError("include_vd=True runs on the fused tcgen05 path only (num_sample_coarse must divide 128; "
+                                          "the literal fp32 kernels have no view-direction operand)")
             feat_pts = torch.empty((B, n_r, n_s, C), device=dev, dtype=torch.float32)
             sigma_pts = torch.empty((B, n_r, n_s), device=dev, dtype=torch.float32)
             for i, (_, mlp) in enumerate(branches):
@@ -530,6 +543,9 @@ class GazeNeRFNet(nn.Module):
         """Same outputs as ``_forward`` with gradients to parameters, codes, gaze and camera (R, T); see gazenerf_b200/train.py."""
         from .train import forward_train
 
+        if self.include_vd:
+            raise NotImplementedError("include_vd=True is inference-only in libgnrf (no reference entry point trains with the view-direction "
+                                      "input, train.py:43); use torch.no_grad()")
         if self.hier_sampling:
             raise NotImplementedError("the differentiable path covers the coarse render only (the reference's hier branch is dead code, "
                                       "SURVEY §0); use torch.no_grad() for hier_sampling=True")

@@ -17,10 +17,9 @@
  *     No exception or abort ever crosses the boundary (the reference's train loop swallows exceptions per
  *     batch, trainer/gazenerf_trainer.py:576-582 -- the Python wrapper raises RuntimeError from the code).
  *
- * Not covered (by design): the view-direction input of the radiance MLPs (GazeNeRFNet(include_vd=True),
- * models/gaze_nerf.py:29-30,70-80 -- every reference entry point constructs the network with include_vd=False; the
- * appearance input of every entry point below is the 127-d per-face code, there is no per-ray view-direction operand) and a
- * backward for the hierarchical (FineSample) pass (the reference's own hier wiring is dead code, models/gaze_nerf.py:282-318).
+ * Not covered (by design): gradients with the view-direction input (include_vd=True is inference-only here, see
+ * gnrf_mlp_tc_fwd_vd; every reference entry point constructs the network with include_vd=False) and a backward for the
+ * hierarchical (FineSample) pass (the reference's own hier wiring is dead code, models/gaze_nerf.py:282-318).
  */
 #ifndef GNRF_H_
 #define GNRF_H_
@@ -119,6 +118,18 @@ int gnrf_mlp_tc_fwd(int n_branch, const void* const* packed, const float* const*
                     const float* tvecs, const float* z_edges, int B, int N_r, int N_s, float* const* feat_ray,
                     float* const* bg_alpha, float* const* weights, void* workspace, size_t workspace_bytes,
                     gnrf_stream_t stream);
+/* include_vd=True (GazeNeRFNet(include_vd=True), models/gaze_nerf.py:29-30,70-80,140-141): RGB_layer_1's input becomes
+ * [hidden 384 | view-direction encoding 27 | appearance 127], the encoding being the reference's Embedder (4 frequencies + input) of the
+ * normalised ray direction.  The 27 columns are constant per RAY, so they fold into a per-ray bias of the fused kernel's last stage:
+ *   gnrf_mlp_tc_pack_vd(params, n_vd = 27, ...)  packs a 192 x 538 RGB_layer_1 (n_vd = 0: same as gnrf_mlp_tc_pack);
+ *   gnrf_mlp_tc_vd_bias(packed, ray_dl [B,N_r,4]) -> vd_bias [B,N_r,192];
+ *   gnrf_mlp_tc_fwd_vd = gnrf_mlp_tc_fwd with vd_bias[i] per branch.  Inference only (the differentiable path has no view-direction
+ *   operand; the drop-in module raises for grad with include_vd=True). */
+int gnrf_mlp_tc_pack_vd(const float* const* params, int n_vd, void* packed, gnrf_stream_t stream);
+int gnrf_mlp_tc_vd_bias(const void* packed, const float* ray_dl, int B, int N_r, float* vd_bias, gnrf_stream_t stream);
+int gnrf_mlp_tc_fwd_vd(int n_branch, const void* const* packed, const float* const* bias, const float* const* vd_bias,
+                       const float* ray_dl, const float* tvecs, const float* z_edges, int B, int N_r, int N_s, float* const* feat_ray,
+                       float* const* bg_alpha, float* const* weights, void* workspace, size_t workspace_bytes, gnrf_stream_t stream);
 /* Developer variant of gnrf_mlp_tc_fwd with explicit instrumentation arguments (no environment variables, no hidden state):
  * dbg_dump (nullable) [10][128][384] fp32 dump of tile 0's per-layer activations; timeline (nullable) [4][10][16] int64 clock64
  * stamps of CTA 0 (tests/tc_timeline.py); cluster_size 1 or 2 (CTAs sharing each weight stage by TMA multicast; 2 = default). */

@@ -214,13 +214,16 @@ def mlp_points(sd: Dict[str, Tensor], prefix: str, vp: Tensor, vd: Tensor, n_lay
     return feat, sigma
 
 
-def mlp_branch(sd, prefix, pe: Tensor, shape_ext: Tensor, appea: Tensor, chunk: int = 1 << 16):
+def mlp_branch(sd, prefix, pe: Tensor, shape_ext: Tensor, appea: Tensor, chunk: int = 1 << 16, vd_pe: Optional[Tensor] = None):
     """pe [B,63,N_r,N_s]; shape_ext [B,181]; appea [B,127] -> feat [B,C,N_r,N_s], sigma [B,1,N_r,N_s].
 
     Builds the broadcast input of models/gaze_nerf.py:248-262,136-143 per point (chunked to bound memory).
+    ``vd_pe`` [B,27,N_r,N_s] (include_vd=True): the view-direction encoding, concatenated IN FRONT of the appearance code
+    (``torch.cat([FGvd_embedder, appea_code], dim=1)``, models/gaze_nerf.py:140-141).
     """
     b, c, n_r, n_s = pe.shape
     pts = pe.permute(0, 2, 3, 1).reshape(b, n_r * n_s, c)
+    vds = vd_pe.permute(0, 2, 3, 1).reshape(b, n_r * n_s, -1) if vd_pe is not None else None
     feats, sigmas = [], []
     for i in range(b):
         fo, so = [], []
@@ -228,6 +231,8 @@ def mlp_branch(sd, prefix, pe: Tensor, shape_ext: Tensor, appea: Tensor, chunk: 
             x = pts[i, s : s + chunk]
             vp = torch.cat([x, shape_ext[i].expand(x.shape[0], -1)], 1)
             vd = appea[i].expand(x.shape[0], -1)
+            if vds is not None:
+                vd = torch.cat([vds[i, s : s + chunk], vd], 1)
             f, sg = mlp_points(sd, prefix, vp, vd)
             fo.append(f)
             so.append(sg)
@@ -411,21 +416,26 @@ def fine_sample(w: Tensor, zvals: Tensor, o: Tensor, d: Tensor, l: Tensor, n_fin
 # --------------------------------------------------------------------------------------
 # full forward (models/gaze_nerf.py:121-351)
 # --------------------------------------------------------------------------------------
-def render_branches(sd, opt: OracleOptions, pts, z_dists, zvals, shape_code, appea_code, gaze_code):
-    """PE -> both branch MLPs -> composite. Returns per-branch (feat_ray, bg_alpha, w)."""
+def render_branches(sd, opt: OracleOptions, pts, z_dists, zvals, shape_code, appea_code, gaze_code, ray_d: Optional[Tensor] = None):
+    """PE -> both branch MLPs -> composite. Returns per-branch (feat_ray, bg_alpha, w).
+    ``ray_d`` [B,3,N_r] (include_vd=True, models/gaze_nerf.py:70-80,240-243): the normalised ray directions, expanded over the samples
+    (utils/model_utils.py:317-318) and encoded with 4 frequencies + the input (27 channels)."""
     pe = posenc(pts, opt.vp_n_freqs, True)
     shape_ext = torch.cat([shape_code, gaze_code], 1)  # models/gaze_nerf.py:248
+    vd_pe = None
+    if ray_d is not None:
+        vd_pe = posenc(ray_d.unsqueeze(-1).expand(-1, -1, -1, pts.shape[-1]), 4, True)
     out = {}
     for name in ("face", "eyes"):
-        feat, sigma = mlp_branch(sd, "fg_CD_predictor_" + name, pe, shape_ext, appea_code)
+        feat, sigma = mlp_branch(sd, "fg_CD_predictor_" + name, pe, shape_ext, appea_code, vd_pe=vd_pe)
         fr, ba, _, w = composite(feat, sigma, z_dists, zvals)
         out[name] = (fr, ba, w)
     return out
 
 
 def forward(sd, opt: OracleOptions, mode: str, batch_xy, shape_code, appea_code, gaze_code, rmats, tvecs,
-            inv_inmats, jitter_u: Optional[Tensor] = None, return_stages: bool = False):
-    """GazeNeRFNet.forward (hier_sampling=False, include_vd=False); models/gaze_nerf.py:211-351.
+            inv_inmats, jitter_u: Optional[Tensor] = None, return_stages: bool = False, include_vd: bool = False):
+    """GazeNeRFNet.forward (hier_sampling=False); models/gaze_nerf.py:211-351.  ``include_vd``: the view-direction input (:70-80).
 
     In "train" mode the caller passes ``jitter_u`` (what ``torch.rand_like(zvals)`` would draw).
     """
@@ -434,7 +444,8 @@ def forward(sd, opt: OracleOptions, mode: str, batch_xy, shape_code, appea_code,
     s = opt.featmap_size
     smp = sample_points(batch_xy, rmats, tvecs, inv_inmats, opt.num_sample_coarse, opt.world_z1, opt.world_z2,
                         jitter_u if mode == "train" else None)
-    br = render_branches(sd, opt, smp["pts"], smp["z_dists"], smp["zvals"], shape_code, appea_code, gaze_code)
+    br = render_branches(sd, opt, smp["pts"], smp["z_dists"], smp["zvals"], shape_code, appea_code, gaze_code,
+                         ray_d=smp["ray_d"] if include_vd else None)
     c = opt.featmap_nc
     feat_face = br["face"][0].view(b, c, s, s)
     feat_eyes = br["eyes"][0].view(b, c, s, s)

@@ -183,6 +183,8 @@ def main():
         _gen_std(BaseOptions, GazeNeRFNet, inputs)
     if want("mid"):
         _gen_mid(BaseOptions, GazeNeRFNet, inputs)
+    if want("vd"):
+        _gen_vd(BaseOptions, GazeNeRFNet, inputs)
 
 
 def _gen_tiny(BaseOptions, GazeNeRFNet, inputs):
@@ -244,6 +246,61 @@ def _gen_mid(BaseOptions, GazeNeRFNet, inputs):
     out.update(chk)
     np.savez_compressed(os.path.join(OUT, "mid_dense_test.npz"), **out)
     print("mid_dense_test", sum(v.nbytes for v in out.values()) // 1024, "KiB raw")
+
+
+def _gen_vd(BaseOptions, GazeNeRFNet, inputs):
+    # ---------------- include_vd=True (view-direction input, models/gaze_nerf.py:70-80): real layer widths, 8x8 rays x 8 samples ----------------
+    opt = BaseOptions({"featmap_size": 8, "featmap_nc": 258, "pred_img_size": 64})
+    opt.num_sample_coarse = 8
+    torch.manual_seed(45)
+    net = GazeNeRFNet(opt, include_vd=True, hier_sampling=False).eval()
+    chk = {"chk/" + k: np.array([float(v.double().sum()), float(v.double().abs().sum())]) for k, v in net.state_dict().items()}
+    shapes = {"shape/" + k: np.array(v.shape, dtype=np.int64) for k, v in net.state_dict().items()}
+    ru, xy, uv, shape, appea, gaze, cam = inputs(opt, 2)
+    # dense density (same recipe as make_dense, with the view-direction input wired in)
+    raw, hooks = {}, []
+    for name, br in (("face", net.fg_CD_predictor_face), ("eyes", net.fg_CD_predictor_eyes)):
+        hooks.append(br.density_module.register_forward_hook(lambda m, i, o, name=name: raw.__setitem__(name, o.detach().clone())))
+    with torch.no_grad():
+        net("test", xy, uv, None, shape, appea, gaze, cam["batch_Rmats"], cam["batch_Tvecs"], cam["batch_inv_inmats"])
+    for h in hooks:
+        h.remove()
+    biases = []
+    with torch.no_grad():
+        for name, br in (("face", net.fg_CD_predictor_face), ("eyes", net.fg_CD_predictor_eyes)):
+            med = float(raw[name].median()) - float(br.density_module.bias[0])
+            br.density_module.weight *= 30.0
+            br.density_module.bias.fill_(-30.0 * med)
+            biases.append(-30.0 * med)
+        # the default init of RGB_layer_1 gives the 27 view-direction columns little weight: scale them so that the test is sensitive to them
+        for br in (net.fg_CD_predictor_face, net.fg_CD_predictor_eyes):
+            br.RGB_layer_1.weight[:, 384:384 + 27] *= 8.0
+    out = {}
+    with torch.no_grad():
+        full = net("test", xy, uv, None, shape, appea, gaze, cam["batch_Rmats"], cam["batch_Tvecs"], cam["batch_inv_inmats"])
+        for k, v in full["coarse_dict"].items():
+            out["img_" + k] = np32(v)
+        smp = net.sample_func(xy, cam["batch_Rmats"], cam["batch_Tvecs"], cam["batch_inv_inmats"], False)
+        pe = net.vp_encoder_face(smp["pts"])
+        vd = net.vd_encoder(smp["dirs"])
+        out["vd_pe"] = np32(vd[:, :, :, 0])
+        n_r, n_s = xy.shape[2], opt.num_sample_coarse
+        ext = torch.cat([shape, gaze], 1)[:, :, None, None].expand(-1, -1, n_r, n_s)
+        app = torch.cat([vd, appea[:, :, None, None].expand(-1, -1, n_r, n_s)], 1)
+        vp = torch.cat([pe, ext], 1)
+        for br, mlp in (("face", net.fg_CD_predictor_face), ("eyes", net.fg_CD_predictor_eyes)):
+            rgb, sig = mlp(vp, app)
+            fr, ba, dep, w = net.calc_color_func(smp["pts"], rgb, sig, smp["z_dists"], smp["zvals"])
+            out["feat_" + br], out["bg_alpha_" + br], out["w_" + br] = np32(fr), np32(ba), np32(w)
+    out["in_xy"], out["in_shape"], out["in_appea"], out["in_gaze"] = np32(xy), np32(shape), np32(appea), np32(gaze)
+    out["in_R"], out["in_T"], out["in_Kinv"] = np32(cam["batch_Rmats"]), np32(cam["batch_Tvecs"]), np32(cam["batch_inv_inmats"])
+    out["meta"] = np.array([8, 258, 64, 8, opt.mlp_hidden_nchannels, 1, 0], dtype=np.int64)
+    out["dense_bias"] = np.array(biases, dtype=np.float64)
+    out["vd_col_scale"] = np.array([8.0])
+    out.update(chk)
+    out.update(shapes)
+    np.savez_compressed(os.path.join(OUT, "std_dense_vd_test.npz"), **out)
+    print("std_dense_vd_test", sum(v.nbytes for v in out.values()) // 1024, "KiB raw")
 
 
 if __name__ == "__main__":

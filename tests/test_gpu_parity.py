@@ -463,3 +463,55 @@ def test_graphed_forward_matches_eager(dev):
         net.neural_render.bg_featmap.mul_(0.9)
     with pytest.raises(RuntimeError):
         gf(**kw2)
+
+
+def test_include_vd_forward_vs_reference_golden_and_oracle(dev):
+    """GazeNeRFNet(include_vd=True): the 27-channel view-direction encoding (models/gaze_nerf.py:70-80,140-141) as a per-ray bias of the
+    fused kernel's last stage, against the reference's own include_vd=True outputs (8x8 rays) and against the oracle at 16x16x64."""
+    from test_oracle_golden import _vd_state_dict
+    g = load_golden("std_dense_vd_test")
+    net, sd = _vd_state_dict(g)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+    net.keep_stages = True
+    with torch.no_grad():
+        out = net("test", **_inputs(g, dev))
+    st = net.last_stages
+    for br in ("face", "eyes"):
+        assert rel_l2(st["feat_" + br].cpu(), g["feat_" + br]) < TOL_TIGHT, br
+        assert max_rel(st["bg_alpha_" + br].cpu(), g["bg_alpha_" + br][:, 0]) < TOL_TIGHT, br
+    for k in ("merge_img_face", "merge_img_eyes", "merge_img", "bg_img"):
+        assert float((out["coarse_dict"][k].cpu() - torch.from_numpy(g["img_" + k])).abs().max()) < TOL_TIGHT, k
+    with pytest.raises(NotImplementedError):
+        net("train", **{k: (v.requires_grad_(True) if k == "shape_code" else v) for k, v in _inputs(g, dev).items()})
+    # mid size (two rays per tile, orbit cameras) vs the oracle
+    opt = G.BaseOptions({"featmap_size": 16, "featmap_nc": 258, "pred_img_size": 64})
+    opt.num_sample_coarse = 64
+    torch.manual_seed(45)
+    net2 = G.GazeNeRFNet(opt, include_vd=True, hier_sampling=False)
+    ru = G.RenderUtils(45, "cpu", opt)
+    shape, appea, gaze = O.synthetic_codes(2)
+    cams = [ru.cam_info_list[3], ru.cam_info_list[20]]
+    cam = {k: torch.cat([c[k] for c in cams], 0) for k in cams[0]}
+    xy = ru.ray_xy.expand(2, -1, -1)
+    sd2 = {k: v.clone() for k, v in net2.state_dict().items()}
+    for br in ("face", "eyes"):
+        k = "fg_CD_predictor_%s." % br
+        sd2[k + "density_module.weight"] = sd2[k + "density_module.weight"] * 4.0
+        w = sd2[k + "RGB_layer_1.weight"].clone()
+        w[:, 384:411] *= 8.0
+        sd2[k + "RGB_layer_1.weight"] = w
+    net2.load_state_dict(sd2)
+    oo = O.OracleOptions(featmap_size=16, featmap_nc=258, pred_img_size=64, num_sample_coarse=64)
+    with torch.no_grad():
+        ref = O.forward(sd2, oo, "test", xy, shape, appea, gaze, cam["batch_Rmats"], cam["batch_Tvecs"], cam["batch_inv_inmats"], return_stages=True,
+                        include_vd=True)
+    net2 = net2.to(dev).eval()
+    net2.keep_stages = True
+    with torch.no_grad():
+        out2 = net2("test", batch_xy=xy.to(dev), batch_uv=None, bg_code=None, shape_code=shape.to(dev), appea_code=appea.to(dev), gaze_code=gaze.to(dev),
+                    **{k: v.to(dev) for k, v in cam.items()})
+    for br in ("face", "eyes"):
+        assert rel_l2(net2.last_stages["feat_" + br].cpu().view(2, 258, 16, 16), ref["stages"]["feat_" + br]) < TOL_TIGHT, br
+    for k, v in ref["coarse_dict"].items():
+        assert float((out2["coarse_dict"][k].cpu() - v).abs().max()) < TOL_TIGHT, k

@@ -165,3 +165,47 @@ def test_mid_size_reference_golden_16x16x64():
     assert np.array_equal(fs["zvals"].numpy(), g["fine_zvals"])
     assert fs["zvals"].shape[-1] == 64 + 64
     assert 0.1 < float(g["bg_alpha_face"].mean()) < 0.9   # non-vacuous
+
+
+def _vd_state_dict(g):
+    """Weights of the include_vd fixture: the drop-in module's seeded init (checksums + shapes stored) + the fixture's dense variant."""
+    import gazenerf_b200 as G
+    opt = G.BaseOptions({"featmap_size": 8, "featmap_nc": 258, "pred_img_size": 64})
+    opt.num_sample_coarse = 8
+    torch.manual_seed(45)
+    net = G.GazeNeRFNet(opt, include_vd=True, hier_sampling=False)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(g["shape/" + k]), k          # state_dict shapes of the reference's include_vd=True network
+        chk = g["chk/" + k]
+        assert abs(float(v.double().sum()) - chk[0]) <= 1e-9 * max(1.0, abs(chk[1])), k
+    sd = O.densify(sd, *g["dense_bias"])
+    for br in ("face", "eyes"):
+        k = "fg_CD_predictor_%s.RGB_layer_1.weight" % br
+        w = sd[k].clone()
+        w[:, 384:384 + 27] *= float(g["vd_col_scale"][0])
+        sd[k] = w
+    return net, sd
+
+
+def test_include_vd_reference_golden():
+    """include_vd=True (models/gaze_nerf.py:70-80,140-141): the oracle with the 27-channel view-direction encoding against the
+    reference's own outputs; the drop-in module reproduces the reference's parameter shapes (RGB_layer_1: 192 x 538) and seeded init."""
+    g = load_golden("std_dense_vd_test")
+    opt = _opt(g["meta"])
+    net, sd = _vd_state_dict(g)
+    assert sd["fg_CD_predictor_face.RGB_layer_1.weight"].shape == (192, 384 + 27 + 127, 1, 1)
+    xy, shape, appea, gaze, R, T, K = _inputs(g)
+    out = O.forward(sd, opt, "test", xy, shape, appea, gaze, R, T, K, return_stages=True, include_vd=True)
+    st = out["stages"]
+    vd = O.posenc(st["ray_d"].unsqueeze(-1), 4, True)[..., 0]
+    assert np.array_equal(vd.numpy(), g["vd_pe"])
+    for name in ("face", "eyes"):
+        assert rel_l2(st["feat_" + name].reshape(2, 258, -1), g["feat_" + name]) < TOL, name
+        assert max_rel(st["bg_alpha_" + name].reshape(2, 1, -1), g["bg_alpha_" + name]) < 2e-5, name
+    for k in ("merge_img_face", "merge_img_eyes", "merge_img", "bg_img"):
+        assert float((out["coarse_dict"][k] - torch.from_numpy(g["img_" + k])).abs().max()) < 5e-6, k
+    # the view direction matters in this fixture: dropping it changes the features visibly
+    no_vd = {k: (v[:, list(range(384)) + list(range(411, 538))] if k.endswith("RGB_layer_1.weight") else v) for k, v in sd.items()}
+    out0 = O.forward(no_vd, opt, "test", xy, shape, appea, gaze, R, T, K, return_stages=True)
+    assert rel_l2(out0["stages"]["feat_face"].reshape(2, 258, -1), g["feat_face"]) > 1e-3
