@@ -676,7 +676,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const FwdArgs args)
 // =====================================================================================================================
 //  RGB_layer_2 after compositing (fold iv):  feat[b][c][ray] = sum_k W2[c][k] hc[b][ray][k] + b2[c] wsum ; bg_alpha = 1 - wsum
 // =====================================================================================================================
-constexpr int kHeadRays = 32;
+// smem-tiled SGEMM: CTA = 64 rays x 64 output channels, thread = 4 rays x 4 channels, K = 192 in slabs of 16 (double buffered through
+// registers).  M = rays (hc is [ray][192], K contiguous), N = channels (W2^T is [192][258], N contiguous); the stores are float4 along the
+// rays of one channel, i.e. 256 contiguous bytes per half warp of the NCHW-like feature map [B][258][N_r].
+constexpr int kHeadTM = 64, kHeadTN = 64, kHeadBK = 16;
 struct HeadArgs {
   const float* aux[2];
   const float* hc[2];
@@ -684,47 +687,80 @@ struct HeadArgs {
   float* feat_ray[2];
   float* bg_alpha[2];
 };
-// grid (ray tiles, B, n_branch); thread = output channel, 32 rays per CTA; hidden rows staged in smem and read as float4 (4 k per LDS)
-__global__ void __launch_bounds__(288) rgb_head_kernel(const HeadArgs ha, int N_r) {
-  __shared__ __align__(16) float s_h[kHeadRays][kH2 + 4];
-  __shared__ float s_w[kHeadRays];
-  const int br = blockIdx.z;
+__global__ void __launch_bounds__(256) rgb_head_kernel(const HeadArgs ha, int N_r, int n_branch) {
+  __shared__ __align__(16) float As[2][kHeadBK][kHeadTM + 4];   // [k][ray]
+  __shared__ __align__(16) float Bs[2][kHeadBK][kHeadTN];       // [k][channel]
+  const int br = blockIdx.z % n_branch, b = blockIdx.z / n_branch;
   const float* __restrict__ aux = ha.aux[br];
-  const float* __restrict__ hc = ha.hc[br];
-  const float* __restrict__ wsum = ha.wsum[br];
-  const int b = blockIdx.y;
-  const int r0 = blockIdx.x * kHeadRays;
-  const int nr = min(kHeadRays, N_r - r0);
-  for (int i = threadIdx.x; i < kHeadRays * kH2; i += blockDim.x) {
-    int r = i / kH2, k = i - r * kH2;
-    s_h[r][k] = (r < nr) ? hc[((size_t)b * N_r + r0 + r) * kH2 + k] : 0.0f;
-  }
-  for (int i = threadIdx.x; i < kHeadRays; i += blockDim.x) {
-    float w = (i < nr) ? wsum[(size_t)b * N_r + r0 + i] : 0.0f;
-    s_w[i] = w;
-    if (i < nr) ha.bg_alpha[br][(size_t)b * N_r + r0 + i] = 1.0f - w;   // utils/model_utils.py:531-532
-  }
+  const float* __restrict__ hc = ha.hc[br] + (size_t)b * N_r * kH2;
+  const float* __restrict__ wsum = ha.wsum[br] + (size_t)b * N_r;
+  const float* __restrict__ w2t = aux + kAuxW2t;
+  const int r0 = blockIdx.x * kHeadTM, n0 = blockIdx.y * kHeadTN;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  // loaders: A: thread -> (ray = tid / 4, 4 consecutive k = (tid % 4) * 4) one float4; B: 4 scalars (k = tid / 16 [+0], channel = (tid % 16) * 4 + j)
+  const int a_ray = tid >> 2, a_k = (tid & 3) * 4;
+  const int b_k = tid >> 4, b_c = (tid & 15) * 4;
+  float4 a_st;
+  float b_st[4];
+  auto fetch = [&](int k0) {
+    a_st = (r0 + a_ray < N_r) ? __ldg(reinterpret_cast<const float4*>(hc + (size_t)(r0 + a_ray) * kH2 + k0 + a_k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b_st[j] = (n0 + b_c + j < kFeat) ? __ldg(w2t + (size_t)(k0 + b_k) * kFeat + n0 + b_c + j) : 0.0f;
+  };
+  auto commit = [&](int buf) {
+    As[buf][a_k + 0][a_ray] = a_st.x; As[buf][a_k + 1][a_ray] = a_st.y; As[buf][a_k + 2][a_ray] = a_st.z; As[buf][a_k + 3][a_ray] = a_st.w;
+    *reinterpret_cast<float4*>(&Bs[buf][b_k][b_c]) = make_float4(b_st[0], b_st[1], b_st[2], b_st[3]);
+  };
+  float acc[4][4];   // [channel][ray]
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  fetch(0);
+  commit(0);
   __syncthreads();
-  const int c = threadIdx.x;
-  if (c >= kFeat) return;
-  const float* w2t = aux + kAuxW2t;
-  float acc[kHeadRays];
+  constexpr int n_k = kH2 / kHeadBK;   // 12
+  for (int kc = 0; kc < n_k; ++kc) {
+    const int buf = kc & 1;
+    if (kc + 1 < n_k) fetch((kc + 1) * kHeadBK);
 #pragma unroll
-  for (int r = 0; r < kHeadRays; ++r) acc[r] = 0.0f;
-  for (int k = 0; k < kH2; k += 4) {
-    const float w0 = __ldg(w2t + (size_t)(k + 0) * kFeat + c), w1 = __ldg(w2t + (size_t)(k + 1) * kFeat + c);
-    const float w2 = __ldg(w2t + (size_t)(k + 2) * kFeat + c), w3 = __ldg(w2t + (size_t)(k + 3) * kFeat + c);
+    for (int kk = 0; kk < kHeadBK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[buf][kk][tx * 4]);
+      const float4 w = *reinterpret_cast<const float4*>(&Bs[buf][kk][ty * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-    for (int r = 0; r < kHeadRays; ++r) {
-      const float4 h = *reinterpret_cast<const float4*>(&s_h[r][k]);
-      acc[r] = fmaf(w3, h.w, fmaf(w2, h.z, fmaf(w1, h.y, fmaf(w0, h.x, acc[r]))));
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wv[i], av[j], acc[i][j]);
+    }
+    if (kc + 1 < n_k) commit(buf ^ 1);
+    __syncthreads();
+  }
+  const int ray = r0 + tx * 4;
+  if (ray >= N_r) return;
+  float ws[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) ws[j] = (ray + j < N_r) ? __ldg(wsum + ray + j) : 0.0f;
+  if (blockIdx.y == 0 && ty == 0) {   // bg_alpha = 1 - sum_k w_k   (utils/model_utils.py:531-532)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (ray + j < N_r) ha.bg_alpha[br][(size_t)b * N_r + ray + j] = 1.0f - ws[j];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = n0 + ty * 4 + i;
+    if (c >= kFeat) continue;
+    const float b2 = __ldg(aux + kAuxB2 + c);
+    float* dst = ha.feat_ray[br] + ((size_t)b * kFeat + c) * N_r + ray;
+    const float v[4] = {fmaf(b2, ws[0], acc[i][0]), fmaf(b2, ws[1], acc[i][1]), fmaf(b2, ws[2], acc[i][2]), fmaf(b2, ws[3], acc[i][3])};
+    if (ray + 3 < N_r && (N_r & 3) == 0) {
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (ray + j < N_r) dst[j] = v[j];
     }
   }
-  const float b2 = __ldg(aux + kAuxB2 + c);
-  float* dst = ha.feat_ray[br] + ((size_t)b * kFeat + c) * N_r + r0;
-#pragma unroll
-  for (int r = 0; r < kHeadRays; ++r)
-    if (r < nr) dst[r] = fmaf(b2, s_w[r], acc[r]);
 }
 
 // =====================================================================================================================
@@ -1070,8 +1106,8 @@ static int mlp_tc_fwd_impl(int n_branch, const void* const* packed, const float*
       ha.feat_ray[i] = feat_ray[j];
       ha.bg_alpha[i] = bg_alpha[j];
     }
-    dim3 g(ceil_div(N_r, kHeadRays), B, n_branch);
-    rgb_head_kernel<<<g, 288, 0, st>>>(ha, N_r);
+    dim3 g(ceil_div(N_r, kHeadTM), ceil_div(kFeat, kHeadTN), B * n_branch);   // blockIdx.z = face * n_branch + branch
+    rgb_head_kernel<<<g, 256, 0, st>>>(ha, N_r, n_branch);
   }
   GNRF_LAUNCH_CHECK();
   count_launches(2);

@@ -401,8 +401,14 @@ static int nr_forward_fused(const float* const* params, const unsigned char* fpa
   int n_sm = 0;
   {
     int rc = device_once(kOnceNrFused, &n_sm, []() -> int {
-      GNRF_CUDA(cudaFuncSetAttribute(nrf::nrf_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nrf::kSmemBudget));
-      GNRF_CUDA(cudaFuncSetAttribute(nrf::nrf_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nrf::kSmemBudget));
+      GNRF_CUDA(cudaFuncSetAttribute(nrf::nrf_a_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, nrf::kSmemBudget));
+      GNRF_CUDA(cudaFuncSetAttribute(nrf::nrf_a_kernel<258, 129>, cudaFuncAttributeMaxDynamicSharedMemorySize, nrf::kSmemBudget));
+      GNRF_CUDA(cudaFuncSetAttribute(nrf::nrf_a_kernel<129, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, nrf::kSmemBudget));
+      GNRF_CUDA(cudaFuncSetAttribute(nrf::nrf_a_kernel<64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, nrf::kSmemBudget));
+      GNRF_CUDA(cudaFuncSetAttribute(nrf::nrf_b_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, nrf::kSmemBudget));
+      GNRF_CUDA(cudaFuncSetAttribute(nrf::nrf_b_kernel<258, 129>, cudaFuncAttributeMaxDynamicSharedMemorySize, nrf::kSmemBudget));
+      GNRF_CUDA(cudaFuncSetAttribute(nrf::nrf_b_kernel<129, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, nrf::kSmemBudget));
+      GNRF_CUDA(cudaFuncSetAttribute(nrf::nrf_b_kernel<64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, nrf::kSmemBudget));
       return GNRF_OK;
     });
     if (rc != GNRF_OK) return rc;
@@ -427,7 +433,11 @@ static int nr_forward_fused(const float* const* params, const unsigned char* fpa
     a.rgb_prev = i == 0 ? nullptr : rgb[(i - 1) & 1];
     a.ci = ci; a.co = co; a.H = s; a.W = s; a.n_img = N;
     // >= 120 KB of dynamic smem per CTA: one CTA per SM, so its 512-column TMEM allocation never waits for a neighbour
-    nrf::nrf_a_kernel<<<min(n_tiles, n_sm), nrf::kAThreads, max(nrf::nrf_a_smem_bytes(g), 120 * 1024), st>>>(a);
+    const int ga = min(n_tiles, n_sm), sa = max(nrf::nrf_a_smem_bytes(g), 120 * 1024);
+    if (ci == 258 && co == 129) nrf::nrf_a_kernel<258, 129><<<ga, nrf::kAThreads, sa, st>>>(a);
+    else if (ci == 129 && co == 64) nrf::nrf_a_kernel<129, 64><<<ga, nrf::kAThreads, sa, st>>>(a);
+    else if (ci == 64 && co == 32) nrf::nrf_a_kernel<64, 32><<<ga, nrf::kAThreads, sa, st>>>(a);
+    else nrf::nrf_a_kernel<0, 0><<<ga, nrf::kAThreads, sa, st>>>(a);
     nrf::BArgs b;
     b.t1 = t1;
     b.pack = fpack;
@@ -435,7 +445,11 @@ static int nr_forward_fused(const float* const* params, const unsigned char* fpa
     b.pre = pre[i & 1];
     b.ci = ci; b.co = co; b.H = s; b.W = s; b.n_img = N;
     const int n_items = n_tiles * (4 / g.qg);
-    nrf::nrf_b_kernel<<<min(n_items, n_sm), nrf::kBThreads, max(nrf::nrf_b_smem_bytes(g), 120 * 1024), st>>>(b);
+    const int gb = min(n_items, n_sm), sb = max(nrf::nrf_b_smem_bytes(g), 120 * 1024);
+    if (ci == 258 && co == 129) nrf::nrf_b_kernel<258, 129><<<gb, nrf::kBThreads, sb, st>>>(b);
+    else if (ci == 129 && co == 64) nrf::nrf_b_kernel<129, 64><<<gb, nrf::kBThreads, sb, st>>>(b);
+    else if (ci == 64 && co == 32) nrf::nrf_b_kernel<64, 32><<<gb, nrf::kBThreads, sb, st>>>(b);
+    else nrf::nrf_b_kernel<0, 0><<<gb, nrf::kBThreads, sb, st>>>(b);
     GNRF_LAUNCH_CHECK();
     count_launches(2);
     fpack += nrf::level_pack(g).total;

@@ -289,10 +289,16 @@ __global__ void ub_kernel(const float* __restrict__ in, int H, int W, float* __r
   out[(size_t)blockIdx.y * n + i] = up2_blur_at(in + (size_t)blockIdx.y * H * W, H, W, Y, X);
 }
 
-__global__ void __launch_bounds__(kAThreads, 1) nrf_a_kernel(const AArgs args) {
+// CI > 0: the level's channel counts are compile-time constants (the reference configuration 258 / 129 / 64): every division and
+// modulo of the index math and the whole geometry fold away (the kernels are partly issue-bound: 35-50 K warp instructions per tile);
+// CI == 0: generic, geometry from the arguments.
+template <int CI, int CO>
+__global__ void __launch_bounds__(kAThreads, 1) nrf_a_kernel(const AArgs args_in) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  AArgs args = args_in;
+  if (CI > 0) { args.ci = CI; args.co = CO; }
   const LevelGeom g = level_geom(args.ci, args.co);
   const LevelPack lp = level_pack(g);
   const int a_bytes = g.k1_steps * kStepBytes;                     // one x tile
@@ -632,10 +638,13 @@ static inline bool level_supported(const LevelGeom& g) {
   return true;
 }
 
-__global__ void __launch_bounds__(kBThreads, 1) nrf_b_kernel(const BArgs args) {
+template <int CI, int CO>
+__global__ void __launch_bounds__(kBThreads, 1) nrf_b_kernel(const BArgs args_in) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  BArgs args = args_in;
+  if (CI > 0) { args.ci = CI; args.co = CO; }
   const LevelGeom g = level_geom(args.ci, args.co);
   const LevelPack lp = level_pack(g);
   const int kBAStages = nrf_b_a_stages(g), kBBStages = nrf_b_b_stages(g);

@@ -31,9 +31,10 @@ class _DataLossFn(torch.autograd.Function):
         terms = torch.empty(5, device=dev)
         sums = torch.empty(9, device=dev)
         ws = torch.empty(L.gnrf_data_loss_workspace_floats(), device=dev)
-        st = torch.cuda.current_stream().cuda_stream
-        _lib.check(L.gnrf_data_loss_fwd(*[t.data_ptr() for t in ins], B, H * W, 1 if use_l1 else 0, float(bg_value), terms.data_ptr(),
-                                        sums.data_ptr(), ws.data_ptr(), st), "gnrf_data_loss_fwd")
+        with torch.cuda.device(dev):   # the launch goes to the tensors' device and ITS current stream
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(L.gnrf_data_loss_fwd(*[t.data_ptr() for t in ins], B, H * W, 1 if use_l1 else 0, float(bg_value), terms.data_ptr(),
+                                            sums.data_ptr(), ws.data_ptr(), st), "gnrf_data_loss_fwd")
         ctx.ins, ctx.sums, ctx.cfg = ins, sums, (B, H * W, 1 if use_l1 else 0, float(bg_value))
         return terms
 
@@ -44,9 +45,10 @@ class _DataLossFn(torch.autograd.Function):
         B, HW, use_l1, bg_value = ctx.cfg
         g = [torch.empty_like(ins[0]), torch.empty_like(ins[1]), torch.empty_like(ins[2]), torch.empty_like(ins[3])]
         gt_ = g_terms.detach().float().contiguous()
-        st = torch.cuda.current_stream().cuda_stream
-        _lib.check(L.gnrf_data_loss_bwd(*[t.data_ptr() for t in ins], B, HW, use_l1, bg_value, sums.data_ptr(), gt_.data_ptr(),
-                                        *[t.data_ptr() for t in g], st), "gnrf_data_loss_bwd")
+        with torch.cuda.device(ins[0].device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(L.gnrf_data_loss_bwd(*[t.data_ptr() for t in ins], B, HW, use_l1, bg_value, sums.data_ptr(), gt_.data_ptr(),
+                                            *[t.data_ptr() for t in g], st), "gnrf_data_loss_bwd")
         return g[0], g[1], g[2], g[3], None, None, None, None, None, None, None
 
 

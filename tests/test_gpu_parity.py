@@ -515,3 +515,34 @@ def test_include_vd_forward_vs_reference_golden_and_oracle(dev):
         assert rel_l2(net2.last_stages["feat_" + br].cpu().view(2, 258, 16, 16), ref["stages"]["feat_" + br]) < TOL_TIGHT, br
     for k, v in ref["coarse_dict"].items():
         assert float((out2["coarse_dict"][k].cpu() - v).abs().max()) < TOL_TIGHT, k
+
+
+def test_abi_reentrant_across_streams_and_devices(dev):
+    """include/gnrf.h: no device-global tables, no process-wide `static` device state.  Packing + forward issued on two user streams at
+    once, and (with >= 2 GPUs) the FIRST use of the library on a second device after the first device has been initialised, must
+    reproduce the default-stream result bit for bit."""
+    g = load_golden("std_dense_test")
+    opt, net = _net_from_golden(g, dev, "tc")
+    kw = _inputs(g, dev)
+    with torch.no_grad():
+        ref = {k: v.clone() for k, v in net("test", **kw)["coarse_dict"].items()}
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = []
+    for s in streams:                       # both streams re-pack (fresh caches) and run concurrently
+        net.invalidate_caches()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s), torch.no_grad():
+            outs.append({k: v.clone() for k, v in net("test", **kw)["coarse_dict"].items()})
+    torch.cuda.synchronize()
+    for o in outs:
+        for k in ref:
+            assert torch.equal(o[k], ref[k]), k
+    if torch.cuda.device_count() >= 2:
+        dev1 = torch.device("cuda:1")
+        opt1, net1 = _net_from_golden(g, dev1, "tc")
+        with torch.cuda.device(dev1), torch.no_grad():
+            out1 = net1("test", **_inputs(g, dev1))["coarse_dict"]
+            tr = net1.neural_render   # training forward kernels (conv_tc / wgrad opt-ins) on the second device, too
+        for k in ref:
+            assert torch.equal(out1[k].cpu(), ref[k].cpu()), k
