@@ -179,7 +179,7 @@ __device__ __forceinline__ void multimem_st_v4(float* addr, float a, float b, fl
 // so LeakyReLU(conv(Blur(x))) == LeakyReLU(Blur(conv(x)))  (neural_renderer.py:103-106, pixel_shuffle_upsample.py:7-16, 41).
 // One thread = 4 consecutive x of one row, all channels (float4 loads/stores; edge taps come from the neighbours' cache lines).
 // rgb_coarse (optional, instead of rgb_prev): the running RGB one level down [N][3][H/2][Wd/2]; its Blur(up2(.)) is formed here.
-__global__ void __launch_bounds__(256) blur_lrelu_rgb_kernel(const float* __restrict__ pre, int C, int H, int Wd,
+__global__ void __launch_bounds__(256, 3) blur_lrelu_rgb_kernel(const float* __restrict__ pre, int C, int H, int Wd,
                                                             const float* __restrict__ rgb_w, const float* __restrict__ rgb_b,
                                                             const float* __restrict__ rgb_prev, int do_sigmoid,
                                                             float* __restrict__ net, float* __restrict__ rgb, const GatherDst gd,
@@ -202,6 +202,34 @@ __global__ void __launch_bounds__(256) blur_lrelu_rgb_kernel(const float* __rest
   for (int j = 0; j < 3; ++j)
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[j][i] = 0.0f;
+  if (rgb_coarse != nullptr) {
+    // Blur(up2(R)) of the running RGB at this thread's 4 pixels, requested up front (its scattered loads overlap the channel loop);
+    // the accumulators start from it.  One set of row weights, four sets of column weights.
+    int iy[3], ix[3];
+    float wy[3], wx[3];
+    nrf::ub_axis(y, H >> 1, iy, wy);
+    const int Wc = Wd >> 1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      nrf::ub_axis(x0 + i, Wc, ix, wx);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float* cp = rgb_coarse + ((size_t)n * 3 + j) * (HW >> 2);
+        float v = 0.0f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float* row = cp + (size_t)iy[a] * Wc;
+          v += wy[a] * (wx[0] * __ldg(row + ix[0]) + wx[1] * __ldg(row + ix[1]) + wx[2] * __ldg(row + ix[2]));
+        }
+        acc[j][i] = v;
+      }
+    }
+  }
+  // whole-warp rows (Wd a multiple of 128): a warp holds 128 consecutive x of one row, so the outer columns x0-1 / x0+4 of a thread are
+  // its neighbour lanes' inner columns (shuffles); only lanes 0 / 31 fetch theirs (one unconditional 3-row load at a per-lane column)
+  const bool warp_rows = (W4 & 31) == 0;
+  const int lane = threadIdx.x & 31;
+  const int xe = warp_rows ? (lane == 0 ? xl : (lane == 31 ? xr : x0)) : 0;
 #pragma unroll 4
   for (int c = 0; c < C; ++c) {
     const float* pc = pl + (size_t)c * HW;
@@ -212,8 +240,16 @@ __global__ void __launch_bounds__(256) blur_lrelu_rgb_kernel(const float* __rest
       const float4 d = *reinterpret_cast<const float4*>(pc + (size_t)yp * Wd + x0);
       col[1] = a.x + 2.0f * b.x + d.x; col[2] = a.y + 2.0f * b.y + d.y;
       col[3] = a.z + 2.0f * b.z + d.z; col[4] = a.w + 2.0f * b.w + d.w;
-      col[0] = pc[(size_t)ym * Wd + xl] + 2.0f * pc[(size_t)y * Wd + xl] + pc[(size_t)yp * Wd + xl];
-      col[5] = pc[(size_t)ym * Wd + xr] + 2.0f * pc[(size_t)y * Wd + xr] + pc[(size_t)yp * Wd + xr];
+      if (warp_rows) {
+        const float e = pc[(size_t)ym * Wd + xe] + 2.0f * pc[(size_t)y * Wd + xe] + pc[(size_t)yp * Wd + xe];
+        col[0] = __shfl_up_sync(0xffffffffu, col[4], 1);
+        col[5] = __shfl_down_sync(0xffffffffu, col[1], 1);
+        if (lane == 0) col[0] = e;
+        if (lane == 31) col[5] = e;
+      } else {
+        col[0] = pc[(size_t)ym * Wd + xl] + 2.0f * pc[(size_t)y * Wd + xl] + pc[(size_t)yp * Wd + xl];
+        col[5] = pc[(size_t)ym * Wd + xr] + 2.0f * pc[(size_t)y * Wd + xr] + pc[(size_t)yp * Wd + xr];
+      }
     }
     float o[4];
 #pragma unroll
@@ -236,10 +272,6 @@ __global__ void __launch_bounds__(256) blur_lrelu_rgb_kernel(const float* __rest
     if (rgb_prev != nullptr) {
       const float4 pr = *reinterpret_cast<const float4*>(rgb_prev + o);
       v[0] += pr.x; v[1] += pr.y; v[2] += pr.z; v[3] += pr.w;
-    } else if (rgb_coarse != nullptr) {
-      const float* cp = rgb_coarse + ((size_t)n * 3 + j) * (HW >> 2);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] += nrf::up2_blur_at(cp, H >> 1, Wd >> 1, y, x0 + i);
     }
     if (do_sigmoid) {
 #pragma unroll
