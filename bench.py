@@ -537,9 +537,32 @@ def run_render(env, args, steps, warmup, F, workload="render", with_e2e=True):
             if packed is not None:
                 h2d = packed.numel() * packed.element_size()
 
-            def e2e_step(i):
+            # ... and that copy is issued one step AHEAD on its own stream into one of two device staging buffers (the step then starts
+            # with a 34 KB device-to-device copy), so the PCIe read of step i+1's inputs never sits on the critical path behind the
+            # 12.6 MB D2H burst of step i.  Every step's inputs still cross PCIe inside the timed region (the first timed step copies
+            # its own inputs at its start).
+            in_stream = torch.cuda.Stream(device=dev)
+            in_stage = [torch.empty_like(graphed.flat_input) for _ in range(2)] if packed is not None else None
+            in_ready, in_read = [None, None], [None, None]   # H2D into the staging buffer done / its last D2D read done
+
+            def prefetch_inputs(i):
+                with torch.cuda.stream(in_stream):
+                    if in_read[i & 1] is not None:
+                        in_stream.wait_event(in_read[i & 1])   # step i-2's D2D read of this staging buffer (long complete)
+                    in_stage[i & 1].copy_(packed, non_blocking=True)
+                    ev_in = torch.cuda.Event()
+                    ev_in.record(in_stream)
+                in_ready[i & 1] = ev_in
+
+            def e2e_step(i, last=False):
                 if packed is not None:
-                    graphed.flat_input.copy_(packed, non_blocking=True)
+                    if in_ready[i & 1] is None:
+                        prefetch_inputs(i)
+                    main_stream.wait_event(in_ready[i & 1])
+                    graphed.flat_input.copy_(in_stage[i & 1], non_blocking=True)
+                    in_read[i & 1] = torch.cuda.Event()
+                    in_read[i & 1].record(main_stream)
+                    in_ready[i & 1] = None
                     kw = {}
                 else:
                     kw = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in pinned.items()}
@@ -547,6 +570,8 @@ def run_render(env, args, steps, warmup, F, workload="render", with_e2e=True):
                 # they cannot pass it before I enter it -> my D2H of step i-2 must be complete before I enter the barrier of step i
                 # (two whole steps of slack: this wait never blocks in practice)
                 out = step(kw, pre_finish=(lambda: main_stream.wait_event(copied[0])) if (peer is not None and copied[0] is not None) else None)
+                if packed is not None and not last:
+                    prefetch_inputs(i + 1)
                 if graphed is not None and peer is None:
                     # the graph's static outputs are overwritten by the next replay: stage them (D2D, 12.6 MB) into one of two device
                     # buffers whose previous D2H has completed
@@ -571,11 +596,11 @@ def run_render(env, args, steps, warmup, F, workload="render", with_e2e=True):
                 stage_free[i & 1] = ev_c
 
             for i in range(2):
-                e2e_step(i)
+                e2e_step(i, last=(i == 1))
             env.barrier()
             t0 = time.perf_counter()
             for i in range(steps):
-                e2e_step(i)
+                e2e_step(i, last=(i == steps - 1))
             env.barrier()
             e2e_s = env.max_over_ranks(time.perf_counter() - t0)
             e2e = {"value": world * F * steps / e2e_s, "unit": "faces/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
