@@ -249,7 +249,7 @@ def synthetic_targets(torch, faces, size, seed, device="cpu"):
     return {"gt": gt, "head": head, "left_eye": le, "right_eye": re, "full_eye": ((le + re) > 0).float()}
 
 
-def run_train(env, steps, warmup, F, with_e2e=True, graph=True):
+def run_train(env, steps, warmup, F, with_e2e=True, graph=True, precision="bf16x3"):
     torch, G, dev, world, rank = env.torch, env.G, env.dev, env.world, env.rank
     L = G.lib()
     opt = G.BaseOptions()
@@ -258,6 +258,7 @@ def run_train(env, steps, warmup, F, with_e2e=True, graph=True):
     from gazenerf_b200.trainer_utils import build_code_and_cam
 
     net = G.GazeNeRFNet(opt, include_vd=False, hier_sampling=False).to(dev).train()
+    net.train_precision = precision
     # the reference's fitting step (trainer/gazenerf_trainer.py:338-528): learnable code offsets + camera deltas next to the network
     off = {"iden": torch.zeros(F, 100, device=dev, requires_grad=True), "expr": torch.zeros(F, 79, device=dev, requires_grad=True),
            "appea": torch.zeros(F, 127, device=dev, requires_grad=True)}
@@ -369,13 +370,17 @@ def run_train(env, steps, warmup, F, with_e2e=True, graph=True):
         "metric": "train faces/s (512x512, 64 samp/ray; forward + loss + backward + Adam)", "value": faces_total / (total_ms * 1e-3),
         "unit": "faces/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16x3 split (fp32 accumulate) on tensor cores for every GEMM (forward, dX, dW); f32 elsewhere", "data": "synthetic",
+        "dtype": {"bf16x3": "bf16x3 split (fp32 accumulate) on tensor cores for every GEMM (forward, dX, dW): per-point activations stored pre-split as bf16 hi/lo planes; f32 elsewhere",
+                  "bf16": "single-pass bf16 (fp32 accumulate) for the per-point MLP GEMMs on one bf16 activation plane; bf16x3 for the neural renderer; f32 elsewhere",
+                  "f32": "bf16x3 split (fp32 accumulate) on tensor cores for every GEMM, fp32 activations re-split in-kernel (r1 path); f32 elsewhere"}[precision],
+        "data": "synthetic",
         "config": {"workload": "config[4]: full train step (trainer perform_fitting): build_code_and_cam -> two-branch render + neural renderer -> GazeNeRFLoss (l1, no VGG) -> backward to weights, code offsets, camera deltas -> Adam",
                    "faces_per_gpu_per_step": F, "rays": N_RAYS, "samples_per_ray": 64, "l2": "256 MiB memset between timed steps (untimed)",
                    "launch": graph_note,
                    "multi_gpu": "data parallel, one flat gradient all-reduce per step" if world > 1 else "single GPU",
-                   "precision_note": "config[4] allows bf16; this path keeps the bf16x3 split so gradients match fp32 autograd to 5e-3"},
-        "roofline": {"bound": "tensor", "kernel": "whole step (conv_tc_kernel forward/dX + wgrad_tc_kernel dW dominate)", "achieved": achieved,
+                   "train_precision": precision,
+                   "precision_note": "config[4] names bf16; the default keeps the bf16x3 split so gradients match fp32 autograd to 5e-3 (--train-precision bf16 = single pass, tolerance in tests/test_train_grad.py)"},
+        "roofline": {"bound": "tensor", "kernel": "whole step (lin_hl_kernel forward/dX + wgrad_hl_kernel dW of the radiance MLPs, conv_tc / wgrad_tc of the neural renderer)", "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": "%s bf16 dense, sustained" % peaks["src"],
                      "traffic": None, "algorithmic_flop_per_step": algo_flop,
                      "note": "MLP GEMM FLOPs as written in the reference, x3 for forward + both gradients; step time, not kernel time"},
@@ -670,6 +675,8 @@ def main():
     ap.add_argument("--workload", default="render", choices=["render", "train", "hier", "c0"])
     ap.add_argument("--no-graph", action="store_true", help="render workloads: eager launches instead of replaying the forward (incl. the fused "
                     "all-gather at N > 1) from a captured CUDA graph (net.graphed)")
+    ap.add_argument("--train-precision", default="bf16x3", choices=["bf16x3", "bf16", "f32"],
+                    help="train workload: storage of the per-point MLP activations (gazenerf_b200/train.py)")
     ap.add_argument("--no-train-graph", action="store_true", help="train workload: eager launches instead of the captured step (GraphedTrainStep)")
     args = ap.parse_args()
     if args.workload == "train" and args.faces_per_gpu == 1:
@@ -700,7 +707,7 @@ def main():
     env = Env(torch, G, rank, local_rank, world, dev, dist)
 
     if args.workload == "train":
-        line = run_train(env, args.steps, args.warmup, args.faces_per_gpu, graph=not args.no_train_graph)
+        line = run_train(env, args.steps, args.warmup, args.faces_per_gpu, graph=not args.no_train_graph, precision=args.train_precision)
     else:
         line = run_render(env, args, args.steps, args.warmup, args.faces_per_gpu, workload=args.workload)
         if args.workload == "render" and world == 1 and not args.no_aux and args.mlp_impl == "tc":

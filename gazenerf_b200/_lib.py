@@ -18,7 +18,7 @@ CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(_ROOT, "include")
 LIB_PATH = os.path.join(_HERE, "libgnrf.so")
 
-SOURCES = ["abi.cu", "geometry.cu", "mlp_simt.cu", "mlp_tc.cu", "compose.cu", "neural_render.cu", "conv_tc.cu", "wgrad_tc.cu",
+SOURCES = ["abi.cu", "geometry.cu", "mlp_simt.cu", "mlp_tc.cu", "compose.cu", "neural_render.cu", "conv_tc.cu", "wgrad_tc.cu", "lin_hl.cu",
            "train_ops.cu", "nr_train.cu", "loss.cu", "data.cu"]
 
 NVCC_FLAGS = [
@@ -42,6 +42,8 @@ SYMBOLS = [
     # training path
     "gnrf_conv_tc_packed_bytes", "gnrf_conv_tc_pack", "gnrf_conv_tc", "gnrf_wgrad_tc_workspace_bytes", "gnrf_wgrad_tc",
     "gnrf_pe_fwd", "gnrf_pe_bwd", "gnrf_composite_cm_fwd", "gnrf_composite_cm_bwd", "gnrf_geom_bwd",
+    "gnrf_lin_hl_packed_bytes", "gnrf_lin_hl_pack", "gnrf_lin_hl", "gnrf_wgrad_hl_workspace_bytes", "gnrf_wgrad_hl", "gnrf_pe_fwd_hl",
+    "gnrf_composite_cm_bwd_hl",
     "gnrf_compose_bwd_blocks", "gnrf_compose_bwd",
     "gnrf_nr_train_saved_bytes", "gnrf_nr_train_fwd", "gnrf_nr_train_bwd_workspace_bytes", "gnrf_nr_train_bwd",
     "gnrf_data_loss_workspace_floats", "gnrf_data_loss_fwd", "gnrf_data_loss_bwd",
@@ -162,6 +164,16 @@ def lib() -> ctypes.CDLL:
     L.gnrf_wgrad_tc_workspace_bytes.argtypes = [i32, i32, i32, i32]
     L.gnrf_wgrad_tc.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, vp, vp, i32, i32, vp, sz, vp]
     L.gnrf_pe_fwd.argtypes = [vp, vp, vp, i32, i32, i32, vp, i64, vp]
+    L.gnrf_pe_fwd_hl.argtypes = [vp, vp, vp, i32, i32, i32, vp, i64, vp, i64, i64, i32, vp]
+    L.gnrf_lin_hl_packed_bytes.restype = sz
+    L.gnrf_lin_hl_packed_bytes.argtypes = [i32, i32, i32]
+    L.gnrf_lin_hl_pack.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+    L.gnrf_lin_hl.argtypes = [vp, i32, i32, i32, vp, i64, i64, vp, i32, vp, i64, i64, i32, vp, i64, vp, i64, i32, i32, i32, vp]
+    L.gnrf_wgrad_hl_workspace_bytes.restype = sz
+    L.gnrf_wgrad_hl_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    L.gnrf_wgrad_hl.argtypes = [vp, i64, i64, vp, i64, i64, i32, i32, i32, i32, i32, vp, vp, i32, vp, sz, vp]
+    L.gnrf_composite_cm_bwd_hl.argtypes = [vp, vp, vp, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32, vp, i64, i64, vp, i64, i64, i32, vp,
+                                           vp, vp]
     L.gnrf_pe_bwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i32, i32, i32, vp, vp, vp, vp]
     L.gnrf_composite_cm_fwd.argtypes = [vp, i64, vp, i64, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     L.gnrf_composite_cm_bwd.argtypes = [vp, vp, vp, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32, vp, i64, vp, i64, vp, vp, vp]

@@ -48,7 +48,8 @@ static inline int device_once(int key, int* n_sm, F&& init) {
   device_once_end(key, dev, rc == GNRF_OK);
   return rc;
 }
-enum { kOnceMlpTc = 0, kOnceMlpSimt = 1, kOnceConvTc = 2, kOnceWgradTc = 3, kOnceNrFused = 4, kOnceMlpTrain = 5 };
+enum { kOnceMlpTc = 0, kOnceMlpSimt = 1, kOnceConvTc = 2, kOnceWgradTc = 3, kOnceNrFused = 4, kOnceMlpTrain = 5, kOnceLinHl2 = 6,
+       kOnceLinHl1 = 7, kOnceWgHl2 = 8, kOnceWgHl1 = 9, kOnceLinHlSm = 10 };
 
 static inline cudaStream_t as_stream(gnrf_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

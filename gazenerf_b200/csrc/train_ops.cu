@@ -7,14 +7,24 @@
 // (CalcRayColor), :11-46 (rotation), models/gaze_nerf.py:175-203 (compose), models/pixel_shuffle_upsample.py:7-42,
 // models/neural_renderer.py:98-113.  The reference obtains these gradients from torch autograd; tests compare against autograd of
 // the CPU oracle.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace gnrf {
 
 // ------------------------------------------------------------------------------------------------- positional encoding
 // pe[b][c][pt], pt = ray * N_s + k, c in [0,63): same op order as the inference kernels (pts = o + ((d*l)*z), accurate sincosf).
+// hl (nullable): the same values as bf16 planes hi = bf16(x), lo = bf16(x - hi) for the pre-split GEMM kernels (lin_hl.cu).
+__device__ __forceinline__ void st_planes(__nv_bfloat16* hl, long long plane_stride, int planes, size_t idx, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hl[idx] = h;
+  if (planes == 2) hl[(size_t)plane_stride + idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
 __global__ void pe_cm_fwd_kernel(const float4* __restrict__ ray_dl, const float* __restrict__ tvecs, const float* __restrict__ z_edges,
-                                 int B, int N_r, int N_s, float* __restrict__ pe, long long pe_img_stride) {
+                                 int B, int N_r, int N_s, float* __restrict__ pe, long long pe_img_stride,
+                                 __nv_bfloat16* __restrict__ hl, long long hl_img_stride, long long hl_plane_stride, int planes) {
   const long long P = (long long)N_r * N_s;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * 3 * P) return;
@@ -27,7 +37,9 @@ __global__ void pe_cm_fwd_kernel(const float4* __restrict__ ray_dl, const float*
   const float z = z_edges[((size_t)b * N_r + ray) * (N_s + 1) + k];
   const float x = __fadd_rn(tvecs[b * 3 + c], __fmul_rn(__fmul_rn(dc, dl.w), z));
   float* o = pe + (size_t)b * pe_img_stride + pt;
+  __nv_bfloat16* oh = hl ? hl + (size_t)b * hl_img_stride + pt : nullptr;
   o[(size_t)c * P] = x;
+  if (oh) st_planes(oh, hl_plane_stride, planes, (size_t)c * P, x);
   float f = 1.0f;
 #pragma unroll
   for (int q = 0; q < 10; ++q) {
@@ -35,6 +47,10 @@ __global__ void pe_cm_fwd_kernel(const float4* __restrict__ ray_dl, const float*
     sincosf(__fmul_rn(x, f), &sv, &cv);
     o[(size_t)(3 + 6 * q + c) * P] = sv;
     o[(size_t)(6 + 6 * q + c) * P] = cv;
+    if (oh) {
+      st_planes(oh, hl_plane_stride, planes, (size_t)(3 + 6 * q + c) * P, sv);
+      st_planes(oh, hl_plane_stride, planes, (size_t)(6 + 6 * q + c) * P, cv);
+    }
     f *= 2.0f;
   }
 }
@@ -138,12 +154,18 @@ composite_cm_fwd_kernel(const float* __restrict__ h, long long h_stride, const f
 // Backward of the above.  g_Hc [B][C+1][N_r] (row C = gradient of sum_k w_k), g_bg [B][N_r] (nullable).
 //   g_h[b][c][pt] = w_k g_Hc[c] * (h > 0)      (h is a post-ReLU activation: this is the gradient of its PRE-activation)
 //   g_w_k = sum_c g_Hc[c] h[c][k] + g_Hc[C] - g_bg ;  reverse scan -> g_alpha -> g_sigma_raw (ReLU-masked), g_delta -> g_z (+=), g_l (+=)
+// PLANES = 0: fp32 outputs; 1 / 2: g_h and g_sigma are bf16 plane tensors (hi | hi + lo, planes `plane_stride` elements apart).
+template <int PLANES>
 __global__ void __launch_bounds__(256)
 composite_cm_bwd_kernel(const float* __restrict__ g_Hc, const float* __restrict__ g_bg, const float* __restrict__ h, long long h_stride,
                         const float* __restrict__ sigma_raw, long long s_stride, const float* __restrict__ weights,
                         const float* __restrict__ z_edges, const float4* __restrict__ ray_dl, int N_r, int N_s, int C,
-                        float* __restrict__ g_h, long long gh_stride, float* __restrict__ g_sigma, long long gs_stride,
-                        float* __restrict__ g_z, float* __restrict__ g_l) {
+                        void* __restrict__ g_h_v, long long gh_stride, void* __restrict__ g_sigma_v, long long gs_stride,
+                        long long gh_plane_stride, long long gs_plane_stride, float* __restrict__ g_z, float* __restrict__ g_l) {
+  float* g_h = static_cast<float*>(g_h_v);
+  float* g_sigma = static_cast<float*>(g_sigma_v);
+  __nv_bfloat16* g_h_hl = static_cast<__nv_bfloat16*>(g_h_v);
+  __nv_bfloat16* g_sigma_hl = static_cast<__nv_bfloat16*>(g_sigma_v);
   extern __shared__ float sm[];
   float* s_w = sm;                 // [N_s]
   float* s_gw = sm + N_s;          // [N_s]
@@ -158,7 +180,7 @@ composite_cm_bwd_kernel(const float* __restrict__ g_Hc, const float* __restrict_
   for (int i = tid; i < 8 * N_s; i += blockDim.x) s_part[i] = 0.0f;
   __syncthreads();
   const float* hb = h + (size_t)b * h_stride + (size_t)r * N_s;
-  float* ghb = g_h + (size_t)b * gh_stride + (size_t)r * N_s;
+  const size_t gh_off = (size_t)b * gh_stride + (size_t)r * N_s;
   for (int k = lane; k < N_s; k += 32) {
     float acc = 0.0f;
     const float wk = s_w[k];
@@ -166,7 +188,9 @@ composite_cm_bwd_kernel(const float* __restrict__ g_Hc, const float* __restrict_
       const float hv = hb[(size_t)c * P + k];
       const float g = s_g[c];
       acc = fmaf(g, hv, acc);
-      ghb[(size_t)c * P + k] = hv > 0.0f ? wk * g : 0.0f;
+      const float gv = hv > 0.0f ? wk * g : 0.0f;
+      if (PLANES == 0) g_h[gh_off + (size_t)c * P + k] = gv;
+      else st_planes(g_h_hl, gh_plane_stride, PLANES, gh_off + (size_t)c * P + k, gv);
     }
     s_part[warp * N_s + k] = acc;
   }
@@ -183,7 +207,7 @@ composite_cm_bwd_kernel(const float* __restrict__ g_Hc, const float* __restrict_
     const float* ze = z_edges + (size_t)rayg * (N_s + 1);
     const float l = ray_dl[rayg].w;
     const float* sg = sigma_raw + (size_t)b * s_stride + (size_t)r * N_s;
-    float* gs = g_sigma + (size_t)b * gs_stride + (size_t)r * N_s;
+    const size_t gs_off = (size_t)b * gs_stride + (size_t)r * N_s;
     float* gz = g_z + (size_t)rayg * (N_s + 1);
     // forward transmittances T_k into s_part[0..N_s)
     float T = 1.0f;
@@ -204,7 +228,9 @@ composite_cm_bwd_kernel(const float* __restrict__ g_Hc, const float* __restrict_
       const float delta = __fmul_rn(dz, l);
       const float s = fmaxf(sg[k], 0.0f);
       const float e = 1.0f - a;  // exp(-s delta)
-      gs[k] = sg[k] > 0.0f ? ga * e * delta : 0.0f;
+      const float gsv = sg[k] > 0.0f ? ga * e * delta : 0.0f;
+      if (PLANES == 0) g_sigma[gs_off + k] = gsv;
+      else st_planes(g_sigma_hl, gs_plane_stride, PLANES, gs_off + k, gsv);
       const float gd = ga * e * s;
       gl += gd * dz;
       gz[k + 1] += gd * l + carry;   // + from delta_k, - from delta_{k+1} (carry)
@@ -436,7 +462,21 @@ extern "C" int gnrf_pe_fwd(const float* ray_dl, const float* tvecs, const float*
   GNRF_CHECK_ARG(ray_dl && tvecs && z_edges && pe && B > 0 && N_r > 0 && N_s > 0);
   const long long total = (long long)B * 3 * N_r * N_s;
   pe_cm_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const float4*>(ray_dl), tvecs, z_edges, B, N_r, N_s, pe, pe_img_stride > 0 ? pe_img_stride : 63ll * N_r * N_s);
+      reinterpret_cast<const float4*>(ray_dl), tvecs, z_edges, B, N_r, N_s, pe, pe_img_stride > 0 ? pe_img_stride : 63ll * N_r * N_s,
+      nullptr, 0, 0, 0);
+  GNRF_LAUNCH_CHECK();
+  count_launches(1);
+  return GNRF_OK;
+}
+
+extern "C" int gnrf_pe_fwd_hl(const float* ray_dl, const float* tvecs, const float* z_edges, int B, int N_r, int N_s, float* pe,
+                              long long pe_img_stride, void* hl, long long hl_img_stride, long long hl_plane_stride, int planes,
+                              gnrf_stream_t stream) {
+  GNRF_CHECK_ARG(ray_dl && tvecs && z_edges && pe && hl && B > 0 && N_r > 0 && N_s > 0 && (planes == 1 || planes == 2));
+  const long long total = (long long)B * 3 * N_r * N_s;
+  pe_cm_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(ray_dl), tvecs, z_edges, B, N_r, N_s, pe, pe_img_stride > 0 ? pe_img_stride : 63ll * N_r * N_s,
+      static_cast<__nv_bfloat16*>(hl), hl_img_stride > 0 ? hl_img_stride : 63ll * N_r * N_s, hl_plane_stride, planes);
   GNRF_LAUNCH_CHECK();
   count_launches(1);
   return GNRF_OK;
@@ -473,9 +513,31 @@ extern "C" int gnrf_composite_cm_bwd(const float* g_Hc, const float* g_bg_alpha,
   GNRF_CHECK_ARG(g_Hc && h && sigma_raw && weights && z_edges && ray_dl && g_h && g_sigma && g_z && g_l);
   GNRF_CHECK_ARG(B > 0 && N_r > 0 && N_s > 0 && N_s <= 1024 && C > 0 && C <= 1024);
   const size_t smem = (size_t)(10 * N_s + C + 1) * sizeof(float);
-  composite_cm_bwd_kernel<<<B * N_r, 256, smem, as_stream(stream)>>>(g_Hc, g_bg_alpha, h, h_stride, sigma_raw, s_stride, weights, z_edges,
-                                                                    reinterpret_cast<const float4*>(ray_dl), N_r, N_s, C, g_h, gh_stride,
-                                                                    g_sigma, gs_stride, g_z, g_l);
+  composite_cm_bwd_kernel<0><<<B * N_r, 256, smem, as_stream(stream)>>>(g_Hc, g_bg_alpha, h, h_stride, sigma_raw, s_stride, weights, z_edges,
+                                                                       reinterpret_cast<const float4*>(ray_dl), N_r, N_s, C, g_h,
+                                                                       gh_stride, g_sigma, gs_stride, 0, 0, g_z, g_l);
+  GNRF_LAUNCH_CHECK();
+  count_launches(1);
+  return GNRF_OK;
+}
+
+extern "C" int gnrf_composite_cm_bwd_hl(const float* g_Hc, const float* g_bg_alpha, const float* h, long long h_stride,
+                                        const float* sigma_raw, long long s_stride, const float* weights, const float* z_edges,
+                                        const float* ray_dl, int B, int N_r, int N_s, int C, void* g_h, long long gh_stride,
+                                        long long gh_plane_stride, void* g_sigma, long long gs_stride, long long gs_plane_stride,
+                                        int planes, float* g_z, float* g_l, gnrf_stream_t stream) {
+  GNRF_CHECK_ARG(g_Hc && h && sigma_raw && weights && z_edges && ray_dl && g_h && g_sigma && g_z && g_l);
+  GNRF_CHECK_ARG(B > 0 && N_r > 0 && N_s > 0 && N_s <= 1024 && C > 0 && C <= 1024 && (planes == 1 || planes == 2));
+  const size_t smem = (size_t)(10 * N_s + C + 1) * sizeof(float);
+  const float4* rd = reinterpret_cast<const float4*>(ray_dl);
+  if (planes == 2)
+    composite_cm_bwd_kernel<2><<<B * N_r, 256, smem, as_stream(stream)>>>(g_Hc, g_bg_alpha, h, h_stride, sigma_raw, s_stride, weights,
+                                                                         z_edges, rd, N_r, N_s, C, g_h, gh_stride, g_sigma, gs_stride,
+                                                                         gh_plane_stride, gs_plane_stride, g_z, g_l);
+  else
+    composite_cm_bwd_kernel<1><<<B * N_r, 256, smem, as_stream(stream)>>>(g_Hc, g_bg_alpha, h, h_stride, sigma_raw, s_stride, weights,
+                                                                         z_edges, rd, N_r, N_s, C, g_h, gh_stride, g_sigma, gs_stride,
+                                                                         gh_plane_stride, gs_plane_stride, g_z, g_l);
   GNRF_LAUNCH_CHECK();
   count_launches(1);
   return GNRF_OK;

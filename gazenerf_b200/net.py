@@ -311,6 +311,7 @@ class GazeNeRFNet(nn.Module):
                                                   min_feat=32, featmap_size=self.featmap_size, img_size=self.pred_img_size)
         # "tc" = fused tcgen05 kernel (default); "simt" = literal fp32 CUDA-core kernels
         self.mlp_impl = mlp_impl
+        self.train_precision = "bf16x3"   # per-point activation storage of the training path: "bf16x3" | "bf16" | "f32" (train.py)
         self._tc_cache: Dict[str, Tuple[tuple, torch.Tensor]] = {}
         self._tvals_cache: Dict[Tuple[int, str], torch.Tensor] = {}
         self.last_stages: Optional[Dict[str, torch.Tensor]] = None

@@ -6,9 +6,14 @@ The reference trains through torch autograd over its eager graph (trainer/gazene
 radiance MLPs (models/mlp_nerf.py:95-119) -> alpha composite (utils/model_utils.py:493-534) -> compose
 (models/gaze_nerf.py:175-203) -> neural renderer (models/neural_renderer.py:98-113) -- is evaluated layer by layer on
 channel-major activations kept in HBM (B200: 180 GB; ~4 GB per face and branch at 64x64x64), every dense layer and both of
-its gradients on tcgen05 tensor cores (conv_tc.cu forward / input gradient, wgrad_tc.cu weight gradient, bf16x3 split
-precision), everything else in streaming CUDA kernels (train_ops.cu, nr_train.cu).  The tape holds two Functions: FeatureMapFn
-(rays -> feature maps) and NeuralRenderFn (feature maps -> images).
+its gradients on tcgen05 tensor cores, everything else in streaming CUDA kernels (train_ops.cu, nr_train.cu).  The tape holds
+two Functions: FeatureMapFn (rays -> feature maps) and NeuralRenderFn (feature maps -> images).
+
+Per-point activations of the radiance MLPs are stored PRE-SPLIT as bf16 planes (hi | lo, csrc/lin_hl.cu) so that the GEMM kernels
+feed them to the tensor cores straight from TMA: ``net.train_precision`` = "bf16x3" (default: hi + lo planes, the bf16x3 scheme of
+the inference kernel), "bf16" (hi plane only: single-pass bf16, what BASELINE config[4] names; half the bytes, a third of the
+MMAs, gradient tolerance stated in tests/test_train_grad.py) or "f32" (r1 path: fp32 activations re-split inside conv_tc.cu /
+wgrad_tc.cu; also taken automatically when a shape is outside the plane kernels' tiling: points % 256, hidden width < 256).
 
 Exact rewrites used (identities of the reference graph, as in the inference kernel):
   * the per-face code columns of FeaExt_module_0 / FeaExt_module_5 / RGB_layer_1 are folded into per-face bias vectors.  The
@@ -179,6 +184,142 @@ def _branch_backward(o: _Ops, T: Sequence[torch.Tensor], sv: Dict[str, torch.Ten
     return g  # type: ignore[return-value]
 
 
+class _HL:
+    """Call helpers of the plane kernels (csrc/lin_hl.cu).  A plane tensor is a bf16 torch tensor [PL][B][rows][P]."""
+
+    def __init__(self, o: _Ops, planes: int, B: int, P: int):
+        self.o, self.L, self.PL, self.B, self.P = o, o.L, planes, B, P
+        self._ws: Optional[torch.Tensor] = None
+
+    def empty(self, rows: int) -> torch.Tensor:
+        return torch.empty((self.PL, self.B, rows, self.P), device=self.o.dev, dtype=torch.bfloat16)
+
+    def pack(self, W: torch.Tensor, bias: Optional[torch.Tensor], N: int, K: int, transposed: bool = False) -> torch.Tensor:
+        assert W.is_contiguous() and W.dtype == torch.float32 and W.shape == ((K, N) if transposed else (N, K)), (W.shape, N, K)
+        pk = torch.empty((self.L.gnrf_lin_hl_packed_bytes(N, K, self.PL),), device=self.o.dev, dtype=torch.uint8)
+        _lib.check(self.L.gnrf_lin_hl_pack(W.data_ptr(), bias.data_ptr() if bias is not None else None, N, K, 1 if transposed else 0,
+                                           self.PL, pk.data_ptr(), self.o.st), "gnrf_lin_hl_pack")
+        return pk
+
+    def lin(self, pk, N, K, x: torch.Tensor, x_row0: int = 0, out: Optional[torch.Tensor] = None, out_row0: int = 0, hl_rows: Optional[int] = None,
+            out_f32: Optional[torch.Tensor] = None, act=0, bias_img=None, mask: Optional[torch.Tensor] = None, mask_rows: int = 0):
+        """x / out / mask: plane tensors, addressed from row x_row0 / out_row0 (row windows of a wider tensor keep its strides)."""
+        P = self.P
+        hl_rows = N if hl_rows is None else hl_rows
+        _lib.check(self.L.gnrf_lin_hl(
+            pk.data_ptr(), N, K, self.PL, x.data_ptr() + x_row0 * P * 2, x.shape[2] * P, x.stride(0), bias_img.data_ptr() if bias_img is not None else None,
+            act, (out.data_ptr() + out_row0 * P * 2) if out is not None else None, out.shape[2] * P if out is not None else 0,
+            out.stride(0) if out is not None else 0, hl_rows, out_f32.data_ptr() if out_f32 is not None else None,
+            out_f32.shape[1] * P if out_f32 is not None else 0, mask.data_ptr() if mask is not None else None,
+            mask.shape[2] * P if mask is not None else 0, mask_rows, self.B, P, self.o.st), "gnrf_lin_hl")
+
+    def wgrad(self, dy: torch.Tensor, N: int, x: torch.Tensor, K: int, db_mode: str, x_row0: int = 0):
+        """-> dW [N][K], db ([B][N] for 'img', [N] for 'sum')."""
+        P, o = self.P, self.o
+        need = self.L.gnrf_wgrad_hl_workspace_bytes(N, K, self.B, P)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty((need,), device=o.dev, dtype=torch.uint8)
+        dW = o.empty(N, K)
+        db = o.empty(self.B, N) if db_mode == "img" else o.empty(N)
+        _lib.check(self.L.gnrf_wgrad_hl(dy.data_ptr(), dy.shape[2] * P, dy.stride(0), x.data_ptr() + x_row0 * P * 2, x.shape[2] * P, x.stride(0),
+                                        self.PL, N, K, self.B, P, dW.data_ptr(), db.data_ptr(), 1 if db_mode == "sum" else 0,
+                                        self._ws.data_ptr(), self._ws.numel(), o.st), "gnrf_wgrad_hl")
+        return dW, db
+
+
+def hl_supported(H: int, P: int) -> bool:
+    return P % 256 == 0 and H >= 256 and H % 2 == 0
+
+
+def _branch_forward_hl(o: _Ops, T: Sequence[torch.Tensor], B, n_r, n_s, H, C, ray_dl, tvecs, z_edges, planes: int) -> Dict[str, torch.Tensor]:
+    """_branch_forward on bf16 plane tensors (no conversion pass in any GEMM); fp32 only where a non-GEMM kernel consumes it."""
+    L, P = o.L, n_r * n_s
+    H2 = H // 2
+    q = _HL(o, planes, B, P)
+    buf0 = q.empty(H + 64)                 # rows [0,H): layer-4 output; rows [H, H+63): positional encoding (layers 0 and 5)
+    pe32 = o.empty(B, PE, P)               # fp32 copy for the encoding's backward
+    _lib.check(L.gnrf_pe_fwd_hl(ray_dl.data_ptr(), tvecs.data_ptr(), z_edges.data_ptr(), B, n_r, n_s, pe32.data_ptr(), PE * P,
+                                buf0.data_ptr() + H * P * 2, (H + 64) * P, buf0.stride(0), planes, o.st), "gnrf_pe_fwd_hl")
+    h: List[Optional[torch.Tensor]] = [None] * 8
+    h[0] = q.empty(H)
+    q.lin(q.pack(T[0], None, H, PE), H, PE, buf0, x_row0=H, out=h[0], act=RELU, bias_img=T[1])
+    for i in (1, 2, 3):
+        h[i] = q.empty(H)
+        q.lin(q.pack(T[2 * i], T[2 * i + 1], H, H), H, H, h[i - 1], out=h[i], act=RELU)
+    q.lin(q.pack(T[8], T[9], H, H), H, H, h[3], out=buf0, act=RELU)                                   # layer 4 -> buf0 rows [0,H)
+    h[5] = q.empty(H)
+    q.lin(q.pack(T[10], None, H, H + PE), H, H + PE, buf0, out=h[5], act=RELU, bias_img=T[11])
+    for i, k in ((6, 12), (7, 14)):
+        h[i] = q.empty(H)
+        q.lin(q.pack(T[k], T[k + 1], H, H), H, H, h[i - 1], out=h[i], act=RELU)
+    r0 = q.empty(H)                        # RGB_layer_0 output (planes) ...
+    sig = o.empty(B, 1, P)                 # ... and the raw density (row H of the same GEMM) in fp32 for the composite
+    q.lin(q.pack(T[16], T[17], H + 1, H), H + 1, H, h[7], out=r0, hl_rows=H, out_f32=sig, act=NONE)
+    hc = o.empty(B, H2, P)
+    q.lin(q.pack(T[18], None, H2, H), H2, H, r0, hl_rows=0, out_f32=hc, act=RELU, bias_img=T[19])
+    Hc, bg_alpha, w = o.empty(B, H2 + 1, n_r), o.empty(B, n_r), o.empty(B, n_r, n_s)
+    _lib.check(L.gnrf_composite_cm_fwd(hc.data_ptr(), H2 * P, sig.data_ptr(), P, z_edges.data_ptr(), ray_dl.data_ptr(), B, n_r, n_s, H2,
+                                       Hc.data_ptr(), bg_alpha.data_ptr(), w.data_ptr(), o.st), "gnrf_composite_cm_fwd")
+    feat = o.empty(B, C, n_r)
+    o.conv(o.pack(T[20], None, C, H2 + 1), C, H2 + 1, Hc.data_ptr(), 0, feat.data_ptr(), 0, B, n_r, act=NONE)
+    return {"buf0": buf0, "pe32": pe32, "h": h, "r0": r0, "sig": sig, "hc": hc, "Hc": Hc, "bg_alpha": bg_alpha, "w": w, "feat": feat,
+            "planes": planes}
+
+
+def _branch_backward_hl(o: _Ops, T: Sequence[torch.Tensor], sv: Dict[str, torch.Tensor], B, n_r, n_s, H, C, ray_dl, z_edges, g_feat, g_alpha,
+                        g_m, g_o, g_z, g_l) -> List[torch.Tensor]:
+    """_branch_backward on plane tensors: every output / input gradient that feeds a GEMM is written as planes by its producer."""
+    L, P = o.L, n_r * n_s
+    H2 = H // 2
+    planes = sv["planes"]
+    q = _HL(o, planes, B, P)
+    buf0, h, r0, hc, Hc, w, sig = sv["buf0"], sv["h"], sv["r0"], sv["hc"], sv["Hc"], sv["w"], sv["sig"]
+    g: List[Optional[torch.Tensor]] = [None] * N_BRANCH_T
+    g[20], _ = o.wgrad(g_feat.data_ptr(), 0, Hc.data_ptr(), 0, C, H2 + 1, B, n_r, "none")
+    g_Hc = o.empty(B, H2 + 1, n_r)
+    o.conv(o.pack(T[20], None, H2 + 1, C, transposed=True), H2 + 1, C, g_feat.data_ptr(), 0, g_Hc.data_ptr(), 0, B, n_r)
+    g_r0, g_hc = q.empty(H + 1), q.empty(H2)       # row H of g_r0: gradient of the raw density
+    _lib.check(L.gnrf_composite_cm_bwd_hl(g_Hc.data_ptr(), g_alpha.data_ptr(), hc.data_ptr(), H2 * P, sig.data_ptr(), P, w.data_ptr(),
+                                          z_edges.data_ptr(), ray_dl.data_ptr(), B, n_r, n_s, H2, g_hc.data_ptr(), H2 * P, g_hc.stride(0),
+                                          g_r0.data_ptr() + H * P * 2, (H + 1) * P, g_r0.stride(0), planes, g_z.data_ptr(), g_l.data_ptr(),
+                                          o.st), "gnrf_composite_cm_bwd_hl")
+    # RGB_layer_1 (hidden part; the appearance columns live in the per-face bias)
+    g[18], g[19] = q.wgrad(g_hc, H2, r0, H, "img")
+    q.lin(q.pack(T[18], None, H, H2, transposed=True), H, H2, g_hc, out=g_r0)
+    del g_hc
+    # RGB_layer_0 + density_module on h7
+    g[16], g[17] = q.wgrad(g_r0, H + 1, h[7], H, "sum")
+    ga = q.empty(H)
+    q.lin(q.pack(T[16], None, H, H + 1, transposed=True), H, H + 1, g_r0, out=ga, mask=h[7])
+    del g_r0
+    for i, k in ((7, 14), (6, 12)):
+        g[k], g[k + 1] = q.wgrad(ga, H, h[i - 1], H, "sum")
+        gb = q.empty(H)
+        q.lin(q.pack(T[k], None, H, H, transposed=True), H, H, ga, out=gb, mask=h[i - 1])
+        ga = gb
+    # skip layer 5: operand [h4 | PE] = rows [0, H+63) of buf0; its input gradient: rows < H (h4, masked) as planes, PE rows fp32
+    g[10], g[11] = q.wgrad(ga, H, buf0, H + PE, "img")
+    g4, g_pe_b = q.empty(H), o.empty(B, PE, P)
+    q.lin(q.pack(T[10], None, H + PE, H, transposed=True), H + PE, H, ga, out=g4, hl_rows=H, out_f32=g_pe_b, mask=buf0, mask_rows=H)
+    # layer 4
+    g[8], g[9] = q.wgrad(g4, H, h[3], H, "sum")
+    ga = q.empty(H)
+    q.lin(q.pack(T[8], None, H, H, transposed=True), H, H, g4, out=ga, mask=h[3])
+    del g4
+    for i in (3, 2, 1):
+        g[2 * i], g[2 * i + 1] = q.wgrad(ga, H, h[i - 1], H, "sum")
+        gb = q.empty(H)
+        q.lin(q.pack(T[2 * i], None, H, H, transposed=True), H, H, ga, out=gb, mask=h[i - 1])
+        ga = gb
+    # layer 0 on the positional encoding
+    g[0], g[1] = q.wgrad(ga, H, buf0, PE, "img", x_row0=H)
+    g_pe_a = o.empty(B, PE, P)
+    q.lin(q.pack(T[0], None, PE, H, transposed=True), PE, H, ga, hl_rows=0, out_f32=g_pe_a)
+    _lib.check(L.gnrf_pe_bwd(g_pe_a.data_ptr(), PE * P, g_pe_b.data_ptr(), PE * P, sv["pe32"].data_ptr(), PE * P, ray_dl.data_ptr(),
+                             z_edges.data_ptr(), B, n_r, n_s, g_m.data_ptr(), g_o.data_ptr(), g_z.data_ptr(), o.st), "gnrf_pe_bwd")
+    return g  # type: ignore[return-value]
+
+
 class FeatureMapFn(torch.autograd.Function):
     """rays -> positional encoding -> both radiance MLPs -> composite -> compose:  feature maps [3B+1, C, S, S] =
     (merge_face | eyes_planes | merge | bg_featmap), with gradients to every argument tensor."""
@@ -193,8 +334,15 @@ class FeatureMapFn(torch.autograd.Function):
         Tf, Te = T[:N_BRANCH_T], T[N_BRANCH_T:2 * N_BRANCH_T]
         ray_dl = o.empty(B, n_r, 4)
         _lib.check(L.gnrf_ray_setup(xy.data_ptr(), rmats.data_ptr(), kinv.data_ptr(), B, n_r, ray_dl.data_ptr(), o.st), "gnrf_ray_setup")
-        sv_f = _branch_forward(o, Tf, B, n_r, n_s, H, C, ray_dl, tvecs, z_edges)
-        sv_e = _branch_forward(o, Te, B, n_r, n_s, H, C, ray_dl, tvecs, z_edges)
+        planes = {"bf16x3": 2, "bf16": 1, "f32": 0}[cfg.get("precision", "bf16x3")]
+        if planes and not hl_supported(H, n_r * n_s):
+            planes = 0
+        if planes:
+            sv_f = _branch_forward_hl(o, Tf, B, n_r, n_s, H, C, ray_dl, tvecs, z_edges, planes)
+            sv_e = _branch_forward_hl(o, Te, B, n_r, n_s, H, C, ray_dl, tvecs, z_edges, planes)
+        else:
+            sv_f = _branch_forward(o, Tf, B, n_r, n_s, H, C, ray_dl, tvecs, z_edges)
+            sv_e = _branch_forward(o, Te, B, n_r, n_s, H, C, ray_dl, tvecs, z_edges)
         n_img = 3 * B + 1
         fm = o.empty(n_img, C, S, S)
         bg = bg_featmap.detach().contiguous()
@@ -235,8 +383,9 @@ class FeatureMapFn(torch.autograd.Function):
         # ---- radiance MLPs + composite + positional encoding
         g_m, g_o, g_l = o.zeros(B, n_r, 3), o.zeros(B, n_r, 3), o.zeros(B, n_r)
         g_z = o.zeros(B, n_r, n_s + 1)
-        g_f = _branch_backward(o, Tf, sv_f, B, n_r, n_s, H, C, ray_dl, z_edges, g_ff, g_af, g_m, g_o, g_z, g_l)
-        g_e = _branch_backward(o, Te, sv_e, B, n_r, n_s, H, C, ray_dl, z_edges, g_fe, g_ae, g_m, g_o, g_z, g_l)
+        bwd = _branch_backward_hl if "planes" in sv_f else _branch_backward
+        g_f = bwd(o, Tf, sv_f, B, n_r, n_s, H, C, ray_dl, z_edges, g_ff, g_af, g_m, g_o, g_z, g_l)
+        g_e = bwd(o, Te, sv_e, B, n_r, n_s, H, C, ray_dl, z_edges, g_fe, g_ae, g_m, g_o, g_z, g_l)
         # ---- geometry
         contrib = o.empty(B, n_r, 12)
         _lib.check(L.gnrf_geom_bwd(xy.data_ptr(), k["rmats"].data_ptr(), k["kinv"].data_ptr(), g_m.data_ptr(), g_o.data_ptr(), g_l.data_ptr(),
@@ -300,7 +449,8 @@ def render_featmaps(net, xy, rmats, tvecs, kinv, gaze, shape_ext, appea, z_edges
     """Differentiable rays -> feature maps [3B+1, C, S, S] (merge_face | eyes_planes | merge | bg_featmap)."""
     tf = branch_tensors(net.fg_CD_predictor_face, shape_ext, appea)
     te = branch_tensors(net.fg_CD_predictor_eyes, shape_ext, appea)
-    cfg = {"net": net, "H": net.mlp_h_channel, "C": net.featmap_nc, "S": net.featmap_size, "n_s": net.num_sample_coarse, "stages": stages}
+    cfg = {"net": net, "H": net.mlp_h_channel, "C": net.featmap_nc, "S": net.featmap_size, "n_s": net.num_sample_coarse, "stages": stages,
+           "precision": getattr(net, "train_precision", "bf16x3")}
     return FeatureMapFn.apply(cfg, xy, rmats, tvecs, kinv, gaze, z_edges, net.neural_render.bg_featmap, *tf, *te)
 
 

@@ -236,6 +236,34 @@ int gnrf_composite_cm_bwd(const float* g_Hc, const float* g_bg_alpha, const floa
                           int N_s, int C, float* g_h, long long gh_stride, float* g_sigma, long long gs_stride, float* g_z,
                           float* g_l, gnrf_stream_t stream);
 
+/* ---- The same layers on PRE-SPLIT bf16 planes (csrc/lin_hl.cu; training path of models/mlp_nerf.py:95-119 without a conversion
+ * pass).  A plane tensor holds x as hi = bf16(x) [and lo = bf16(x - hi), `plane_stride` elements after hi]: [planes][img][rows][HW],
+ * points contiguous; planes = 2 is the bf16x3 scheme of the kernels above, planes = 1 single-pass bf16 (half the bytes; gradient
+ * tolerance stated in tests/test_train_grad.py).  All strides in ELEMENTS (bf16 or float); HW a multiple of 256, K >= 32.
+ *   gnrf_lin_hl:  y[img][n][p] = act( sum_k W[n][k] x[img][k][p] + bias[n] + bias_img[img][n] ) * (mask[img][n][p] > 0 for n < mask_rows)
+ *     rows n < hl_rows are written as planes to `out`, rows n >= hl_rows as fp32 to out_f32[img][n - hl_rows][p] (for the non-GEMM
+ *     consumers: composite, positional-encoding backward).  mask = hi plane of a saved post-ReLU activation (input gradient).
+ *   gnrf_wgrad_hl: dW[n][k] = sum_img sum_p dY[img][n][p] X[img][k][p]; db as in gnrf_wgrad_tc.  N >= 128, HW a multiple of 32.
+ *   gnrf_pe_fwd_hl: gnrf_pe_fwd that also writes the encoding as planes; gnrf_composite_cm_bwd_hl: g_h / g_sigma as planes. */
+size_t gnrf_lin_hl_packed_bytes(int N, int K, int planes);
+int gnrf_lin_hl_pack(const float* W, const float* bias, int N, int K, int transposed, int planes, void* packed, gnrf_stream_t stream);
+int gnrf_lin_hl(const void* packed, int N, int K, int planes, const void* X, long long x_img_stride, long long x_plane_stride,
+                const float* bias_img, int act, void* out, long long out_img_stride, long long out_plane_stride, int hl_rows,
+                float* out_f32, long long f32_img_stride, const void* mask, long long mask_img_stride, int mask_rows, int n_img,
+                int HW, gnrf_stream_t stream);
+size_t gnrf_wgrad_hl_workspace_bytes(int N, int K, int n_img, int HW);
+int gnrf_wgrad_hl(const void* dY, long long dy_img_stride, long long dy_plane_stride, const void* X, long long x_img_stride,
+                  long long x_plane_stride, int planes, int N, int K, int n_img, int HW, float* dW, float* db, int db_sum,
+                  void* workspace, size_t workspace_bytes, gnrf_stream_t stream);
+int gnrf_pe_fwd_hl(const float* ray_dl, const float* tvecs, const float* z_edges, int B, int N_r, int N_s, float* pe,
+                   long long pe_img_stride, void* hl, long long hl_img_stride, long long hl_plane_stride, int planes,
+                   gnrf_stream_t stream);
+int gnrf_composite_cm_bwd_hl(const float* g_Hc, const float* g_bg_alpha, const float* h, long long h_stride, const float* sigma_raw,
+                             long long s_stride, const float* weights, const float* z_edges, const float* ray_dl, int B, int N_r,
+                             int N_s, int C, void* g_h, long long gh_stride, long long gh_plane_stride, void* g_sigma,
+                             long long gs_stride, long long gs_plane_stride, int planes, float* g_z, float* g_l,
+                             gnrf_stream_t stream);
+
 /* Ray geometry backward (GenSamplePoints, utils/model_utils.py:364-372): per-ray gradients -> contrib [B][N_r][12] =
  * (dL/dR 3x3 row-major, dL/dT 3); the caller sums over rays. */
 int gnrf_geom_bwd(const float* xy, const float* rmats, const float* inv_inmats, const float* g_m, const float* g_o,
