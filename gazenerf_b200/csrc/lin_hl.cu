@@ -13,8 +13,10 @@
 //       A = packed weights (K-major no-swizzle core matrices, bulk copy), B = activation planes, which are MN-major for this
 //       product (points contiguous): SWIZZLE_128B MN-major atoms [64 pt x 8 ch] written by tensor-map TMA (one box per 64-point group).
 //       Two 256-column TMEM accumulators: the epilogue of (tile, M-tile) i overlaps the MMAs of i+1.  Epilogue thread = output
-//       channel, so it owns 32 CONSECUTIVE points per tcgen05.ld: bias (+per-image bias), ReLU or the ReLU mask of the saved
-//       activation (input gradient), hi/lo split, 16-byte vector stores of both planes (or fp32 rows for the non-GEMM consumers).
+//       channel, so it owns 32 CONSECUTIVE points per tcgen05.ld: bias (+per-image bias), ReLU or the saved ReLU sign bits (input
+//       gradient; the forward writes them as a 1-bit-per-element tensor), hi/lo split, then a swizzled smem slot per warp and ONE TMA
+//       tensor store of [planes][32 rows][32 points] (direct per-thread stores touched 32 different lines per instruction and held the
+//       kernel at 2 TB/s of output); fp32 rows for the non-GEMM consumers go out as plain vector stores.
 //   * wgrad_hl_kernel (weight gradient)               dW[out][in] = sum_pt dY[out][pt] X[in][pt]
 //       both operands K-major (K = points) SWIZZLE_64B tiles of 32 points straight from TMA; M = 128 rows of dY, N = ALL rows of X
 //       (<= 392, two UMMA N-blocks) so that dY is read once and X n_mt times (r1: 2x / 3x); an all-ones row group in front of X
@@ -39,11 +41,15 @@ constexpr int kLhWPlane = 128 * kLhKb * 2;       // [2 K16 slices][128 rows x 32
 template <int PL>
 struct LhCfg {
   static constexpr int kStageBytes = PL * (kLhActPlane + kLhWPlane);
-  static constexpr int kStages = PL == 2 ? 4 : 8;
+  static constexpr int kStages = PL == 2 ? 4 : 7;   // bytes in flight per SM bound the L2 -> SM stream (4 x 48 KB measured 5 % faster
+  static constexpr int kSlots = PL == 2 ? 1 : 2;    // than 3 x 48 KB + a second output staging slot per epilogue warp)
   static constexpr int kWOff = PL * kLhActPlane;
   static constexpr int kBarFull = 0, kBarEmpty = kStages, kBarAccFull = 2 * kStages, kBarAccEmpty = 2 * kStages + 2,
                        kNumBars = 2 * kStages + 4;
-  static constexpr int kSmemBars = kStages * kStageBytes;
+  // output staging: per epilogue warp kSlots slots of [PL planes][32 rows][64 B] (SWIZZLE_64B), drained by TMA tensor stores
+  static constexpr int kSlotBytes = PL * 2048;
+  static constexpr int kSmemStage = kStages * kStageBytes;
+  static constexpr int kSmemBars = kSmemStage + 8 * kSlots * kSlotBytes;
   static constexpr int kSmemMisc = kSmemBars + kNumBars * 8;
   static constexpr int kSmemBytes = kSmemMisc + 64 + 1024;
 };
@@ -58,9 +64,12 @@ struct LinArgs {
   int hl_rows;
   float* out_f32;               // fp32 rows: output row r >= hl_rows -> out_f32[img][r - hl_rows][pt]
   long long f32_img_stride;
-  const __nv_bfloat16* mask;    // hi plane of a saved post-ReLU activation: v = mask > 0 ? v : 0 for rows < mask_rows
-  long long mask_img_stride;
+  const uint32_t* mask_bits;    // [n_img][rows][HW/32] sign bits of a saved post-ReLU activation: v = bit ? v : 0 for rows < mask_rows
+  long long mask_img_stride;    // in 32-bit words
   int mask_rows;
+  uint32_t* mask_out;           // nullable: bit j of word [img][row][p/32] = (output > 0), rows < mask_out_rows
+  long long mask_out_img_stride;
+  int mask_out_rows;
 };
 
 __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -68,7 +77,8 @@ __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, ui
 }
 
 template <int PL>
-__global__ void __launch_bounds__(kLhThreads, 1) lin_hl_kernel(const LinArgs args, const __grid_constant__ CUtensorMap x_map) {
+__global__ void __launch_bounds__(kLhThreads, 1) lin_hl_kernel(const LinArgs args, const __grid_constant__ CUtensorMap x_map,
+                                                               const __grid_constant__ CUtensorMap out_map) {
   using C = LhCfg<PL>;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -88,71 +98,99 @@ __global__ void __launch_bounds__(kLhThreads, 1) lin_hl_kernel(const LinArgs arg
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // item = (tile, M-tile), M-tile fastest ACROSS CTAs: the n_mt CTAs that need the same activation tile read it at the same time, so it
+  // comes from HBM once (with one CTA walking the M-tiles of its tile, the re-reads 10 and 20 us later missed L2: 1.5x DRAM reads).
+  // Tried and rejected: those n_mt CTAs as a cluster with the tile multicast (every SM still ingests the same bytes -- the limit is
+  // the per-SM L2 -> SM stream -- and the lockstep cost 15 %); L2 prefetch of the next tile (no gain here, 2x DRAM reads in wgrad_hl).
+  const int n_items = args.n_tiles * args.n_mt;
 
   if (warp < 8) {
     // ======================================= epilogue: thread = output channel, 4 x 32 consecutive points =======================
     const int q = warp & 3, hf = warp >> 2;
+    const int words_per_row = args.HW >> 5;
+    const uint64_t out_map_ptr = reinterpret_cast<uint64_t>(&out_map);
+    const uint32_t slot0 = smem_base + (uint32_t)C::kSmemStage + (uint32_t)(warp * C::kSlots * C::kSlotBytes);
+    const uint32_t my_off = (uint32_t)(lane * 64), sw = ((uint32_t)lane >> 1) & 3u;
+    uint32_t n_st = 0;   // TMA stores issued by this warp (slot = n_st & 1)
     int it = 0;
-    for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int tile = item / args.n_mt, mt = item - tile * args.n_mt;
       const int img = tile / args.tiles_per_img, p_tile = (tile - img * args.tiles_per_img) * kLhTileN + hf * 128;
-      for (int mt = 0; mt < args.n_mt; ++mt, ++it) {
+      {
         const int buf = it & 1;
-        const int row = mt * 128 + q * 32 + lane;
+        const int row_base = mt * 128 + q * 32, row = row_base + lane;
+        const bool warp_live = row_base < args.N_out, warp_planes = row_base < args.hl_rows;   // hl_rows % 32 == 0 or >= N_out
         const bool valid = row < args.N_out;
         float b = 0.0f;
         if (valid) {
           b = args.bias[row];
           if (args.bias_img != nullptr) b += args.bias_img[(size_t)img * args.N_out + row];
         }
-        const bool use_mask = valid && args.mask != nullptr && row < args.mask_rows;
-        const __nv_bfloat16* mrow = args.mask + (size_t)img * args.mask_img_stride + (size_t)row * args.HW + p_tile;
-        uint4 mk[4];
-        if (use_mask) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) mk[j] = *reinterpret_cast<const uint4*>(mrow + j * 8);
-        }
+        const bool use_mask = valid && args.mask_bits != nullptr && row < args.mask_rows;
+        uint4 mw4 = make_uint4(~0u, ~0u, ~0u, ~0u);
+        if (use_mask)
+          mw4 = *reinterpret_cast<const uint4*>(args.mask_bits + (size_t)img * args.mask_img_stride + (size_t)row * words_per_row + (p_tile >> 5));
+        const uint32_t mw[4] = {mw4.x, mw4.y, mw4.z, mw4.w};
+        uint32_t mo[4] = {0u, 0u, 0u, 0u};
         mbar_wait(bar(C::kBarAccFull + buf), (uint32_t)((it >> 1) & 1));
         tc_fence_after_sync();
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + hf * 128);
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t r[32];
           tmem_ld32(t_addr + (uint32_t)(c * 32), r);
-          uint4 mk_next[4];
-          if (use_mask && c < 3) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) mk_next[j] = *reinterpret_cast<const uint4*>(mrow + (c + 1) * 32 + j * 8);
-          }
           tmem_wait_ld();
-          if (valid) {
+          if (warp_live) {
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               v[j] = __uint_as_float(r[j]) + b;
               if (args.act) v[j] = fmaxf(v[j], 0.0f);
             }
-            if (use_mask) {
-              const uint32_t* mw = reinterpret_cast<const uint32_t*>(mk);
+            if (args.mask_bits != nullptr) {   // warp-uniform: the input-gradient calls
+              const uint32_t m = mw[c];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int bits = (int)(short)((mw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);   // bf16 > 0  <=>  its bits as int16 > 0
-                v[j] = bits > 0 ? v[j] : 0.0f;
-              }
+              for (int j = 0; j < 32; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0.0f;
+            }
+            if (args.mask_out != nullptr) {    // warp-uniform: the forward calls
+#pragma unroll
+              for (int j = 0; j < 32; ++j) mo[c] |= (v[j] > 0.0f ? 1u : 0u) << j;
             }
             const int p0 = p_tile + c * 32;
-            if (row < args.hl_rows) {
+            if (warp_planes) {
               uint32_t hi[16], lo[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-              __nv_bfloat16* o = args.out + (size_t)img * args.out_img_stride + (size_t)row * args.HW + p0;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) st_global_v4(o + j * 8, hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-              if (PL == 2) {
-                o += args.out_plane_stride;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) st_global_v4(o + j * 8, lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              if (n_st >= (uint32_t)C::kSlots) {   // the store that last used this slot has finished READING it
+                if (lane == 0) {
+                  if (C::kSlots == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                  else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+                __syncwarp();
               }
-            } else {
+              const uint32_t slot = slot0 + (n_st % (uint32_t)C::kSlots) * (uint32_t)C::kSlotBytes;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot + my_off + (((uint32_t)j ^ sw) << 4)), "r"(hi[4 * j]),
+                             "r"(hi[4 * j + 1]), "r"(hi[4 * j + 2]), "r"(hi[4 * j + 3])
+                             : "memory");
+              if (PL == 2) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 2048u + my_off + (((uint32_t)j ^ sw) << 4)),
+                               "r"(lo[4 * j]), "r"(lo[4 * j + 1]), "r"(lo[4 * j + 2]), "r"(lo[4 * j + 3])
+                               : "memory");
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {   // one tensor store: [PL planes][32 rows][32 points]; rows past the tensor are clipped by the TMA unit
+                asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(out_map_ptr),
+                             "r"(p0), "r"(row_base), "r"(img), "r"(0), "r"(slot)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+              ++n_st;
+            } else if (valid) {
               float* o = args.out_f32 + (size_t)img * args.f32_img_stride + (size_t)(row - args.hl_rows) * args.HW + p0;
 #pragma unroll
               for (int j = 0; j < 8; ++j)
@@ -160,24 +198,26 @@ __global__ void __launch_bounds__(kLhThreads, 1) lin_hl_kernel(const LinArgs arg
                              __float_as_uint(v[4 * j + 3]));
             }
           }
-          if (use_mask && c < 3) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) mk[j] = mk_next[j];
-          }
         }
+        if (valid && args.mask_out != nullptr && row < args.mask_out_rows)
+          *reinterpret_cast<uint4*>(args.mask_out + (size_t)img * args.mask_out_img_stride + (size_t)row * words_per_row + (p_tile >> 5)) =
+              make_uint4(mo[0], mo[1], mo[2], mo[3]);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(C::kBarAccEmpty + buf));
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores complete before the CTA exits
+    __syncwarp();
   } else if (warp == 8) {
     // ======================================= loader: one tensor-map TMA (activations) + one bulk copy (weights) per stage =======
     if (elect_one()) {
       const uint64_t map_ptr = reinterpret_cast<uint64_t>(&x_map);
       uint32_t s = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int tile = item / args.n_mt, mt = item - tile * args.n_mt;
         const int img = tile / args.tiles_per_img, p0 = (tile - img * args.tiles_per_img) * kLhTileN;
-        for (int mt = 0; mt < args.n_mt; ++mt) {
+        {
           const unsigned char* wsrc = args.wpack + (size_t)mt * args.n_kb * (PL * kLhWPlane);
           for (int kb = 0; kb < args.n_kb; ++kb) {
             mbar_wait_spin(bar(C::kBarEmpty + s), ph ^ 1);
@@ -210,8 +250,8 @@ __global__ void __launch_bounds__(kLhThreads, 1) lin_hl_kernel(const LinArgs arg
       const uint32_t idesc = umma_idesc_bf16(128, kLhTileN) | (1u << 16);   // bit 16: B is MN-major
       uint32_t s = 0, ph = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
-        for (int mt = 0; mt < args.n_mt; ++mt, ++it) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        {
           const int buf = it & 1;
           mbar_wait_spin(bar(C::kBarAccEmpty + buf), (uint32_t)(((it >> 1) & 1) ^ 1));
           tc_fence_after_sync();
@@ -304,15 +344,16 @@ static LinPlan lin_plan(int N, int K, int planes) {
 }
 
 template <int PL>
-static int lin_hl_launch_t(const LinArgs& a, const CUtensorMap& map, int n_sm, cudaStream_t st) {
+static int lin_hl_launch_t(const LinArgs& a, const CUtensorMap& map, const CUtensorMap& out_map, int n_sm, cudaStream_t st) {
   int dummy = 0;
   int rc = device_once(PL == 2 ? kOnceLinHl2 : kOnceLinHl1, &dummy, []() -> int {
     GNRF_CUDA(cudaFuncSetAttribute(lin_hl_kernel<PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, LhCfg<PL>::kSmemBytes));
     return GNRF_OK;
   });
   if (rc != GNRF_OK) return rc;
-  const int grid = a.n_tiles < n_sm ? a.n_tiles : n_sm;
-  lin_hl_kernel<PL><<<grid, kLhThreads, LhCfg<PL>::kSmemBytes, st>>>(a, map);
+  const int n_items = a.n_tiles * a.n_mt;
+  const int grid = n_items < n_sm ? n_items : n_sm;
+  lin_hl_kernel<PL><<<grid, kLhThreads, LhCfg<PL>::kSmemBytes, st>>>(a, map, out_map);
   return GNRF_OK;
 }
 
@@ -587,15 +628,17 @@ extern "C" int gnrf_lin_hl_pack(const float* W, const float* bias, int N, int K,
 
 extern "C" int gnrf_lin_hl(const void* packed, int N, int K, int planes, const void* X, long long x_img_stride, long long x_plane_stride,
                            const float* bias_img, int act, void* out, long long out_img_stride, long long out_plane_stride, int hl_rows,
-                           float* out_f32, long long f32_img_stride, const void* mask, long long mask_img_stride, int mask_rows,
-                           int n_img, int HW, gnrf_stream_t stream) {
+                           float* out_f32, long long f32_img_stride, const void* mask_bits, long long mask_img_stride, int mask_rows,
+                           void* mask_out, long long mask_out_img_stride, int mask_out_rows, int n_img, int HW, gnrf_stream_t stream) {
   GNRF_CHECK_ARG(packed && X && N > 0 && K > 0 && n_img > 0 && HW > 0 && (planes == 1 || planes == 2));
   GNRF_CHECK_ARG(HW % tc::kLhTileN == 0 && K >= tc::kLhKb);
   GNRF_CHECK_ARG(hl_rows >= 0 && (hl_rows == 0 || out != nullptr) && (hl_rows >= N || out_f32 != nullptr));
+  GNRF_CHECK_ARG(hl_rows >= N || hl_rows % 32 == 0);   // a 32-row epilogue group is either all planes or all fp32
   GNRF_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & 15) == 0 && x_img_stride % 8 == 0 && x_plane_stride % 8 == 0);
   GNRF_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0 &&
-                 (reinterpret_cast<uintptr_t>(mask) & 15) == 0 && out_img_stride % 8 == 0 && out_plane_stride % 8 == 0 &&
-                 f32_img_stride % 4 == 0 && mask_img_stride % 8 == 0);
+                 (reinterpret_cast<uintptr_t>(mask_bits) & 15) == 0 && (reinterpret_cast<uintptr_t>(mask_out) & 15) == 0 &&
+                 out_img_stride % 8 == 0 && out_plane_stride % 8 == 0 && f32_img_stride % 4 == 0 && mask_img_stride % 4 == 0 &&
+                 mask_out_img_stride % 4 == 0);
   int n_sm = 0;
   {
     int rc = device_once(kOnceLinHlSm, &n_sm, []() -> int { return GNRF_OK; });
@@ -628,11 +671,26 @@ extern "C" int gnrf_lin_hl(const void* packed, int N, int K, int planes, const v
   a.hl_rows = hl_rows;
   a.out_f32 = out_f32;
   a.f32_img_stride = f32_img_stride > 0 ? f32_img_stride : (long long)(N - hl_rows) * HW;
-  a.mask = static_cast<const __nv_bfloat16*>(mask);
-  a.mask_img_stride = mask_img_stride > 0 ? mask_img_stride : (long long)N * HW;
+  a.mask_bits = static_cast<const uint32_t*>(mask_bits);
+  a.mask_img_stride = mask_img_stride > 0 ? mask_img_stride : (long long)N * (HW / 32);
   a.mask_rows = mask_rows > 0 ? mask_rows : N;
+  a.mask_out = static_cast<uint32_t*>(mask_out);
+  a.mask_out_img_stride = mask_out_img_stride > 0 ? mask_out_img_stride : (long long)N * (HW / 32);
+  a.mask_out_rows = mask_out_rows > 0 ? mask_out_rows : N;
   if (planes == 2 && hl_rows > 0 && out_plane_stride <= 0) return fail(GNRF_ERR_ARG, "lin_hl: out_plane_stride required with 2 planes");
-  int rc = planes == 2 ? tc::lin_hl_launch_t<2>(a, map, n_sm, as_stream(stream)) : tc::lin_hl_launch_t<1>(a, map, n_sm, as_stream(stream));
+  CUtensorMap out_map = map;   // unused when no row is written as planes
+  if (hl_rows > 0) {
+    const int rows_pl = hl_rows < N ? hl_rows : N;
+    const cuuint64_t gdim[4] = {(cuuint64_t)HW, (cuuint64_t)rows_pl, (cuuint64_t)n_img, (cuuint64_t)planes};
+    const cuuint64_t gstr[3] = {(cuuint64_t)HW * 2, (cuuint64_t)a.out_img_stride * 2,
+                                (cuuint64_t)(planes == 2 ? out_plane_stride : a.out_img_stride * n_img) * 2};
+    const cuuint32_t box[4] = {32, 32, 1, (cuuint32_t)planes}, estr[4] = {1, 1, 1, 1};
+    CUresult cr = enc(&out_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(GNRF_ERR_CUDA, "lin_hl: cuTensorMapEncodeTiled(out) failed (%d)", (int)cr);
+  }
+  int rc = planes == 2 ? tc::lin_hl_launch_t<2>(a, map, out_map, n_sm, as_stream(stream))
+                       : tc::lin_hl_launch_t<1>(a, map, out_map, n_sm, as_stream(stream));
   if (rc != GNRF_OK) return rc;
   GNRF_LAUNCH_CHECK();
   count_launches(1);

@@ -201,9 +201,15 @@ class _HL:
                                            self.PL, pk.data_ptr(), self.o.st), "gnrf_lin_hl_pack")
         return pk
 
+    def bits(self, rows: int) -> torch.Tensor:
+        """ReLU sign bits of a [rows][P] activation: one bit per element (written by lin(sign_out=...), read by lin(mask=...))."""
+        return torch.empty((self.B, rows, self.P // 32), device=self.o.dev, dtype=torch.int32)
+
     def lin(self, pk, N, K, x: torch.Tensor, x_row0: int = 0, out: Optional[torch.Tensor] = None, out_row0: int = 0, hl_rows: Optional[int] = None,
-            out_f32: Optional[torch.Tensor] = None, act=0, bias_img=None, mask: Optional[torch.Tensor] = None, mask_rows: int = 0):
-        """x / out / mask: plane tensors, addressed from row x_row0 / out_row0 (row windows of a wider tensor keep its strides)."""
+            out_f32: Optional[torch.Tensor] = None, act=0, bias_img=None, mask: Optional[torch.Tensor] = None, mask_rows: int = 0,
+            sign_out: Optional[torch.Tensor] = None):
+        """x / out: plane tensors, addressed from row x_row0 / out_row0 (row windows of a wider tensor keep its strides);
+        mask / sign_out: bit tensors from bits()."""
         P = self.P
         hl_rows = N if hl_rows is None else hl_rows
         _lib.check(self.L.gnrf_lin_hl(
@@ -211,7 +217,9 @@ class _HL:
             act, (out.data_ptr() + out_row0 * P * 2) if out is not None else None, out.shape[2] * P if out is not None else 0,
             out.stride(0) if out is not None else 0, hl_rows, out_f32.data_ptr() if out_f32 is not None else None,
             out_f32.shape[1] * P if out_f32 is not None else 0, mask.data_ptr() if mask is not None else None,
-            mask.shape[2] * P if mask is not None else 0, mask_rows, self.B, P, self.o.st), "gnrf_lin_hl")
+            mask.shape[1] * (P // 32) if mask is not None else 0, mask_rows,
+            sign_out.data_ptr() if sign_out is not None else None, sign_out.shape[1] * (P // 32) if sign_out is not None else 0,
+            sign_out.shape[1] if sign_out is not None else 0, self.B, P, self.o.st), "gnrf_lin_hl")
 
     def wgrad(self, dy: torch.Tensor, N: int, x: torch.Tensor, K: int, db_mode: str, x_row0: int = 0):
         """-> dW [N][K], db ([B][N] for 'img', [N] for 'sum')."""
@@ -241,17 +249,18 @@ def _branch_forward_hl(o: _Ops, T: Sequence[torch.Tensor], B, n_r, n_s, H, C, ra
     _lib.check(L.gnrf_pe_fwd_hl(ray_dl.data_ptr(), tvecs.data_ptr(), z_edges.data_ptr(), B, n_r, n_s, pe32.data_ptr(), PE * P,
                                 buf0.data_ptr() + H * P * 2, (H + 64) * P, buf0.stride(0), planes, o.st), "gnrf_pe_fwd_hl")
     h: List[Optional[torch.Tensor]] = [None] * 8
+    sg = [q.bits(H) for _ in range(8)]     # ReLU sign bits of the eight hidden activations (1 bit per element) for the backward
     h[0] = q.empty(H)
-    q.lin(q.pack(T[0], None, H, PE), H, PE, buf0, x_row0=H, out=h[0], act=RELU, bias_img=T[1])
+    q.lin(q.pack(T[0], None, H, PE), H, PE, buf0, x_row0=H, out=h[0], act=RELU, bias_img=T[1], sign_out=sg[0])
     for i in (1, 2, 3):
         h[i] = q.empty(H)
-        q.lin(q.pack(T[2 * i], T[2 * i + 1], H, H), H, H, h[i - 1], out=h[i], act=RELU)
-    q.lin(q.pack(T[8], T[9], H, H), H, H, h[3], out=buf0, act=RELU)                                   # layer 4 -> buf0 rows [0,H)
+        q.lin(q.pack(T[2 * i], T[2 * i + 1], H, H), H, H, h[i - 1], out=h[i], act=RELU, sign_out=sg[i])
+    q.lin(q.pack(T[8], T[9], H, H), H, H, h[3], out=buf0, act=RELU, sign_out=sg[4])                   # layer 4 -> buf0 rows [0,H)
     h[5] = q.empty(H)
-    q.lin(q.pack(T[10], None, H, H + PE), H, H + PE, buf0, out=h[5], act=RELU, bias_img=T[11])
+    q.lin(q.pack(T[10], None, H, H + PE), H, H + PE, buf0, out=h[5], act=RELU, bias_img=T[11], sign_out=sg[5])
     for i, k in ((6, 12), (7, 14)):
         h[i] = q.empty(H)
-        q.lin(q.pack(T[k], T[k + 1], H, H), H, H, h[i - 1], out=h[i], act=RELU)
+        q.lin(q.pack(T[k], T[k + 1], H, H), H, H, h[i - 1], out=h[i], act=RELU, sign_out=sg[i])
     r0 = q.empty(H)                        # RGB_layer_0 output (planes) ...
     sig = o.empty(B, 1, P)                 # ... and the raw density (row H of the same GEMM) in fp32 for the composite
     q.lin(q.pack(T[16], T[17], H + 1, H), H + 1, H, h[7], out=r0, hl_rows=H, out_f32=sig, act=NONE)
@@ -262,8 +271,8 @@ def _branch_forward_hl(o: _Ops, T: Sequence[torch.Tensor], B, n_r, n_s, H, C, ra
                                        Hc.data_ptr(), bg_alpha.data_ptr(), w.data_ptr(), o.st), "gnrf_composite_cm_fwd")
     feat = o.empty(B, C, n_r)
     o.conv(o.pack(T[20], None, C, H2 + 1), C, H2 + 1, Hc.data_ptr(), 0, feat.data_ptr(), 0, B, n_r, act=NONE)
-    return {"buf0": buf0, "pe32": pe32, "h": h, "r0": r0, "sig": sig, "hc": hc, "Hc": Hc, "bg_alpha": bg_alpha, "w": w, "feat": feat,
-            "planes": planes}
+    return {"buf0": buf0, "pe32": pe32, "h": h, "sg": sg, "r0": r0, "sig": sig, "hc": hc, "Hc": Hc, "bg_alpha": bg_alpha, "w": w,
+            "feat": feat, "planes": planes}
 
 
 def _branch_backward_hl(o: _Ops, T: Sequence[torch.Tensor], sv: Dict[str, torch.Tensor], B, n_r, n_s, H, C, ray_dl, z_edges, g_feat, g_alpha,
@@ -273,7 +282,7 @@ def _branch_backward_hl(o: _Ops, T: Sequence[torch.Tensor], sv: Dict[str, torch.
     H2 = H // 2
     planes = sv["planes"]
     q = _HL(o, planes, B, P)
-    buf0, h, r0, hc, Hc, w, sig = sv["buf0"], sv["h"], sv["r0"], sv["hc"], sv["Hc"], sv["w"], sv["sig"]
+    buf0, h, r0, hc, Hc, w, sig, sg = sv["buf0"], sv["h"], sv["r0"], sv["hc"], sv["Hc"], sv["w"], sv["sig"], sv["sg"]
     g: List[Optional[torch.Tensor]] = [None] * N_BRANCH_T
     g[20], _ = o.wgrad(g_feat.data_ptr(), 0, Hc.data_ptr(), 0, C, H2 + 1, B, n_r, "none")
     g_Hc = o.empty(B, H2 + 1, n_r)
@@ -290,26 +299,26 @@ def _branch_backward_hl(o: _Ops, T: Sequence[torch.Tensor], sv: Dict[str, torch.
     # RGB_layer_0 + density_module on h7
     g[16], g[17] = q.wgrad(g_r0, H + 1, h[7], H, "sum")
     ga = q.empty(H)
-    q.lin(q.pack(T[16], None, H, H + 1, transposed=True), H, H + 1, g_r0, out=ga, mask=h[7])
+    q.lin(q.pack(T[16], None, H, H + 1, transposed=True), H, H + 1, g_r0, out=ga, mask=sg[7])
     del g_r0
     for i, k in ((7, 14), (6, 12)):
         g[k], g[k + 1] = q.wgrad(ga, H, h[i - 1], H, "sum")
         gb = q.empty(H)
-        q.lin(q.pack(T[k], None, H, H, transposed=True), H, H, ga, out=gb, mask=h[i - 1])
+        q.lin(q.pack(T[k], None, H, H, transposed=True), H, H, ga, out=gb, mask=sg[i - 1])
         ga = gb
     # skip layer 5: operand [h4 | PE] = rows [0, H+63) of buf0; its input gradient: rows < H (h4, masked) as planes, PE rows fp32
     g[10], g[11] = q.wgrad(ga, H, buf0, H + PE, "img")
     g4, g_pe_b = q.empty(H), o.empty(B, PE, P)
-    q.lin(q.pack(T[10], None, H + PE, H, transposed=True), H + PE, H, ga, out=g4, hl_rows=H, out_f32=g_pe_b, mask=buf0, mask_rows=H)
+    q.lin(q.pack(T[10], None, H + PE, H, transposed=True), H + PE, H, ga, out=g4, hl_rows=H, out_f32=g_pe_b, mask=sg[4], mask_rows=H)
     # layer 4
     g[8], g[9] = q.wgrad(g4, H, h[3], H, "sum")
     ga = q.empty(H)
-    q.lin(q.pack(T[8], None, H, H, transposed=True), H, H, g4, out=ga, mask=h[3])
+    q.lin(q.pack(T[8], None, H, H, transposed=True), H, H, g4, out=ga, mask=sg[3])
     del g4
     for i in (3, 2, 1):
         g[2 * i], g[2 * i + 1] = q.wgrad(ga, H, h[i - 1], H, "sum")
         gb = q.empty(H)
-        q.lin(q.pack(T[2 * i], None, H, H, transposed=True), H, H, ga, out=gb, mask=h[i - 1])
+        q.lin(q.pack(T[2 * i], None, H, H, transposed=True), H, H, ga, out=gb, mask=sg[i - 1])
         ga = gb
     # layer 0 on the positional encoding
     g[0], g[1] = q.wgrad(ga, H, buf0, PE, "img", x_row0=H)

@@ -240,17 +240,20 @@ int gnrf_composite_cm_bwd(const float* g_Hc, const float* g_bg_alpha, const floa
  * pass).  A plane tensor holds x as hi = bf16(x) [and lo = bf16(x - hi), `plane_stride` elements after hi]: [planes][img][rows][HW],
  * points contiguous; planes = 2 is the bf16x3 scheme of the kernels above, planes = 1 single-pass bf16 (half the bytes; gradient
  * tolerance stated in tests/test_train_grad.py).  All strides in ELEMENTS (bf16 or float); HW a multiple of 256, K >= 32.
- *   gnrf_lin_hl:  y[img][n][p] = act( sum_k W[n][k] x[img][k][p] + bias[n] + bias_img[img][n] ) * (mask[img][n][p] > 0 for n < mask_rows)
- *     rows n < hl_rows are written as planes to `out`, rows n >= hl_rows as fp32 to out_f32[img][n - hl_rows][p] (for the non-GEMM
- *     consumers: composite, positional-encoding backward).  mask = hi plane of a saved post-ReLU activation (input gradient).
+ *   gnrf_lin_hl:  y[img][n][p] = act( sum_k W[n][k] x[img][k][p] + bias[n] + bias_img[img][n] ) * mask_bit[img][n][p] (n < mask_rows)
+ *     rows n < hl_rows (a multiple of 32, or >= N) are written as planes to `out`, rows n >= hl_rows as fp32 to
+ *     out_f32[img][n - hl_rows][p] (for the non-GEMM consumers: composite, positional-encoding backward).
+ *     mask_out (nullable): uint32 [img][rows][HW/32], bit (p % 32) of word p/32 = (y > 0) -- the ReLU sign bits the input gradient of
+ *     the NEXT layer needs; mask_bits (nullable): such a tensor, applied to this call's output (input-gradient use).  Mask strides
+ *     in 32-bit words.
  *   gnrf_wgrad_hl: dW[n][k] = sum_img sum_p dY[img][n][p] X[img][k][p]; db as in gnrf_wgrad_tc.  N >= 128, HW a multiple of 32.
  *   gnrf_pe_fwd_hl: gnrf_pe_fwd that also writes the encoding as planes; gnrf_composite_cm_bwd_hl: g_h / g_sigma as planes. */
 size_t gnrf_lin_hl_packed_bytes(int N, int K, int planes);
 int gnrf_lin_hl_pack(const float* W, const float* bias, int N, int K, int transposed, int planes, void* packed, gnrf_stream_t stream);
 int gnrf_lin_hl(const void* packed, int N, int K, int planes, const void* X, long long x_img_stride, long long x_plane_stride,
                 const float* bias_img, int act, void* out, long long out_img_stride, long long out_plane_stride, int hl_rows,
-                float* out_f32, long long f32_img_stride, const void* mask, long long mask_img_stride, int mask_rows, int n_img,
-                int HW, gnrf_stream_t stream);
+                float* out_f32, long long f32_img_stride, const void* mask_bits, long long mask_img_stride, int mask_rows,
+                void* mask_out, long long mask_out_img_stride, int mask_out_rows, int n_img, int HW, gnrf_stream_t stream);
 size_t gnrf_wgrad_hl_workspace_bytes(int N, int K, int n_img, int HW);
 int gnrf_wgrad_hl(const void* dY, long long dy_img_stride, long long dy_plane_stride, const void* X, long long x_img_stride,
                   long long x_plane_stride, int planes, int N, int K, int n_img, int HW, float* dW, float* db, int db_sum,

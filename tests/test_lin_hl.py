@@ -37,7 +37,15 @@ def _w_eff(W: torch.Tensor, planes: int) -> torch.Tensor:
     return hi.double() + lo.double()
 
 
-def _lin(L, W, bias, x_pl, planes, n_img, HW, act=0, bias_img=None, hl_rows=None, mask_pl=None, mask_rows=0, transposed=False):
+def _bits(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [img][rows][HW] -> int32 [img][rows][HW/32]: bit (p % 32) of word p / 32 = x > 0."""
+    b = (x > 0).reshape(*x.shape[:-1], x.shape[-1] // 32, 32).to(torch.int64)
+    w = (b << torch.arange(32, device=x.device)).sum(-1)
+    return (w - ((w >> 31) << 32)).to(torch.int32).contiguous()
+
+
+def _lin(L, W, bias, x_pl, planes, n_img, HW, act=0, bias_img=None, hl_rows=None, mask_bits=None, mask_rows=0, transposed=False,
+         sign_out=None):
     from gazenerf_b200 import _lib
     dev = x_pl.device
     st = torch.cuda.current_stream().cuda_stream
@@ -52,8 +60,11 @@ def _lin(L, W, bias, x_pl, planes, n_img, HW, act=0, bias_img=None, hl_rows=None
     _lib.check(L.gnrf_lin_hl(pk.data_ptr(), N, K, planes, x_pl.data_ptr(), K_rows * HW, x_pl.stride(0),
                              bias_img.data_ptr() if bias_img is not None else None, act,
                              out.data_ptr(), out.shape[2] * HW, out.stride(0), hl_rows, out32.data_ptr(), out32.shape[1] * HW,
-                             mask_pl.data_ptr() if mask_pl is not None else None, mask_pl.shape[2] * HW if mask_pl is not None else 0,
-                             mask_rows, n_img, HW, st), "gnrf_lin_hl")
+                             mask_bits.data_ptr() if mask_bits is not None else None,
+                             mask_bits.shape[1] * (HW // 32) if mask_bits is not None else 0, mask_rows,
+                             sign_out.data_ptr() if sign_out is not None else None,
+                             sign_out.shape[1] * (HW // 32) if sign_out is not None else 0, sign_out.shape[1] if sign_out is not None else 0,
+                             n_img, HW, st), "gnrf_lin_hl")
     torch.cuda.synchronize()
     return out, out32
 
@@ -71,11 +82,13 @@ def test_lin_hl_forward(planes, N, K, HW, n_img, act):
     bimg = (0.1 * torch.randn(n_img, N, generator=g)).to(dev)
     x = torch.randn(n_img, K, HW, generator=g).to(dev)
     x_pl = _planes(x, planes)
-    out, _ = _lin(L, W, b, x_pl, planes, n_img, HW, act=act, bias_img=bimg)
+    sign = torch.full((n_img, N, HW // 32), 0x55555555, device=dev, dtype=torch.int32)
+    out, _ = _lin(L, W, b, x_pl, planes, n_img, HW, act=act, bias_img=bimg, sign_out=sign)
     ref = torch.einsum("nk,ikp->inp", _w_eff(W, planes), _value(x_pl)) + b.double()[None, :, None] + bimg.double()[:, :, None]
     if act:
         ref = ref.clamp_min(0)
     assert torch.isfinite(out.float()).all()
+    assert torch.equal(sign, _bits(out[0].float()))   # the sign bits describe exactly what was stored
     err = _rel(_value(out), ref)
     assert err < (3e-5 if planes == 2 else 4e-3), err
     if planes == 2:   # the lo plane is the bf16 rounding of the residual: |lo| <= ulp(hi)/2
@@ -107,8 +120,7 @@ def test_lin_hl_fp32_rows_and_mask(planes):
     gy_pl = _planes(torch.randn(n_img, 384, HW, generator=g).to(dev), planes)
     saved = torch.randn(n_img, 448, HW, generator=g).clamp_min(0).to(dev)
     saved[:, :, ::7] = 0.0
-    saved_pl = _planes(saved, planes)
-    out, out32 = _lin(L, Wf, None, gy_pl, planes, n_img, HW, hl_rows=384, mask_pl=saved_pl, mask_rows=384, transposed=True)
+    out, out32 = _lin(L, Wf, None, gy_pl, planes, n_img, HW, hl_rows=384, mask_bits=_bits(saved), mask_rows=384, transposed=True)
     ref = torch.einsum("nk,inp->ikp", _w_eff(Wf, planes), _value(gy_pl))
     ref_m = ref[:, :384] * (saved[:, :384] > 0)
     assert _rel(_value(out), ref_m) < (3e-5 if planes == 2 else 4e-3)
@@ -158,7 +170,7 @@ def test_lin_hl_strided_views():
     _lib.check(L.gnrf_lin_hl_pack(W.data_ptr(), None, H, PE, 0, 2, pk.data_ptr(), st), "pack")
     x_ptr = buf.data_ptr() + H * HW * 2
     _lib.check(L.gnrf_lin_hl(pk.data_ptr(), H, PE, 2, x_ptr, (H + 64) * HW, buf.stride(0), None, 1, buf.data_ptr(), (H + 64) * HW,
-                             buf.stride(0), H, None, 0, None, 0, 0, n_img, HW, st), "gnrf_lin_hl")
+                             buf.stride(0), H, None, 0, None, 0, 0, None, 0, 0, n_img, HW, st), "gnrf_lin_hl")
     torch.cuda.synchronize()
     ref = torch.einsum("nk,ikp->inp", _w_eff(W, 2), _value(_planes(pe, 2))).clamp_min(0)
     assert _rel(_value(buf[:, :, :H]), ref) < 3e-5
