@@ -371,6 +371,7 @@ def run_train(env, steps, warmup, F, with_e2e=True, graph=True, precision="bf16x
         "unit": "faces/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"bf16x3": "bf16x3 split (fp32 accumulate) on tensor cores for every GEMM (forward, dX, dW): per-point activations stored pre-split as bf16 hi/lo planes; f32 elsewhere",
+                  "mixed": "forward: bf16x3 split on pre-split bf16 hi/lo planes (as the default); backward (dX, dW of the per-point MLP layers): single-pass bf16 on one bf16 plane per gradient tensor; neural renderer bf16x3; f32 elsewhere",
                   "bf16": "single-pass bf16 (fp32 accumulate) for the per-point MLP GEMMs on one bf16 activation plane; bf16x3 for the neural renderer; f32 elsewhere",
                   "f32": "bf16x3 split (fp32 accumulate) on tensor cores for every GEMM, fp32 activations re-split in-kernel (r1 path); f32 elsewhere"}[precision],
         "data": "synthetic",
@@ -675,7 +676,7 @@ def main():
     ap.add_argument("--workload", default="render", choices=["render", "train", "hier", "c0"])
     ap.add_argument("--no-graph", action="store_true", help="render workloads: eager launches instead of replaying the forward (incl. the fused "
                     "all-gather at N > 1) from a captured CUDA graph (net.graphed)")
-    ap.add_argument("--train-precision", default="bf16x3", choices=["bf16x3", "bf16", "f32"],
+    ap.add_argument("--train-precision", default="bf16x3", choices=["bf16x3", "mixed", "bf16", "f32"],
                     help="train workload: storage of the per-point MLP activations (gazenerf_b200/train.py)")
     ap.add_argument("--no-train-graph", action="store_true", help="train workload: eager launches instead of the captured step (GraphedTrainStep)")
     args = ap.parse_args()
@@ -715,7 +716,9 @@ def main():
             aux = {}
             for name, fn in (("hier", lambda: run_render(env, args, 5, 3, 1, workload="hier", with_e2e=False)),
                              ("c0", lambda: run_render(env, args, 5, 3, 1, workload="c0", with_e2e=False)),
-                             ("train", lambda: run_train(env, 5, 3, 2, with_e2e=False, graph=not args.no_train_graph))):
+                             ("train", lambda: run_train(env, 5, 3, 2, with_e2e=False, graph=not args.no_train_graph)),
+                             ("train_mixed", lambda: run_train(env, 5, 3, 2, with_e2e=False, graph=not args.no_train_graph,
+                                                               precision="mixed"))):
                 try:
                     r = fn()
                     aux[name] = {k: r[k] for k in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "dtype", "config", "roofline",

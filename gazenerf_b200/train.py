@@ -11,8 +11,9 @@ two Functions: FeatureMapFn (rays -> feature maps) and NeuralRenderFn (feature m
 
 Per-point activations of the radiance MLPs are stored PRE-SPLIT as bf16 planes (hi | lo, csrc/lin_hl.cu) so that the GEMM kernels
 feed them to the tensor cores straight from TMA: ``net.train_precision`` = "bf16x3" (default: hi + lo planes, the bf16x3 scheme of
-the inference kernel), "bf16" (hi plane only: single-pass bf16, what BASELINE config[4] names; half the bytes, a third of the
-MMAs, gradient tolerance stated in tests/test_train_grad.py) or "f32" (r1 path: fp32 activations re-split inside conv_tc.cu /
+the inference kernel), "mixed" (forward as "bf16x3" -- images and loss identical to it -- but every GRADIENT tensor stored as one
+bf16 plane and both backward GEMMs single-pass on the hi planes), "bf16" (hi plane only everywhere: single-pass bf16, what BASELINE
+config[4] names; half the bytes, a third of the MMAs; tolerances of both in tests/test_train_grad.py) or "f32" (r1 path: fp32 activations re-split inside conv_tc.cu /
 wgrad_tc.cu; also taken automatically when a shape is outside the plane kernels' tiling: points % 256, hidden width < 256).
 
 Exact rewrites used (identities of the reference graph, as in the inference kernel):
@@ -272,15 +273,17 @@ def _branch_forward_hl(o: _Ops, T: Sequence[torch.Tensor], B, n_r, n_s, H, C, ra
     feat = o.empty(B, C, n_r)
     o.conv(o.pack(T[20], None, C, H2 + 1), C, H2 + 1, Hc.data_ptr(), 0, feat.data_ptr(), 0, B, n_r, act=NONE)
     return {"buf0": buf0, "pe32": pe32, "h": h, "sg": sg, "r0": r0, "sig": sig, "hc": hc, "Hc": Hc, "bg_alpha": bg_alpha, "w": w,
-            "feat": feat, "planes": planes}
+            "feat": feat, "planes": planes, "planes_bwd": planes}
 
 
 def _branch_backward_hl(o: _Ops, T: Sequence[torch.Tensor], sv: Dict[str, torch.Tensor], B, n_r, n_s, H, C, ray_dl, z_edges, g_feat, g_alpha,
                         g_m, g_o, g_z, g_l) -> List[torch.Tensor]:
-    """_branch_backward on plane tensors: every output / input gradient that feeds a GEMM is written as planes by its producer."""
+    """_branch_backward on plane tensors: every output / input gradient that feeds a GEMM is written as planes by its producer.
+    sv["planes_bwd"] = 1 with 2-plane saved activations is the "mixed" mode: gradients are stored as one bf16 plane and both
+    backward GEMMs run single-pass on the hi planes (the saved activations' hi plane is plane 0 of the same tensor)."""
     L, P = o.L, n_r * n_s
     H2 = H // 2
-    planes = sv["planes"]
+    planes = sv["planes_bwd"]
     q = _HL(o, planes, B, P)
     buf0, h, r0, hc, Hc, w, sig, sg = sv["buf0"], sv["h"], sv["r0"], sv["hc"], sv["Hc"], sv["w"], sv["sig"], sv["sg"]
     g: List[Optional[torch.Tensor]] = [None] * N_BRANCH_T
@@ -343,12 +346,13 @@ class FeatureMapFn(torch.autograd.Function):
         Tf, Te = T[:N_BRANCH_T], T[N_BRANCH_T:2 * N_BRANCH_T]
         ray_dl = o.empty(B, n_r, 4)
         _lib.check(L.gnrf_ray_setup(xy.data_ptr(), rmats.data_ptr(), kinv.data_ptr(), B, n_r, ray_dl.data_ptr(), o.st), "gnrf_ray_setup")
-        planes = {"bf16x3": 2, "bf16": 1, "f32": 0}[cfg.get("precision", "bf16x3")]
+        planes, planes_bwd = {"bf16x3": (2, 2), "mixed": (2, 1), "bf16": (1, 1), "f32": (0, 0)}[cfg.get("precision", "bf16x3")]
         if planes and not hl_supported(H, n_r * n_s):
             planes = 0
         if planes:
             sv_f = _branch_forward_hl(o, Tf, B, n_r, n_s, H, C, ray_dl, tvecs, z_edges, planes)
             sv_e = _branch_forward_hl(o, Te, B, n_r, n_s, H, C, ray_dl, tvecs, z_edges, planes)
+            sv_f["planes_bwd"] = sv_e["planes_bwd"] = planes_bwd
         else:
             sv_f = _branch_forward(o, Tf, B, n_r, n_s, H, C, ray_dl, tvecs, z_edges)
             sv_e = _branch_forward(o, Te, B, n_r, n_s, H, C, ray_dl, tvecs, z_edges)
