@@ -57,7 +57,9 @@ __global__ void pe_cm_fwd_kernel(const float4* __restrict__ ray_dl, const float*
 
 // One warp per ray.  g_x = g_pe[c] + sum_q 2^q (g_sin cos - g_cos sin)   (two gradient sources: layer 0 and the skip layer),
 // then  g_z[k] += g_x . m,  g_m += sum_k g_x z_k,  g_o += sum_k g_x     with m = d*l.
-__global__ void pe_cm_bwd_kernel(const float* __restrict__ g_a, long long ga_stride, const float* __restrict__ g_b, long long gb_stride,
+// (register-capped: fully unrolled it used 255 registers = one 256-thread block per SM, 4 % issue utilisation, 475 us; the loads of one
+// frequency pair are enough to keep 8 blocks per SM busy)
+__global__ void __launch_bounds__(256, 4) pe_cm_bwd_kernel(const float* __restrict__ g_a, long long ga_stride, const float* __restrict__ g_b, long long gb_stride,
                                  const float* __restrict__ pe, long long pe_stride, const float4* __restrict__ ray_dl,
                                  const float* __restrict__ z_edges, int B, int N_r, int N_s, float* __restrict__ g_m,
                                  float* __restrict__ g_o, float* __restrict__ g_z) {
@@ -81,7 +83,7 @@ __global__ void pe_cm_bwd_kernel(const float* __restrict__ g_a, long long ga_str
     for (int c = 0; c < 3; ++c) {
       float gx = G(c);
       float f = 1.0f;
-#pragma unroll
+#pragma unroll 2
       for (int q = 0; q < 10; ++q) {
         const float sv = pp[(size_t)(3 + 6 * q + c) * P], cv = pp[(size_t)(6 + 6 * q + c) * P];
         gx += f * (G(3 + 6 * q + c) * cv - G(6 + 6 * q + c) * sv);
@@ -184,6 +186,7 @@ composite_cm_bwd_kernel(const float* __restrict__ g_Hc, const float* __restrict_
   for (int k = lane; k < N_s; k += 32) {
     float acc = 0.0f;
     const float wk = s_w[k];
+#pragma unroll 4
     for (int c = warp; c < C; c += 8) {
       const float hv = hb[(size_t)c * P + k];
       const float g = s_g[c];
@@ -400,6 +403,45 @@ __device__ __forceinline__ float up2_coef(int i, int j, int n) {
   const int other = (i & 1) ? min(a + 1, n - 1) : max(a - 1, 0);
   return (a == j ? 0.75f : 0.0f) + (other == j ? 0.25f : 0.0f);
 }
+// Same operator in separable form for W % 32 == 0 and H % rows_per == 0: one warp walks a 32-pixel column strip down rows_per rows,
+// neighbours along x through warp shuffles (+ one halo load on the two edge lanes), three horizontally-adjointed rows kept in
+// registers.  Adjoint taps of the reflect-padded [1,2,1] along an axis of length n at position j: the neighbour j-1 contributes with
+// weight 2 when it is border row 0 (which reads its inner neighbour twice), else 1; likewise j+1 = n-1.  2 loads per pixel
+// instead of 18, no 64-bit index arithmetic (the thread-per-pixel kernel above ran at 0.8 TB/s).
+__global__ void __launch_bounds__(256) blur_adj_strip_kernel(const float* __restrict__ g_out, const float* __restrict__ act, float slope,
+                                                             int H, int Wd, int rows_per, float* __restrict__ g_in) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x = ((int)blockIdx.x * ((int)blockDim.x >> 5) + warp) * 32 + lane;
+  if (x - lane >= Wd) return;
+  const int y0 = (int)blockIdx.y * rows_per;
+  const size_t base = (size_t)blockIdx.z * H * Wd;
+  const float wxm = x >= 1 ? (x == 1 ? 2.0f : 1.0f) : 0.0f;
+  const float wxp = x <= Wd - 2 ? (x == Wd - 2 ? 2.0f : 1.0f) : 0.0f;
+  auto masked = [&](size_t o) {
+    float m = g_out[o];
+    if (act != nullptr && !(act[o] > 0.0f)) m *= slope;
+    return m;
+  };
+  auto hrow = [&](int yy) -> float {   // yy is warp-uniform
+    if (yy < 0 || yy >= H) return 0.0f;
+    const size_t o = base + (size_t)yy * Wd + x;
+    const float m = masked(o);
+    float l = __shfl_up_sync(0xffffffffu, m, 1), r = __shfl_down_sync(0xffffffffu, m, 1);
+    if (lane == 0 && x > 0) l = masked(o - 1);
+    if (lane == 31 && x < Wd - 1) r = masked(o + 1);
+    return fmaf(wxm, l, fmaf(wxp, r, 2.0f * m));
+  };
+  float hm = hrow(y0 - 1), h0 = hrow(y0);
+  for (int y = y0; y < y0 + rows_per; ++y) {
+    const float hp = hrow(y + 1);
+    const float wym = y >= 1 ? (y == 1 ? 2.0f : 1.0f) : 0.0f;
+    const float wyp = y <= H - 2 ? (y == H - 2 ? 2.0f : 1.0f) : 0.0f;
+    g_in[base + (size_t)y * Wd + x] = fmaf(wym, hm, fmaf(wyp, hp, 2.0f * h0)) * 0.0625f;
+    hm = h0;
+    h0 = hp;
+  }
+}
+
 // g_in [planes][H][W] = Up2^T g_out [planes][2H][2W]
 __global__ void up2_adj_kernel(const float* __restrict__ g_out, int H, int Wd, long long total, float* __restrict__ g_in) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -433,13 +475,13 @@ __global__ void sigmoid_bwd_kernel(const float* __restrict__ g_img, const float*
 //   g_res[n][c][h][w] = sum over the four j == c (mod ci) of the un-shuffled gradient.
 __global__ void psu_bwd_kernel(const float* __restrict__ g_sh, const float* __restrict__ sh, const float* __restrict__ x, int ci, int H,
                                int Wd, long long total, float* __restrict__ g_pre, float* __restrict__ g_res) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;   // total = N * ci * H * W
-  const int w = (int)(idx % Wd);
-  const int h = (int)((idx / Wd) % H);
-  const int c = (int)((idx / ((long long)Wd * H)) % ci);
-  const int n = (int)(idx / ((long long)Wd * H * ci));
+  // grid.y = n * ci + c, grid.x * 256 threads = the H * W pixels of that plane (32-bit index arithmetic only)
+  const int pix = (int)blockIdx.x * (int)blockDim.x + (int)threadIdx.x;
+  if (pix >= H * Wd) return;
+  const int h = pix / Wd, w = pix - h * Wd;
+  const int n = (int)blockIdx.y / ci, c = (int)blockIdx.y - n * ci;
   const size_t HW = (size_t)H * Wd;
+  const size_t idx = (size_t)blockIdx.y * HW + (size_t)pix;
   float acc = 0.0f;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -571,7 +613,14 @@ extern "C" int gnrf_compose_bwd(const float* g_out, const float* feat_face, cons
 namespace gnrf {
 int launch_blur_adj(const float* g_out, const float* act, float slope, int planes, int H, int Wd, float* g_in, cudaStream_t st) {
   const long long total = (long long)planes * H * Wd;
-  blur_adj_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g_out, act, slope, H, Wd, total, g_in);
+  constexpr int kRows = 32;
+  if (Wd % 32 == 0 && H % kRows == 0 && Wd >= 3 && H >= 3 && planes <= 65535) {
+    const int strips = Wd / 32, wpb = strips < 8 ? strips : 8;
+    dim3 grid((unsigned)((strips + wpb - 1) / wpb), (unsigned)(H / kRows), (unsigned)planes);
+    blur_adj_strip_kernel<<<grid, 32 * wpb, 0, st>>>(g_out, act, slope, H, Wd, kRows, g_in);
+  } else {
+    blur_adj_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g_out, act, slope, H, Wd, total, g_in);
+  }
   count_launches(1);
   return GNRF_OK;
 }
@@ -589,7 +638,8 @@ int launch_sigmoid_bwd(const float* g_img, const float* img, long long total, fl
 int launch_psu_bwd(const float* g_sh, const float* sh, const float* x, int N, int ci, int H, int Wd, float* g_pre, float* g_res,
                    cudaStream_t st) {
   const long long total = (long long)N * ci * H * Wd;
-  psu_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g_sh, sh, x, ci, H, Wd, total, g_pre, g_res);
+  if ((long long)N * ci > 65535) return fail(GNRF_ERR_UNSUPPORTED, "psu_bwd: N * ci = %lld exceeds the grid", (long long)N * ci);
+  psu_bwd_kernel<<<dim3((unsigned)((H * Wd + 255) / 256), (unsigned)(N * ci)), 256, 0, st>>>(g_sh, sh, x, ci, H, Wd, total, g_pre, g_res);
   count_launches(1);
   return GNRF_OK;
 }
