@@ -5,7 +5,7 @@ import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(ROOT, "gazenerf_b200", "libgnrf.so")
 out = subprocess.run(["cuobjdump", "-sass", lib], stdout=subprocess.PIPE, text=True).stdout
-OPS = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UBLKCP", "SYNCS", "UTCATOMSWS", "ELECT", "MULTIMEM", "STG.E.128.STRONG.SYS", "HMMA", "FFMA"]
+OPS = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "UTCATOMSWS", "ELECT", "MULTIMEM", "STG.E.128.STRONG.SYS", "HMMA", "FFMA"]
 kern, counts, total = None, collections.OrderedDict(), {}
 for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
@@ -33,8 +33,8 @@ def demangle(n):
         return n
 print("# r2 — SASS opcode histogram of `gazenerf_b200/libgnrf.so` (`cuobjdump -sass`, sm_100a)\n")
 print("`UTCHMMA` = tcgen05.mma, `LDTM`/`STTM` = tcgen05.ld/st (TMEM), `UBLKCP` = cp.async.bulk (TMA bulk copy; `.MULTICAST` = cluster multicast),")
-print("`UTMALDG` = cp.async.bulk.tensor (tensor-map TMA), `UTCBAR` = tcgen05.commit -> mbarrier, `SYNCS` = mbarrier ops, `ELECT` = elect.sync.\n")
-cols = ["UTCHMMA", "LDTM", "STTM", "UBLKCP", "UBLKCP.MULTICAST", "UTMALDG", "UTCBAR", "SYNCS", "ELECT", "FFMA"]
+print("`UTMALDG` / `UTMASTG` = cp.async.bulk.tensor load / store (tensor-map TMA), `UTCBAR` = tcgen05.commit -> mbarrier, `SYNCS` = mbarrier ops, `ELECT` = elect.sync.\n")
+cols = ["UTCHMMA", "LDTM", "STTM", "UBLKCP", "UBLKCP.MULTICAST", "UTMALDG", "UTMASTG", "UTCBAR", "SYNCS", "ELECT", "FFMA"]
 print("| kernel | SASS instr | " + " | ".join(cols) + " |\n|---|---:|" + "---:|" * len(cols))
 for k, c in counts.items():
     if total[k] < 50:
