@@ -264,12 +264,15 @@ __global__ void __launch_bounds__(kLhThreads, 1) lin_hl_kernel(const LinArgs arg
             for (int k16 = 0; k16 < 2; ++k16) {
               const uint64_t b_hi = mk((((sb + (uint32_t)(k16 * 2048)) >> 4) & 0x3FFFu) | kBLoFlags, kBHi);
               const uint64_t a_hi = mk((((sb + (uint32_t)(C::kWOff + k16 * 4096)) >> 4) & 0x3FFFu) | kALoFlags, kAHi);
-              umma_ss(d, a_hi, b_hi, idesc, (kb == 0 && k16 == 0) ? 0u : 1u);
               if (PL == 2) {
+                // W_hi feeds two consecutive UMMAs from the tensor core's A collector (one smem read of the 4 KB slice instead of two)
                 const uint64_t b_lo = mk((((sb + (uint32_t)(4096 + k16 * 2048)) >> 4) & 0x3FFFu) | kBLoFlags, kBHi);
                 const uint64_t a_lo = mk((((sb + (uint32_t)(C::kWOff + kLhWPlane + k16 * 4096)) >> 4) & 0x3FFFu) | kALoFlags, kAHi);
+                umma_ss_a_fill(d, a_hi, b_hi, idesc, (kb == 0 && k16 == 0) ? 0u : 1u);
+                umma_ss_a_lastuse(d, a_hi, b_lo, idesc, 1u);
                 umma_ss(d, a_lo, b_hi, idesc, 1u);
-                umma_ss(d, a_hi, b_lo, idesc, 1u);
+              } else {
+                umma_ss(d, a_hi, b_hi, idesc, (kb == 0 && k16 == 0) ? 0u : 1u);
               }
             }
             umma_commit(bar(C::kBarEmpty + s));
