@@ -374,32 +374,42 @@ def test_config4_full_size_feature_map_gradients_vs_oracle_autograd(dev):
     tvals = torch.linspace(0.0, 1.0, n_s + 1).to(dev)
     _lib.check(L.gnrf_coarse_depths(tv.detach().contiguous().data_ptr(), tvals.data_ptr(), ju_d.data_ptr(), B, S * S, n_s, 2.5, -3.5, z_edges.data_ptr(),
                                     torch.cuda.current_stream().cuda_stream))
-    shape_ext = torch.cat([dl["shape_code"], dl["gaze_code"]], 1)
-    fm = render_featmaps(net, xy, rm, tv, kinv, dl["gaze_code"], shape_ext, dl["appea_code"], z_edges)
-    assert fm.shape == (3 * B + 1, C, S, S)
-    got_sub = fm[:3 * B].detach().reshape(3 * B, C, S * S)[:, :, rays].cpu()
-    assert max_rel(got_sub, fm_ref.detach()) < TOL_TIGHT
-    cot = torch.zeros(3 * B + 1, C, S * S)
-    cot[:3 * B, :, rays] = cot_sub
-    fm.backward(cot.view(3 * B + 1, C, S, S).to(dev))
-    torch.cuda.synchronize()
-    # ---- compare: relative L2 per tensor, 5e-3 (ReLU / max decisions within ~1e-5 of zero flip; see tests/test_train_grad.py header)
-    errs = {}
-    for k, p in net.named_parameters():
-        ref = sd[k].grad
-        if ref is None or float(ref.abs().max()) == 0.0:
-            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
-            continue
-        errs[k] = rel_l2(p.grad.cpu(), ref)
-    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
-    print("full-size feature-map cotangent: worst parameter-gradient rel-L2 vs oracle autograd:", worst)
-    assert len(errs) >= 49 and all((v < (2e-2 if sd[k].numel() == 1 else 5e-3)) for k, v in errs.items()), worst
-    gin = {k: rel_l2(dl[k].grad.cpu(), leaves[k].grad) for k in leaves}
-    print("input-gradient rel-L2:", gin)
-    for k in ("shape_code", "appea_code"):
-        assert gin[k] < 5e-3, (k, gin[k])
-    for k in ("gaze_code", "batch_Rmats", "batch_Tvecs"):
-        assert gin[k] < 1e-2, (k, gin[k])
+    # both parity-grade storage modes of the training path (gazenerf_b200/train.py): "bf16x3" (default; every tensor to 5e-3) and
+    # "mixed" (same forward, single-pass bf16 backward on one gradient plane: stated tolerance 1e-2 for parameters and codes; the
+    # camera-pose gradients are sums of signed per-point terms through the positional encoding's 2^q-scaled derivatives and carry the
+    # bf16 rounding of the per-point gradients less gracefully: measured 2.9e-2 / 2.0e-2 at this size, stated 5e-2)
+    for precision, t_par, t_code, t_cam in (("bf16x3", 5e-3, 5e-3, 1e-2), ("mixed", 1e-2, 1e-2, 5e-2)):
+        net.train_precision = precision
+        for p_ in net.parameters():
+            p_.grad = None
+        dl = {k: kw[k].to(dev).requires_grad_(True) for k in leaves}
+        rm, tv = dl["batch_Rmats"], dl["batch_Tvecs"].reshape(B, 3)
+        shape_ext = torch.cat([dl["shape_code"], dl["gaze_code"]], 1)
+        fm = render_featmaps(net, xy, rm, tv, kinv, dl["gaze_code"], shape_ext, dl["appea_code"], z_edges)
+        assert fm.shape == (3 * B + 1, C, S, S)
+        got_sub = fm[:3 * B].detach().reshape(3 * B, C, S * S)[:, :, rays].cpu()
+        assert max_rel(got_sub, fm_ref.detach()) < TOL_TIGHT
+        cot = torch.zeros(3 * B + 1, C, S * S)
+        cot[:3 * B, :, rays] = cot_sub
+        fm.backward(cot.view(3 * B + 1, C, S, S).to(dev))
+        torch.cuda.synchronize()
+        # ---- compare: relative L2 per tensor (ReLU / max decisions within ~1e-5 of zero flip; see tests/test_train_grad.py header)
+        errs = {}
+        for k, p in net.named_parameters():
+            ref = sd[k].grad
+            if ref is None or float(ref.abs().max()) == 0.0:
+                assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+                continue
+            errs[k] = rel_l2(p.grad.cpu(), ref)
+        worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
+        print(precision, "full-size feature-map cotangent: worst parameter-gradient rel-L2 vs oracle autograd:", worst)
+        assert len(errs) >= 49 and all((v < (max(2e-2, 4 * t_par) if sd[k].numel() == 1 else t_par)) for k, v in errs.items()), (precision, worst)
+        gin = {k: rel_l2(dl[k].grad.cpu(), leaves[k].grad) for k in leaves}
+        print(precision, "input-gradient rel-L2:", gin)
+        for k in ("shape_code", "appea_code"):
+            assert gin[k] < t_code, (precision, k, gin[k])
+        for k in ("gaze_code", "batch_Rmats", "batch_Tvecs"):
+            assert gin[k] < t_cam, (precision, k, gin[k])
 
 
 def test_config4_neural_render_backward_full_size_vs_oracle_autograd(dev):
