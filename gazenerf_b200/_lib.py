@@ -44,7 +44,7 @@ SYMBOLS = [
     "gnrf_pe_fwd", "gnrf_pe_bwd", "gnrf_composite_cm_fwd", "gnrf_composite_cm_bwd", "gnrf_geom_bwd",
     "gnrf_lin_hl_packed_bytes", "gnrf_lin_hl_pack", "gnrf_lin_hl", "gnrf_wgrad_hl_workspace_bytes", "gnrf_wgrad_hl", "gnrf_pe_fwd_hl",
     "gnrf_composite_cm_bwd_hl",
-    "gnrf_compose_bwd_blocks", "gnrf_compose_bwd",
+    "gnrf_compose_bwd_blocks", "gnrf_compose_bwd_groups", "gnrf_compose_bwd",
     "gnrf_nr_train_saved_bytes", "gnrf_nr_train_fwd", "gnrf_nr_train_bwd_workspace_bytes", "gnrf_nr_train_bwd",
     "gnrf_data_loss_workspace_floats", "gnrf_data_loss_fwd", "gnrf_data_loss_bwd",
     # dataset sample -> device tensors
@@ -178,7 +178,8 @@ def lib() -> ctypes.CDLL:
     L.gnrf_composite_cm_fwd.argtypes = [vp, i64, vp, i64, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     L.gnrf_composite_cm_bwd.argtypes = [vp, vp, vp, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32, vp, i64, vp, i64, vp, vp, vp]
     L.gnrf_geom_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]
-    L.gnrf_compose_bwd_blocks.argtypes = [i32]
+    L.gnrf_compose_bwd_blocks.argtypes = [i32, i32]
+    L.gnrf_compose_bwd_groups.argtypes = [i32]
     L.gnrf_compose_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.gnrf_nr_train_saved_bytes.restype = sz
     L.gnrf_nr_train_saved_bytes.argtypes = [i32, i32, i32, i32, i32]

@@ -383,9 +383,10 @@ class FeatureMapFn(torch.autograd.Function):
         P2 = S * S
         sv_f, sv_e = k["sv_f"], k["sv_e"]
         g_ff, g_fe = o.empty(B, C, P2), o.empty(B, C, P2)
-        g_af, g_ae = o.empty(B, P2), o.empty(B, P2)
+        n_grp = L.gnrf_compose_bwd_groups(C)               # channel groups: partial sums, added up below in a fixed order
+        g_af, g_ae = o.empty(n_grp, B, P2), o.empty(n_grp, B, P2)
         g_bg = o.empty(1, C, S, S)
-        nblk = L.gnrf_compose_bwd_blocks(P2)
+        nblk = L.gnrf_compose_bwd_blocks(P2, C)
         g_gz = o.empty(B, nblk, 2)
         _lib.check(L.gnrf_compose_bwd(g_fm.data_ptr(), sv_f["feat"].data_ptr(), sv_f["bg_alpha"].data_ptr(), sv_e["feat"].data_ptr(),
                                       sv_e["bg_alpha"].data_ptr(), k["bg"].data_ptr(), k["gaze"].data_ptr(), B, C, P2, g_ff.data_ptr(),
@@ -393,6 +394,7 @@ class FeatureMapFn(torch.autograd.Function):
                    "gnrf_compose_bwd")
         g_bg = g_bg + g_fm[3 * B:3 * B + 1]
         g_gaze = g_gz.sum(1)
+        g_af, g_ae = g_af.sum(0), g_ae.sum(0)
         # ---- radiance MLPs + composite + positional encoding
         g_m, g_o, g_l = o.zeros(B, n_r, 3), o.zeros(B, n_r, 3), o.zeros(B, n_r)
         g_z = o.zeros(B, n_r, n_s + 1)

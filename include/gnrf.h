@@ -272,9 +272,10 @@ int gnrf_composite_cm_bwd_hl(const float* g_Hc, const float* g_bg_alpha, const f
 int gnrf_geom_bwd(const float* xy, const float* rmats, const float* inv_inmats, const float* g_m, const float* g_o,
                   const float* g_l, const float* g_z, int B, int N_r, int N_s, float* contrib, gnrf_stream_t stream);
 
-/* Backward of gnrf_compose_fwd.  g_out [3][B][C][P] -> g_feat_* [B][C][P], g_a_* [B][P], g_bg [C][P],
- * g_gaze_part [B][gnrf_compose_bwd_blocks(P)][2] (the caller sums over blocks). */
-int gnrf_compose_bwd_blocks(int P);
+/* Backward of gnrf_compose_fwd.  g_out [3][B][C][P] -> g_feat_* [B][C][P], g_bg [C][P], and per channel-group partial sums the caller
+ * adds up in order: g_a_* [gnrf_compose_bwd_groups(C)][B][P], g_gaze_part [B][gnrf_compose_bwd_blocks(P, C)][2]. */
+int gnrf_compose_bwd_groups(int C);
+int gnrf_compose_bwd_blocks(int P, int C);
 int gnrf_compose_bwd(const float* g_out, const float* feat_face, const float* a_face, const float* feat_eyes, const float* a_eyes,
                      const float* bg, const float* gaze, int B, int C, int P, float* g_feat_face, float* g_a_face,
                      float* g_feat_eyes, float* g_a_eyes, float* g_bg, float* g_gaze_part, gnrf_stream_t stream);

@@ -259,16 +259,18 @@ def test_compose_bwd(dev):
     sum((o * g).sum() for o, g in zip(outs, gs)).backward()
     d = lambda x: x.detach().contiguous().to(dev)
     g_out = d(torch.stack(gs, 0))
-    g_ff, g_fe, g_af, g_ae = torch.empty(B, C, P, device=dev), torch.empty(B, C, P, device=dev), torch.empty(B, P, device=dev), torch.empty(B, P, device=dev)
+    n_grp = L.gnrf_compose_bwd_groups(C)
+    g_ff, g_fe = torch.empty(B, C, P, device=dev), torch.empty(B, C, P, device=dev)
+    g_af, g_ae = torch.empty(n_grp, B, P, device=dev), torch.empty(n_grp, B, P, device=dev)
     g_bg = torch.empty(C, P, device=dev)
-    nblk = L.gnrf_compose_bwd_blocks(P)
+    nblk = L.gnrf_compose_bwd_blocks(P, C)
     part = torch.empty(B, nblk, 2, device=dev)
     ins = [d(ff), d(af), d(fe), d(ae), d(bg), d(gaze)]
     _lib.check(L.gnrf_compose_bwd(g_out.data_ptr(), *[x.data_ptr() for x in ins], B, C, P, g_ff.data_ptr(), g_af.data_ptr(), g_fe.data_ptr(),
                                   g_ae.data_ptr(), g_bg.data_ptr(), part.data_ptr(), S()))
     torch.cuda.synchronize()
     assert rel_l2(g_ff.cpu().reshape(ff.shape), ff.grad) < 1e-5 and rel_l2(g_fe.cpu().reshape(fe.shape), fe.grad) < 1e-5
-    assert rel_l2(g_af.cpu().reshape(af.shape), af.grad) < 1e-5 and rel_l2(g_ae.cpu().reshape(ae.shape), ae.grad) < 1e-5
+    assert rel_l2(g_af.sum(0).cpu().reshape(af.shape), af.grad) < 1e-5 and rel_l2(g_ae.sum(0).cpu().reshape(ae.shape), ae.grad) < 1e-5
     assert rel_l2(g_bg.cpu().reshape(bg.shape), bg.grad) < 1e-5
     assert rel_l2(part.sum(1).cpu(), gaze.grad) < 1e-4
 
