@@ -168,7 +168,7 @@ def lib() -> ctypes.CDLL:
     L.gnrf_lin_hl_packed_bytes.restype = sz
     L.gnrf_lin_hl_packed_bytes.argtypes = [i32, i32, i32]
     L.gnrf_lin_hl_pack.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
-    L.gnrf_lin_hl.argtypes = [vp, i32, i32, i32, vp, i64, i64, vp, i32, vp, i64, i64, i32, vp, i64, vp, i64, i32, vp, i64, i32, i32, i32, vp]
+    L.gnrf_lin_hl.argtypes = [vp, i32, i32, i32, vp, i64, i64, vp, i32, i32, vp, i64, i64, i32, vp, i64, vp, i64, i32, vp, i64, i32, i32, i32, vp]
     L.gnrf_wgrad_hl_workspace_bytes.restype = sz
     L.gnrf_wgrad_hl_workspace_bytes.argtypes = [i32, i32, i32, i32]
     L.gnrf_wgrad_hl.argtypes = [vp, i64, i64, vp, i64, i64, i32, i32, i32, i32, i32, vp, vp, i32, vp, sz, vp]

@@ -58,7 +58,7 @@ struct LinArgs {
   const unsigned char* wpack;   // [n_mt][n_kb][PL planes][2 K16 slices][128 rows x 32 B]
   const float* bias;            // [n_mt * 128] (zero padded), follows the blobs in the packed buffer
   const float* bias_img;        // [n_img][N_out] or null
-  int N_out, K_in, n_mt, n_kb, HW, n_img, tiles_per_img, n_tiles, act;
+  int N_out, K_in, n_mt, n_kb, HW, n_img, tiles_per_img, n_tiles, act, act_rows;   // ReLU on rows < act_rows (a multiple of 32, or >= N_out)
   __nv_bfloat16* out;           // planes: rows < hl_rows
   long long out_img_stride, out_plane_stride;
   int hl_rows;
@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(kLhThreads, 1) lin_hl_kernel(const LinArgs arg
         const int buf = it & 1;
         const int row_base = mt * 128 + q * 32, row = row_base + lane;
         const bool warp_live = row_base < args.N_out, warp_planes = row_base < args.hl_rows;   // hl_rows % 32 == 0 or >= N_out
+        const bool relu = args.act != 0 && row_base < args.act_rows;
         const bool valid = row < args.N_out;
         float b = 0.0f;
         if (valid) {
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(kLhThreads, 1) lin_hl_kernel(const LinArgs arg
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               v[j] = __uint_as_float(r[j]) + b;
-              if (args.act) v[j] = fmaxf(v[j], 0.0f);
+              if (relu) v[j] = fmaxf(v[j], 0.0f);
             }
             if (args.mask_bits != nullptr) {   // warp-uniform: the input-gradient calls
               const uint32_t m = mw[c];
@@ -630,13 +631,15 @@ extern "C" int gnrf_lin_hl_pack(const float* W, const float* bias, int N, int K,
 }
 
 extern "C" int gnrf_lin_hl(const void* packed, int N, int K, int planes, const void* X, long long x_img_stride, long long x_plane_stride,
-                           const float* bias_img, int act, void* out, long long out_img_stride, long long out_plane_stride, int hl_rows,
+                           const float* bias_img, int act, int act_rows, void* out, long long out_img_stride, long long out_plane_stride,
+                           int hl_rows,
                            float* out_f32, long long f32_img_stride, const void* mask_bits, long long mask_img_stride, int mask_rows,
                            void* mask_out, long long mask_out_img_stride, int mask_out_rows, int n_img, int HW, gnrf_stream_t stream) {
   GNRF_CHECK_ARG(packed && X && N > 0 && K > 0 && n_img > 0 && HW > 0 && (planes == 1 || planes == 2));
   GNRF_CHECK_ARG(HW % tc::kLhTileN == 0 && K >= tc::kLhKb);
   GNRF_CHECK_ARG(hl_rows >= 0 && (hl_rows == 0 || out != nullptr) && (hl_rows >= N || out_f32 != nullptr));
   GNRF_CHECK_ARG(hl_rows >= N || hl_rows % 32 == 0);   // a 32-row epilogue group is either all planes or all fp32
+  GNRF_CHECK_ARG(act_rows >= 0 && (act_rows >= N || act_rows % 32 == 0));
   GNRF_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & 15) == 0 && x_img_stride % 8 == 0 && x_plane_stride % 8 == 0);
   GNRF_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(mask_bits) & 15) == 0 && (reinterpret_cast<uintptr_t>(mask_out) & 15) == 0 &&
@@ -668,6 +671,7 @@ extern "C" int gnrf_lin_hl(const void* packed, int N, int K, int planes, const v
   a.bias_img = bias_img;
   a.N_out = N; a.K_in = K; a.n_mt = pl.n_mt; a.n_kb = pl.n_kb; a.HW = HW; a.n_img = n_img;
   a.tiles_per_img = HW / tc::kLhTileN; a.n_tiles = a.tiles_per_img * n_img; a.act = act;
+  a.act_rows = act_rows > 0 ? act_rows : N;
   a.out = static_cast<__nv_bfloat16*>(out);
   a.out_img_stride = out_img_stride > 0 ? out_img_stride : (long long)N * HW;
   a.out_plane_stride = out_plane_stride;

@@ -208,14 +208,14 @@ class _HL:
 
     def lin(self, pk, N, K, x: torch.Tensor, x_row0: int = 0, out: Optional[torch.Tensor] = None, out_row0: int = 0, hl_rows: Optional[int] = None,
             out_f32: Optional[torch.Tensor] = None, act=0, bias_img=None, mask: Optional[torch.Tensor] = None, mask_rows: int = 0,
-            sign_out: Optional[torch.Tensor] = None):
+            sign_out: Optional[torch.Tensor] = None, act_rows: int = 0):
         """x / out: plane tensors, addressed from row x_row0 / out_row0 (row windows of a wider tensor keep its strides);
         mask / sign_out: bit tensors from bits()."""
         P = self.P
         hl_rows = N if hl_rows is None else hl_rows
         _lib.check(self.L.gnrf_lin_hl(
             pk.data_ptr(), N, K, self.PL, x.data_ptr() + x_row0 * P * 2, x.shape[2] * P, x.stride(0), bias_img.data_ptr() if bias_img is not None else None,
-            act, (out.data_ptr() + out_row0 * P * 2) if out is not None else None, out.shape[2] * P if out is not None else 0,
+            act, act_rows, (out.data_ptr() + out_row0 * P * 2) if out is not None else None, out.shape[2] * P if out is not None else 0,
             out.stride(0) if out is not None else 0, hl_rows, out_f32.data_ptr() if out_f32 is not None else None,
             out_f32.shape[1] * P if out_f32 is not None else 0, mask.data_ptr() if mask is not None else None,
             mask.shape[1] * (P // 32) if mask is not None else 0, mask_rows,
@@ -262,17 +262,23 @@ def _branch_forward_hl(o: _Ops, T: Sequence[torch.Tensor], B, n_r, n_s, H, C, ra
     for i, k in ((6, 12), (7, 14)):
         h[i] = q.empty(H)
         q.lin(q.pack(T[k], T[k + 1], H, H), H, H, h[i - 1], out=h[i], act=RELU, sign_out=sg[i])
-    r0 = q.empty(H)                        # RGB_layer_0 output (planes) ...
-    sig = o.empty(B, 1, P)                 # ... and the raw density (row H of the same GEMM) in fp32 for the composite
-    q.lin(q.pack(T[16], T[17], H + 1, H), H + 1, H, h[7], out=r0, hl_rows=H, out_f32=sig, act=NONE)
-    hc = o.empty(B, H2, P)
-    q.lin(q.pack(T[18], None, H2, H), H2, H, r0, hl_rows=0, out_f32=hc, act=RELU, bias_img=T[19])
+    # RGB_layer_0 has no activation (models/mlp_nerf.py:110-111), so RGB_layer_1(RGB_layer_0(h7)) is ONE linear map of h7 -- the same
+    # exact fold the inference kernel uses; the density row rides along:
+    #   [hc_pre ; sigma_raw] = [W1h W0 ; wd] h7 + [b1_face + W1h b0 ; bd]      (193 rows; ReLU on the first 192 only)
+    # One 2-M-tile GEMM replaces a 385-row and a 192-row one in the forward and in both backward products; the 384-row RGB_layer_0
+    # output is never materialised.  The gradients of the four original tensors follow from the product rule in _branch_backward_hl.
+    W0, b0, wd, bd, W1h = T[16][:H], T[17][:H], T[16][H:], T[17][H:], T[18]
+    W_eff = torch.cat([(W1h.double() @ W0.double()).float(), wd], 0).contiguous()                     # [H2 + 1][H]
+    b_eff = torch.cat([T[19] + (W1h @ b0)[None], bd[None].expand(B, 1)], 1).contiguous()              # [B][H2 + 1] per-face bias
+    hs = o.empty(B, H2 + 1, P)             # rows [0,H2): RGB_layer_1 output (post-ReLU); row H2: raw density -- fp32 for the composite
+    q.lin(q.pack(W_eff, None, H2 + 1, H), H2 + 1, H, h[7], hl_rows=0, out_f32=hs, act=RELU, act_rows=H2, bias_img=b_eff)
     Hc, bg_alpha, w = o.empty(B, H2 + 1, n_r), o.empty(B, n_r), o.empty(B, n_r, n_s)
-    _lib.check(L.gnrf_composite_cm_fwd(hc.data_ptr(), H2 * P, sig.data_ptr(), P, z_edges.data_ptr(), ray_dl.data_ptr(), B, n_r, n_s, H2,
-                                       Hc.data_ptr(), bg_alpha.data_ptr(), w.data_ptr(), o.st), "gnrf_composite_cm_fwd")
+    _lib.check(L.gnrf_composite_cm_fwd(hs.data_ptr(), (H2 + 1) * P, hs.data_ptr() + H2 * P * 4, (H2 + 1) * P, z_edges.data_ptr(),
+                                       ray_dl.data_ptr(), B, n_r, n_s, H2, Hc.data_ptr(), bg_alpha.data_ptr(), w.data_ptr(), o.st),
+               "gnrf_composite_cm_fwd")
     feat = o.empty(B, C, n_r)
     o.conv(o.pack(T[20], None, C, H2 + 1), C, H2 + 1, Hc.data_ptr(), 0, feat.data_ptr(), 0, B, n_r, act=NONE)
-    return {"buf0": buf0, "pe32": pe32, "h": h, "sg": sg, "r0": r0, "sig": sig, "hc": hc, "Hc": Hc, "bg_alpha": bg_alpha, "w": w,
+    return {"buf0": buf0, "pe32": pe32, "h": h, "sg": sg, "hs": hs, "W_eff": W_eff, "Hc": Hc, "bg_alpha": bg_alpha, "w": w,
             "feat": feat, "planes": planes, "planes_bwd": planes}
 
 
@@ -285,25 +291,27 @@ def _branch_backward_hl(o: _Ops, T: Sequence[torch.Tensor], sv: Dict[str, torch.
     H2 = H // 2
     planes = sv["planes_bwd"]
     q = _HL(o, planes, B, P)
-    buf0, h, r0, hc, Hc, w, sig, sg = sv["buf0"], sv["h"], sv["r0"], sv["hc"], sv["Hc"], sv["w"], sv["sig"], sv["sg"]
+    buf0, h, hs, Hc, w, sg, W_eff = sv["buf0"], sv["h"], sv["hs"], sv["Hc"], sv["w"], sv["sg"], sv["W_eff"]
     g: List[Optional[torch.Tensor]] = [None] * N_BRANCH_T
     g[20], _ = o.wgrad(g_feat.data_ptr(), 0, Hc.data_ptr(), 0, C, H2 + 1, B, n_r, "none")
     g_Hc = o.empty(B, H2 + 1, n_r)
     o.conv(o.pack(T[20], None, H2 + 1, C, transposed=True), H2 + 1, C, g_feat.data_ptr(), 0, g_Hc.data_ptr(), 0, B, n_r)
-    g_r0, g_hc = q.empty(H + 1), q.empty(H2)       # row H of g_r0: gradient of the raw density
-    _lib.check(L.gnrf_composite_cm_bwd_hl(g_Hc.data_ptr(), g_alpha.data_ptr(), hc.data_ptr(), H2 * P, sig.data_ptr(), P, w.data_ptr(),
-                                          z_edges.data_ptr(), ray_dl.data_ptr(), B, n_r, n_s, H2, g_hc.data_ptr(), H2 * P, g_hc.stride(0),
-                                          g_r0.data_ptr() + H * P * 2, (H + 1) * P, g_r0.stride(0), planes, g_z.data_ptr(), g_l.data_ptr(),
-                                          o.st), "gnrf_composite_cm_bwd_hl")
-    # RGB_layer_1 (hidden part; the appearance columns live in the per-face bias)
-    g[18], g[19] = q.wgrad(g_hc, H2, r0, H, "img")
-    q.lin(q.pack(T[18], None, H, H2, transposed=True), H, H2, g_hc, out=g_r0)
-    del g_hc
-    # RGB_layer_0 + density_module on h7
-    g[16], g[17] = q.wgrad(g_r0, H + 1, h[7], H, "sum")
+    g_hs = q.empty(H2 + 1)                         # rows [0,H2): gradient of the RGB_layer_1 pre-activation; row H2: of the raw density
+    _lib.check(L.gnrf_composite_cm_bwd_hl(g_Hc.data_ptr(), g_alpha.data_ptr(), hs.data_ptr(), (H2 + 1) * P, hs.data_ptr() + H2 * P * 4,
+                                          (H2 + 1) * P, w.data_ptr(), z_edges.data_ptr(), ray_dl.data_ptr(), B, n_r, n_s, H2,
+                                          g_hs.data_ptr(), (H2 + 1) * P, g_hs.stride(0), g_hs.data_ptr() + H2 * P * 2, (H2 + 1) * P,
+                                          g_hs.stride(0), planes, g_z.data_ptr(), g_l.data_ptr(), o.st), "gnrf_composite_cm_bwd_hl")
+    # folded RGB head on h7: dW_eff [H2+1][H], per-face bias gradient [B][H2+1]; product rule back to the four original tensors
+    gW_eff, gb_eff = q.wgrad(g_hs, H2 + 1, h[7], H, "img")
+    W0, b0, W1h = T[16][:H], T[17][:H], T[18]
+    gWp, gbp = gW_eff[:H2], gb_eff[:, :H2]                                                            # the RGB_layer_1 part
+    g[16] = torch.cat([W1h.t() @ gWp, gW_eff[H2:]], 0)                                              # dW0 = W1h^T dW' ; density row
+    g[17] = torch.cat([W1h.t() @ gbp.sum(0), gb_eff[:, H2].sum(0, keepdim=True)], 0)                # db0 = W1h^T sum_b db' ; density bias
+    g[18] = gWp @ W0.t() + torch.outer(gbp.sum(0), b0)                                              # dW1h = dW' W0^T + db' b0^T
+    g[19] = gbp.contiguous()                                                                        # per-face bias of RGB_layer_1
     ga = q.empty(H)
-    q.lin(q.pack(T[16], None, H, H + 1, transposed=True), H, H + 1, g_r0, out=ga, mask=sg[7])
-    del g_r0
+    q.lin(q.pack(W_eff, None, H, H2 + 1, transposed=True), H, H2 + 1, g_hs, out=ga, mask=sg[7])
+    del g_hs
     for i, k in ((7, 14), (6, 12)):
         g[k], g[k + 1] = q.wgrad(ga, H, h[i - 1], H, "sum")
         gb = q.empty(H)

@@ -241,6 +241,7 @@ int gnrf_composite_cm_bwd(const float* g_Hc, const float* g_bg_alpha, const floa
  * points contiguous; planes = 2 is the bf16x3 scheme of the kernels above, planes = 1 single-pass bf16 (half the bytes; gradient
  * tolerance stated in tests/test_train_grad.py).  All strides in ELEMENTS (bf16 or float); HW a multiple of 256, K >= 32.
  *   gnrf_lin_hl:  y[img][n][p] = act( sum_k W[n][k] x[img][k][p] + bias[n] + bias_img[img][n] ) * mask_bit[img][n][p] (n < mask_rows)
+ *     act (GNRF_ACT_NONE / GNRF_ACT_RELU) applies to rows n < act_rows (0 = all rows; a multiple of 32 otherwise);
  *     rows n < hl_rows (a multiple of 32, or >= N) are written as planes to `out`, rows n >= hl_rows as fp32 to
  *     out_f32[img][n - hl_rows][p] (for the non-GEMM consumers: composite, positional-encoding backward).
  *     mask_out (nullable): uint32 [img][rows][HW/32], bit (p % 32) of word p/32 = (y > 0) -- the ReLU sign bits the input gradient of
@@ -251,7 +252,7 @@ int gnrf_composite_cm_bwd(const float* g_Hc, const float* g_bg_alpha, const floa
 size_t gnrf_lin_hl_packed_bytes(int N, int K, int planes);
 int gnrf_lin_hl_pack(const float* W, const float* bias, int N, int K, int transposed, int planes, void* packed, gnrf_stream_t stream);
 int gnrf_lin_hl(const void* packed, int N, int K, int planes, const void* X, long long x_img_stride, long long x_plane_stride,
-                const float* bias_img, int act, void* out, long long out_img_stride, long long out_plane_stride, int hl_rows,
+                const float* bias_img, int act, int act_rows, void* out, long long out_img_stride, long long out_plane_stride, int hl_rows,
                 float* out_f32, long long f32_img_stride, const void* mask_bits, long long mask_img_stride, int mask_rows,
                 void* mask_out, long long mask_out_img_stride, int mask_out_rows, int n_img, int HW, gnrf_stream_t stream);
 size_t gnrf_wgrad_hl_workspace_bytes(int N, int K, int n_img, int HW);

@@ -45,7 +45,7 @@ def _bits(x: torch.Tensor) -> torch.Tensor:
 
 
 def _lin(L, W, bias, x_pl, planes, n_img, HW, act=0, bias_img=None, hl_rows=None, mask_bits=None, mask_rows=0, transposed=False,
-         sign_out=None):
+         sign_out=None, act_rows=0):
     from gazenerf_b200 import _lib
     dev = x_pl.device
     st = torch.cuda.current_stream().cuda_stream
@@ -58,7 +58,7 @@ def _lin(L, W, bias, x_pl, planes, n_img, HW, act=0, bias_img=None, hl_rows=None
     out32 = torch.full((n_img, max(N - hl_rows, 1), HW), float("nan"), device=dev, dtype=torch.float32)
     K_rows = x_pl.shape[2]
     _lib.check(L.gnrf_lin_hl(pk.data_ptr(), N, K, planes, x_pl.data_ptr(), K_rows * HW, x_pl.stride(0),
-                             bias_img.data_ptr() if bias_img is not None else None, act,
+                             bias_img.data_ptr() if bias_img is not None else None, act, act_rows,
                              out.data_ptr(), out.shape[2] * HW, out.stride(0), hl_rows, out32.data_ptr(), out32.shape[1] * HW,
                              mask_bits.data_ptr() if mask_bits is not None else None,
                              mask_bits.shape[1] * (HW // 32) if mask_bits is not None else 0, mask_rows,
@@ -112,6 +112,11 @@ def test_lin_hl_fp32_rows_and_mask(planes):
     ref = torch.einsum("nk,ikp->inp", _w_eff(W, planes), _value(x_pl)) + b.double()[None, :, None]
     assert _rel(_value(out), ref[:, :384]) < (3e-5 if planes == 2 else 4e-3)
     assert _rel(out32, ref[:, 384:]) < 2e-5
+    # folded RGB head: 193 fp32 outputs, ReLU on the first 192 rows only (row 192 = raw density)
+    _, o193 = _lin(L, W[:193].contiguous(), b[:193].contiguous(), x_pl, planes, n_img, HW, act=1, hl_rows=0, act_rows=192)
+    r193 = ref[:, :193].clone()
+    r193[:, :192] = r193[:, :192].clamp_min(0)
+    assert _rel(o193, r193) < 2e-5 and float(o193[:, 192].min()) < 0
     # all-fp32 output (hl_rows = 0)
     _, o32 = _lin(L, W[:192].contiguous(), b[:192].contiguous(), x_pl, planes, n_img, HW, act=1, hl_rows=0)
     assert _rel(o32, ref[:, :192].clamp_min(0)) < 2e-5
@@ -169,7 +174,7 @@ def test_lin_hl_strided_views():
     pk = torch.empty((L.gnrf_lin_hl_packed_bytes(H, PE, 2),), device=dev, dtype=torch.uint8)
     _lib.check(L.gnrf_lin_hl_pack(W.data_ptr(), None, H, PE, 0, 2, pk.data_ptr(), st), "pack")
     x_ptr = buf.data_ptr() + H * HW * 2
-    _lib.check(L.gnrf_lin_hl(pk.data_ptr(), H, PE, 2, x_ptr, (H + 64) * HW, buf.stride(0), None, 1, buf.data_ptr(), (H + 64) * HW,
+    _lib.check(L.gnrf_lin_hl(pk.data_ptr(), H, PE, 2, x_ptr, (H + 64) * HW, buf.stride(0), None, 1, 0, buf.data_ptr(), (H + 64) * HW,
                              buf.stride(0), H, None, 0, None, 0, 0, None, 0, 0, n_img, HW, st), "gnrf_lin_hl")
     torch.cuda.synchronize()
     ref = torch.einsum("nk,ikp->inp", _w_eff(W, 2), _value(_planes(pe, 2))).clamp_min(0)
