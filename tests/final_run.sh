@@ -1,4 +1,4 @@
-# scratch: the end-of-round validation sequence (full GPU suite, default bench line, train bench in every precision mode)
+# scratch: the end-of-round validation sequence (full GPU suite, default bench line, train bench in every precision mode, launch lists)
 timeout 1200 python -m pytest tests -q -m gpu 2>&1 | tail -4
 timeout 600 python bench.py > gpurun_out/r2_bench_n1.json 2> gpurun_out/bench_n1.err; tail -1 gpurun_out/bench_n1.err
 rm -f gpurun_out/r2_bench_train.json
@@ -11,3 +11,5 @@ for k,v in d["aux"].items(): print(" aux", k, v.get("value"), v.get("ms_per_step
 for l in open("gpurun_out/r2_bench_train.json"):
     t=json.loads(l); print("train", t["config"]["train_precision"], t["value"], t["ms_per_step"], t["roofline"]["frac"], t["e2e"]["value"])
 PY
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 1600 --csv --log-file gpurun_out/train_launches.csv python tests/train_probe.py 2 > gpurun_out/train_probe.log 2>&1; tail -1 gpurun_out/train_probe.log
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 1600 --csv --log-file gpurun_out/train_launches_mixed.csv python tests/prof_train.py mixed 3 > gpurun_out/prof_train2.log 2>&1; tail -1 gpurun_out/prof_train2.log
