@@ -244,6 +244,176 @@ composite_cm_bwd_kernel(const float* __restrict__ g_Hc, const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------- compositing, warp per ray (N_s <= 64, even)
+// Same mathematics as the two kernels above with ONE WARP per ray instead of one 256-thread CTA: lane owns the ADJACENT samples
+// k = 2 lane and 2 lane + 1 (8-byte loads, bf16x2 plane stores), every warp streams all C channels of its ray (no shared memory, no
+// block barriers, no thread-0 serial section that idles 255 threads), the sequential cumprod runs redundantly on all lanes over shuffle
+// broadcasts -- the same operations in the same order as the serial loop, so the forward weights are bit-identical -- and the
+// per-channel dot products of the forward are reduced 32 channels at a time by a transposing butterfly (31 shuffles instead of 160).
+__device__ __forceinline__ void ray_alpha2(const float* __restrict__ sg, const float* __restrict__ ze, float l, int N_s, int lane,
+                                           float (&a)[2], float (&dz)[2], float (&sraw)[2]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int k = 2 * lane + i;
+    a[i] = 0.0f; dz[i] = 0.0f; sraw[i] = 0.0f;
+    if (k < N_s) {
+      dz[i] = __fsub_rn(ze[k + 1], ze[k]);
+      sraw[i] = sg[k];
+      a[i] = __fsub_rn(1.0f, expf(-__fmul_rn(fmaxf(sraw[i], 0.0f), __fmul_rn(dz[i], l))));
+    }
+  }
+}
+
+// two adjacent elements of a plane tensor (idx even): hi pair and, with two planes, the lo pair of the residuals
+__device__ __forceinline__ void st_planes2(__nv_bfloat16* hl, long long plane_stride, int planes, size_t idx, float v0, float v1) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+  *reinterpret_cast<__nv_bfloat162*>(hl + idx) = h;
+  if (planes == 2) {
+    const float2 hf = __bfloat1622float2(h);
+    *reinterpret_cast<__nv_bfloat162*>(hl + (size_t)plane_stride + idx) = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+composite_cm_fwd_warp_kernel(const float* __restrict__ h, long long h_stride, const float* __restrict__ sigma_raw, long long s_stride,
+                             const float* __restrict__ z_edges, const float4* __restrict__ ray_dl, int n_rays, int N_r, int N_s, int C,
+                             float* __restrict__ Hc, float* __restrict__ bg_alpha, float* __restrict__ weights) {
+  const int rayg = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (rayg >= n_rays) return;
+  const int b = rayg / N_r, r = rayg - b * N_r;
+  const long long P = (long long)N_r * N_s;
+  float a[2], dz[2], sraw[2], w[2] = {0.0f, 0.0f};
+  ray_alpha2(sigma_raw + (size_t)b * s_stride + (size_t)r * N_s, z_edges + (size_t)rayg * (N_s + 1), ray_dl[rayg].w, N_s, lane, a, dz, sraw);
+  float T = 1.0f, acc_w = 0.0f;
+  for (int src = 0; 2 * src < N_s; ++src) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {   // sample k = 2 src + i (N_s is even)
+      const float ak = __shfl_sync(0xffffffffu, a[i], src);
+      const float wk = __fmul_rn(ak, T);
+      T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.0f, ak), 1e-10f));
+      if (lane == src) w[i] = wk;
+      acc_w += wk;
+    }
+  }
+  const bool ok = 2 * lane < N_s;
+  if (ok) *reinterpret_cast<float2*>(weights + (size_t)rayg * N_s + 2 * lane) = make_float2(w[0], w[1]);
+  if (lane == 0) {
+    bg_alpha[rayg] = 1.0f - acc_w;
+    Hc[((size_t)b * (C + 1) + C) * N_r + r] = acc_w;
+  }
+  const float* hb = h + (size_t)b * h_stride + (size_t)r * N_s + 2 * lane;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float* hp = hb + (size_t)min(c0 + j, C - 1) * P;   // clamped: channels past C are computed and dropped
+      const float2 x = ok ? *reinterpret_cast<const float2*>(hp) : make_float2(0.0f, 0.0f);
+      v[j] = fmaf(w[1], x.y, w[0] * x.x);
+    }
+    // transposing butterfly: after the step with offset `off`, lane keeps the channels whose bit `off` equals its own lane bit
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool up = (lane & off) != 0;
+#pragma unroll
+      for (int j = 0; j < off; ++j) {
+        const float send = up ? v[j] : v[j + off];
+        const float keep = up ? v[j + off] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    if (c0 + lane < C) Hc[((size_t)b * (C + 1) + c0 + lane) * N_r + r] = v[0];
+  }
+}
+
+template <int PLANES>
+__global__ void __launch_bounds__(256)
+composite_cm_bwd_warp_kernel(const float* __restrict__ g_Hc, const float* __restrict__ g_bg, const float* __restrict__ h, long long h_stride,
+                             const float* __restrict__ sigma_raw, long long s_stride, const float* __restrict__ weights,
+                             const float* __restrict__ z_edges, const float4* __restrict__ ray_dl, int n_rays, int N_r, int N_s, int C,
+                             void* __restrict__ g_h_v, long long gh_stride, void* __restrict__ g_sigma_v, long long gs_stride,
+                             long long gh_plane_stride, long long gs_plane_stride, float* __restrict__ g_z, float* __restrict__ g_l) {
+  const int rayg = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (rayg >= n_rays) return;
+  float* g_h = static_cast<float*>(g_h_v);
+  float* g_sigma = static_cast<float*>(g_sigma_v);
+  __nv_bfloat16* g_h_hl = static_cast<__nv_bfloat16*>(g_h_v);
+  __nv_bfloat16* g_sigma_hl = static_cast<__nv_bfloat16*>(g_sigma_v);
+  const int b = rayg / N_r, r = rayg - b * N_r;
+  const long long P = (long long)N_r * N_s;
+  const bool ok = 2 * lane < N_s;
+  const float2 wv = ok ? *reinterpret_cast<const float2*>(weights + (size_t)rayg * N_s + 2 * lane) : make_float2(0.0f, 0.0f);
+  // ---- channel pass: g_h and the dot products g_w_k = sum_c g_Hc[c] h[c][k]
+  const float* hb = h + (size_t)b * h_stride + (size_t)r * N_s + 2 * lane;
+  const float* gc = g_Hc + (size_t)b * (C + 1) * N_r + r;
+  const size_t gh_off = (size_t)b * gh_stride + (size_t)r * N_s + 2 * lane;
+  float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll 8
+  for (int c = 0; c < C; ++c) {
+    const float g = gc[(size_t)c * N_r];   // warp-uniform address: one broadcast transaction
+    const float2 x = ok ? *reinterpret_cast<const float2*>(hb + (size_t)c * P) : make_float2(0.0f, 0.0f);
+    acc0 = fmaf(g, x.x, acc0);
+    acc1 = fmaf(g, x.y, acc1);
+    const float gv0 = x.x > 0.0f ? wv.x * g : 0.0f, gv1 = x.y > 0.0f ? wv.y * g : 0.0f;
+    if (ok) {
+      if (PLANES == 0) *reinterpret_cast<float2*>(g_h + gh_off + (size_t)c * P) = make_float2(gv0, gv1);
+      else st_planes2(g_h_hl, gh_plane_stride, PLANES, gh_off + (size_t)c * P, gv0, gv1);
+    }
+  }
+  const float gsum = gc[(size_t)C * N_r] - (g_bg ? g_bg[rayg] : 0.0f);
+  const float gw[2] = {acc0 + gsum, acc1 + gsum};
+  // ---- transmittances (forward recurrence) and the reverse recurrence G_k = dL/dT_{k+1}, both over shuffle broadcasts
+  const float l = ray_dl[rayg].w;
+  float a[2], dz[2], sraw[2], Tk[2] = {0.0f, 0.0f}, Gn[2] = {0.0f, 0.0f};
+  ray_alpha2(sigma_raw + (size_t)b * s_stride + (size_t)r * N_s, z_edges + (size_t)rayg * (N_s + 1), l, N_s, lane, a, dz, sraw);
+  float T = 1.0f;
+  for (int src = 0; 2 * src < N_s; ++src) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float ak = __shfl_sync(0xffffffffu, a[i], src);
+      if (lane == src) Tk[i] = T;
+      T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.0f, ak), 1e-10f));
+    }
+  }
+  float G = 0.0f;
+  for (int src = (N_s >> 1) - 1; src >= 0; --src) {
+#pragma unroll
+    for (int i = 1; i >= 0; --i) {
+      const float ak = __shfl_sync(0xffffffffu, a[i], src), gwk = __shfl_sync(0xffffffffu, gw[i], src);
+      if (lane == src) Gn[i] = G;   // G before the update = dL/dT_{k+1}
+      G = gwk * ak + G * (1.0f - ak + 1e-10f);
+    }
+  }
+  // ---- per-sample gradients (each lane its own two samples)
+  float gd[2], gsv[2], gl = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float ga = (gw[i] - Gn[i]) * Tk[i];
+    const float delta = __fmul_rn(dz[i], l);
+    const float sp = fmaxf(sraw[i], 0.0f);
+    const float e = 1.0f - a[i];   // exp(-s delta)
+    gsv[i] = sraw[i] > 0.0f ? ga * e * delta : 0.0f;
+    gd[i] = ok ? ga * e * sp : 0.0f;
+    gl += gd[i] * dz[i];
+  }
+  if (ok) {
+    const size_t gs_off = (size_t)b * gs_stride + (size_t)r * N_s + 2 * lane;
+    if (PLANES == 0) *reinterpret_cast<float2*>(g_sigma + gs_off) = make_float2(gsv[0], gsv[1]);
+    else st_planes2(g_sigma_hl, gs_plane_stride, PLANES, gs_off, gsv[0], gsv[1]);
+  }
+  // g_z[j] += l * (gd_{j-1} - gd_j): edge j is the far end of sample j-1 and the near end of sample j
+  float* gz = g_z + (size_t)rayg * (N_s + 1);
+  float prev = __shfl_up_sync(0xffffffffu, gd[1], 1);        // gd_{2 lane - 1}
+  if (lane == 0) prev = 0.0f;
+  if (ok) {
+    gz[2 * lane] += l * (prev - gd[0]);
+    gz[2 * lane + 1] += l * (gd[0] - gd[1]);
+  }
+  const float last = __shfl_sync(0xffffffffu, gd[1], (N_s >> 1) - 1);   // gd_{N_s - 1}
+  if (lane == 0) gz[N_s] += l * last;
+  for (int o = 16; o > 0; o >>= 1) gl += __shfl_xor_sync(0xffffffffu, gl, o);
+  if (lane == 0) g_l[rayg] += gl;
+}
+
 // ------------------------------------------------------------------------------------------------- geometry backward
 // Per ray: (g_m, g_o, g_l, g_z edges) -> contributions to g_R (9) and g_T (3):  d0 = R p, p = Kinv (x,y,1); m = -d0/d0_z, l = -|d0|/d0_z;
 // every depth edge has dz/dT_z = 1 (coarse_depths, jitter is an affine blend with weights summing to 1).
@@ -546,8 +716,12 @@ extern "C" int gnrf_composite_cm_fwd(const float* h, long long h_stride, const f
                                      gnrf_stream_t stream) {
   GNRF_CHECK_ARG(h && sigma_raw && z_edges && ray_dl && Hc && bg_alpha && weights);
   GNRF_CHECK_ARG(B > 0 && N_r > 0 && N_s > 0 && N_s <= 4096 && C > 0);
-  composite_cm_fwd_kernel<<<B * N_r, 256, N_s * sizeof(float), as_stream(stream)>>>(
-      h, h_stride, sigma_raw, s_stride, z_edges, reinterpret_cast<const float4*>(ray_dl), N_r, N_s, C, Hc, bg_alpha, weights);
+  if (N_s <= 64 && N_s % 2 == 0 && h_stride % 2 == 0 && (reinterpret_cast<uintptr_t>(h) & 7) == 0)
+    composite_cm_fwd_warp_kernel<<<ceil_div(B * N_r, 8), 256, 0, as_stream(stream)>>>(
+        h, h_stride, sigma_raw, s_stride, z_edges, reinterpret_cast<const float4*>(ray_dl), B * N_r, N_r, N_s, C, Hc, bg_alpha, weights);
+  else
+    composite_cm_fwd_kernel<<<B * N_r, 256, N_s * sizeof(float), as_stream(stream)>>>(
+        h, h_stride, sigma_raw, s_stride, z_edges, reinterpret_cast<const float4*>(ray_dl), N_r, N_s, C, Hc, bg_alpha, weights);
   GNRF_LAUNCH_CHECK();
   count_launches(1);
   return GNRF_OK;
@@ -560,9 +734,15 @@ extern "C" int gnrf_composite_cm_bwd(const float* g_Hc, const float* g_bg_alpha,
   GNRF_CHECK_ARG(g_Hc && h && sigma_raw && weights && z_edges && ray_dl && g_h && g_sigma && g_z && g_l);
   GNRF_CHECK_ARG(B > 0 && N_r > 0 && N_s > 0 && N_s <= 1024 && C > 0 && C <= 1024);
   const size_t smem = (size_t)(10 * N_s + C + 1) * sizeof(float);
-  composite_cm_bwd_kernel<0><<<B * N_r, 256, smem, as_stream(stream)>>>(g_Hc, g_bg_alpha, h, h_stride, sigma_raw, s_stride, weights, z_edges,
-                                                                       reinterpret_cast<const float4*>(ray_dl), N_r, N_s, C, g_h,
-                                                                       gh_stride, g_sigma, gs_stride, 0, 0, g_z, g_l);
+  if (N_s <= 64 && N_s % 2 == 0 && h_stride % 2 == 0 && gh_stride % 2 == 0 && gs_stride % 2 == 0 &&
+      ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(g_h) | reinterpret_cast<uintptr_t>(g_sigma)) & 7) == 0)
+    composite_cm_bwd_warp_kernel<0><<<ceil_div(B * N_r, 8), 256, 0, as_stream(stream)>>>(
+        g_Hc, g_bg_alpha, h, h_stride, sigma_raw, s_stride, weights, z_edges, reinterpret_cast<const float4*>(ray_dl), B * N_r, N_r, N_s, C,
+        g_h, gh_stride, g_sigma, gs_stride, 0, 0, g_z, g_l);
+  else
+    composite_cm_bwd_kernel<0><<<B * N_r, 256, smem, as_stream(stream)>>>(g_Hc, g_bg_alpha, h, h_stride, sigma_raw, s_stride, weights, z_edges,
+                                                                         reinterpret_cast<const float4*>(ray_dl), N_r, N_s, C, g_h,
+                                                                         gh_stride, g_sigma, gs_stride, 0, 0, g_z, g_l);
   GNRF_LAUNCH_CHECK();
   count_launches(1);
   return GNRF_OK;
@@ -577,7 +757,18 @@ extern "C" int gnrf_composite_cm_bwd_hl(const float* g_Hc, const float* g_bg_alp
   GNRF_CHECK_ARG(B > 0 && N_r > 0 && N_s > 0 && N_s <= 1024 && C > 0 && C <= 1024 && (planes == 1 || planes == 2));
   const size_t smem = (size_t)(10 * N_s + C + 1) * sizeof(float);
   const float4* rd = reinterpret_cast<const float4*>(ray_dl);
-  if (planes == 2)
+  if (N_s <= 64 && N_s % 2 == 0 && h_stride % 2 == 0 && gh_stride % 2 == 0 && gs_stride % 2 == 0 && gh_plane_stride % 2 == 0 &&
+      gs_plane_stride % 2 == 0 &&
+      ((reinterpret_cast<uintptr_t>(h) & 7) | (reinterpret_cast<uintptr_t>(g_h) & 3) | (reinterpret_cast<uintptr_t>(g_sigma) & 3)) == 0) {
+    if (planes == 2)
+      composite_cm_bwd_warp_kernel<2><<<ceil_div(B * N_r, 8), 256, 0, as_stream(stream)>>>(
+          g_Hc, g_bg_alpha, h, h_stride, sigma_raw, s_stride, weights, z_edges, rd, B * N_r, N_r, N_s, C, g_h, gh_stride, g_sigma, gs_stride,
+          gh_plane_stride, gs_plane_stride, g_z, g_l);
+    else
+      composite_cm_bwd_warp_kernel<1><<<ceil_div(B * N_r, 8), 256, 0, as_stream(stream)>>>(
+          g_Hc, g_bg_alpha, h, h_stride, sigma_raw, s_stride, weights, z_edges, rd, B * N_r, N_r, N_s, C, g_h, gh_stride, g_sigma, gs_stride,
+          gh_plane_stride, gs_plane_stride, g_z, g_l);
+  } else if (planes == 2)
     composite_cm_bwd_kernel<2><<<B * N_r, 256, smem, as_stream(stream)>>>(g_Hc, g_bg_alpha, h, h_stride, sigma_raw, s_stride, weights,
                                                                          z_edges, rd, N_r, N_s, C, g_h, gh_stride, g_sigma, gs_stride,
                                                                          gh_plane_stride, gs_plane_stride, g_z, g_l);
