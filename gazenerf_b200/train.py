@@ -33,6 +33,8 @@ from . import _lib
 
 PE = 63
 N_BRANCH_T = 21  # effective tensors per branch, see branch_tensors()
+# net.train_precision -> (planes of the saved activations, planes of the gradient tensors); 0 = fp32 tensors (r1 kernels)
+TRAIN_PRECISIONS = {"bf16x3": (2, 2), "mixed": (2, 1), "bf16": (1, 1), "f32": (0, 0)}
 
 
 def branch_tensors(mlp, shape_ext: torch.Tensor, appea: torch.Tensor) -> List[torch.Tensor]:
@@ -354,7 +356,7 @@ class FeatureMapFn(torch.autograd.Function):
         Tf, Te = T[:N_BRANCH_T], T[N_BRANCH_T:2 * N_BRANCH_T]
         ray_dl = o.empty(B, n_r, 4)
         _lib.check(L.gnrf_ray_setup(xy.data_ptr(), rmats.data_ptr(), kinv.data_ptr(), B, n_r, ray_dl.data_ptr(), o.st), "gnrf_ray_setup")
-        planes, planes_bwd = {"bf16x3": (2, 2), "mixed": (2, 1), "bf16": (1, 1), "f32": (0, 0)}[cfg.get("precision", "bf16x3")]
+        planes, planes_bwd = TRAIN_PRECISIONS[cfg.get("precision", "bf16x3")]
         if planes and not hl_supported(H, n_r * n_s):
             planes = 0
         if planes:
@@ -470,10 +472,13 @@ class NeuralRenderFn(torch.autograd.Function):
 
 def render_featmaps(net, xy, rmats, tvecs, kinv, gaze, shape_ext, appea, z_edges, stages=None) -> torch.Tensor:
     """Differentiable rays -> feature maps [3B+1, C, S, S] (merge_face | eyes_planes | merge | bg_featmap)."""
+    precision = getattr(net, "train_precision", "bf16x3")
+    if precision not in TRAIN_PRECISIONS:
+        raise ValueError("train_precision must be one of %s, got %r" % (sorted(TRAIN_PRECISIONS), precision))
     tf = branch_tensors(net.fg_CD_predictor_face, shape_ext, appea)
     te = branch_tensors(net.fg_CD_predictor_eyes, shape_ext, appea)
     cfg = {"net": net, "H": net.mlp_h_channel, "C": net.featmap_nc, "S": net.featmap_size, "n_s": net.num_sample_coarse, "stages": stages,
-           "precision": getattr(net, "train_precision", "bf16x3")}
+           "precision": precision}
     return FeatureMapFn.apply(cfg, xy, rmats, tvecs, kinv, gaze, z_edges, net.neural_render.bg_featmap, *tf, *te)
 
 

@@ -164,3 +164,18 @@ def test_training_path_effective_tensors_reproduce_the_reference_layers():
     # autograd maps a per-face bias gradient back to codes and weight columns
     (T[1].sum() + T[19].sum()).backward()
     assert mlp.FeaExt_module_0.weight.grad[:, PE:].abs().sum() > 0 and mlp.RGB_layer_1.weight.grad[:, 384:].abs().sum() > 0
+
+
+def test_train_precision_is_validated_before_any_device_work():
+    """net.train_precision (gazenerf_b200/train.py) selects the activation storage of the differentiable path; an unknown mode must
+    fail loudly in Python, not fall through to some default."""
+    import pytest
+    import torch
+    from gazenerf_b200 import train
+
+    class _Net:
+        train_precision = "fp8"
+
+    with pytest.raises(ValueError, match="train_precision"):
+        train.render_featmaps(_Net(), *([None] * 9))
+    assert set(train.TRAIN_PRECISIONS) == {"bf16x3", "mixed", "bf16", "f32"}
