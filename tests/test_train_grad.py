@@ -534,10 +534,12 @@ def test_full_gradients_other_shapes_vs_oracle(dev, B, S, n_s, mode, seed):
 
 
 @gpu
-@pytest.mark.parametrize("precision", ["bf16x3", "f32"])
-def test_train_path_forward_matches_fused_inference_full_size(dev, precision):
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 1e-4), ("mixed", 1e-4), ("f32", 1e-4), ("bf16", 2e-2)])
+def test_train_path_forward_matches_fused_inference_full_size(dev, precision, tol):
     """BASELINE config[1] size (64x64 rays x 64 samples -> 512x512, B = 1): the layer-wise differentiable forward and the fused
-    tcgen05 inference kernel are two independent implementations of the same graph; their images must agree to 1e-4."""
+    tcgen05 inference kernel are two independent implementations of the same graph; their images must agree to 1e-4 in every
+    parity-grade storage mode ("mixed" shares the bf16x3 forward); the single-pass "bf16" throughput mode is held to 2e-2 (abs, images
+    in [0,1]) on this steep-density (x30) network."""
     import gazenerf_b200 as G
     from bench import synthetic_inputs
     opt = G.BaseOptions()
@@ -555,5 +557,5 @@ def test_train_path_forward_matches_fused_inference_full_size(dev, precision):
     out = net("train", **kw, jitter_u=ju)["coarse_dict"]              # differentiable layer-wise path
     assert out["merge_img"].grad_fn is not None and ref["merge_img"].grad_fn is None
     for k in IMG_KEYS:
-        assert float((out[k].detach() - ref[k]).abs().max()) < 1e-4, k
+        assert float((out[k].detach() - ref[k]).abs().max()) < tol, (k, float((out[k].detach() - ref[k]).abs().max()))
     assert float((ref["merge_img"] - ref["bg_img"]).abs().max()) > 0.05   # the head is actually visible
