@@ -71,7 +71,12 @@ def _lin(L, W, bias, x_pl, planes, n_img, HW, act=0, bias_img=None, hl_rows=None
 
 @pytest.mark.parametrize("planes", [2, 1])
 @pytest.mark.parametrize("N,K,HW,n_img,act", [(384, 384, 512, 2, 1), (384, 63, 256, 1, 1), (384, 447, 768, 1, 1), (192, 384, 256, 2, 1),
-                                               (160, 96, 1024, 1, 0)])
+                                               (160, 96, 1024, 1, 0),
+                                               # edges: one tile per image and more images than M-tiles; the smallest K (one stage);
+                                               # K = 33 (second K-block holds ONE valid row, the rest zero-filled by the TMA unit);
+                                               # N = 100 (rows 100..127 of the only M-tile clipped by the tensor store); 5 M-tiles
+                                               (128, 64, 256, 3, 1), (128, 32, 256, 1, 0), (256, 33, 512, 1, 1), (100, 128, 256, 2, 0),
+                                               (600, 64, 256, 1, 1)])
 def test_lin_hl_forward(planes, N, K, HW, n_img, act):
     from gazenerf_b200 import _lib
     L = _lib.lib()
@@ -135,7 +140,10 @@ def test_lin_hl_fp32_rows_and_mask(planes):
 
 @pytest.mark.parametrize("planes", [2, 1])
 @pytest.mark.parametrize("N,K,HW,n_img,db_sum", [(384, 384, 2048, 2, 1), (384, 447, 1024, 1, 0), (384, 63, 512, 2, 0), (192, 384, 1024, 2, 0),
-                                                  (385, 384, 4096, 1, 1)])
+                                                  (385, 384, 4096, 1, 1),
+                                                  # edges: a single 32-point K-block per image (split-K clamps to 1); one X row; 193 rows
+                                                  # (the folded RGB head); three column chunks
+                                                  (128, 128, 32, 2, 0), (128, 1, 256, 1, 1), (193, 384, 512, 2, 0), (128, 800, 256, 1, 1)])
 def test_wgrad_hl(planes, N, K, HW, n_img, db_sum):
     from gazenerf_b200 import _lib
     L = _lib.lib()

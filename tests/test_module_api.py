@@ -128,6 +128,16 @@ def test_abi_argument_checks_fail_cleanly_without_a_gpu():
     assert L.gnrf_conv_tc_packed_bytes(384, 384) > 2 * 384 * 384 * 2 and L.gnrf_conv_tc_packed_bytes(0, 4) == 0
     assert L.gnrf_wgrad_tc_workspace_bytes(384, 384, 2, 262144) >= 128 * 208 * 4
     assert L.gnrf_nr_train_saved_bytes(7, 258, 64, 3, 32) > 0 and L.gnrf_nr_train_bwd_workspace_bytes(7, 258, 64, 3, 32) > 0
+    # plane kernels of the training path (csrc/lin_hl.cu)
+    assert L.gnrf_lin_hl(None, 384, 384, 2, None, 0, 0, None, 1, 0, None, 0, 0, 384, None, 0, None, 0, 0, None, 0, 0, 2, 512, None) == 1
+    assert b"gnrf_lin_hl" in L.gnrf_last_error()
+    assert L.gnrf_lin_hl_pack(None, None, 384, 384, 0, 2, None, None) == 1
+    assert L.gnrf_wgrad_hl(None, 0, 0, None, 0, 0, 2, 384, 384, 2, 512, None, None, 1, None, 0, None) == 1
+    assert L.gnrf_pe_fwd_hl(None, None, None, 1, 64, 8, None, 0, None, 0, 0, 2, None) == 1
+    assert L.gnrf_composite_cm_bwd_hl(None, None, None, 0, None, 0, None, None, None, 1, 64, 8, 192, None, 0, 0, None, 0, 0, 2, None, None, None) == 1
+    assert L.gnrf_lin_hl_packed_bytes(384, 384, 2) >= 2 * 384 * 384 * 2 + 384 * 4 and L.gnrf_lin_hl_packed_bytes(384, 384, 1) < L.gnrf_lin_hl_packed_bytes(384, 384, 2)
+    assert L.gnrf_lin_hl_packed_bytes(384, 384, 3) == 0 and L.gnrf_wgrad_hl_workspace_bytes(384, 384, 2, 262144) >= 128 * 400 * 4
+    assert L.gnrf_compose_bwd_groups(258) == 8 and L.gnrf_compose_bwd_blocks(4096, 258) == 32 * 8
 
 
 def test_training_path_effective_tensors_reproduce_the_reference_layers():
